@@ -1,0 +1,192 @@
+/*
+ * nesie_b200.h -- C ABI of libnesie_b200.so, the B200 (sm_100a) implementation of the
+ * Nesie / VoteNet data-parallel hot path (PointNet++ SA/FP operators, pseudo-label NMS,
+ * side-uncertainty loss, teacher EMA).
+ *
+ * Every entry point replaces one launcher of the reference (OpenSpaceAI/Nesie, a fork of
+ * mmdetection3d 0.15.0); the reference interface it stands in for is cited per function
+ * (paths relative to the reference's mmdet3d/).  The conventions are the reference's:
+ *   - plain device pointers + sizes, contiguous row-major tensors, int32 indices, fp32 data;
+ *   - the CALLER allocates every output (and zero-fills where stated);
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*) and the call returns
+ *     without synchronising;
+ * with one deliberate difference: a failed launch returns a non-zero status (the CUDA error
+ * code, or a NESIE_ERR_* value) and records a message for nesie_last_error() instead of
+ * printing and calling exit(-1) like the reference launchers do
+ * (e.g. ops/ball_query/src/ball_query_cuda.cu:73-77).
+ *
+ * There is no CPU path behind this ABI: without a CUDA device every compute entry point fails.
+ */
+#ifndef NESIE_B200_H_
+#define NESIE_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NESIE_OK 0
+#define NESIE_ERR_INVALID_ARG 10001 /* bad sizes / null pointers / unsupported shape */
+#define NESIE_ERR_UNSUPPORTED 10002 /* shape outside what the kernel family covers */
+
+/* ABI version (bumped on any signature change) and last error text of the calling thread. */
+int nesie_abi_version(void);
+const char *nesie_last_error(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Furthest point sampling.
+ * Replaces furthest_point_sampling_kernel_launcher(b,n,m,dataset,temp,idxs,stream)
+ *   ops/furthest_point_sample/src/furthest_point_sample_cuda.cu:143-209 (kernel :25-141),
+ *   bound by furthest_point_sampling_wrapper, src/furthest_point_sample.cpp:32-43,59-65.
+ * xyz (b,n,3) f32; idx (b,m) i32 out.  temp (b,n) f32 is OPTIONAL: the reference needs it as
+ * scratch pre-filled with 1e10 (furthest_point_sample.py:30); here the running min-distances
+ * live in registers.  temp == NULL means "start from 1e10"; a non-NULL temp is read as the
+ * initial min-distances and receives the final ones, exactly like the reference's buffer.
+ * Bit-exact contract: d = fma(dz,dz,fma(dx,dx,dy*dy)), start index 0, ties resolved the way
+ * the reference's per-thread strided scan + shared-memory tree do.
+ * nesie_fps_needs_temp() returns 1 when (b,n,m) falls back to the global-memory kernel that
+ * requires a caller-provided temp.
+ */
+int nesie_fps(int b, int n, int m, const float *xyz, float *temp, int *idx, void *stream);
+int nesie_fps_needs_temp(int b, int n, int m);
+
+/* Replaces furthest_point_sampling_with_dist_kernel_launcher
+ *   furthest_point_sample_cuda.cu:333-399 (kernel :213-331), wrapper .cpp:45-57,
+ * dist (b,n,n) f32; temp (b,n) f32 REQUIRED, pre-filled with 1e10 by the caller
+ * (furthest_point_sample.py:66); idx (b,m) i32 out. */
+int nesie_fps_with_dist(int b, int n, int m, const float *dist, float *temp, int *idx,
+                        void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Ball query.  Replaces ball_query_kernel_launcher(b,n,m,min_radius,max_radius,nsample,
+ *   new_xyz,xyz,idx,stream)  ops/ball_query/src/ball_query_cuda.cu:56-78 (kernel :11-54),
+ *   bound by ball_query_wrapper, src/ball_query.cpp:30-47.  Note the reference's argument
+ *   order: centres (new_xyz (b,m,3)) before points (xyz (b,n,3)).
+ * idx (b,m,nsample) i32.  Unlike the reference, the kernel writes EVERY slot of idx (rows
+ * without a hit are written as zeros), so the caller's zero-fill (ball_query.py:35) is
+ * allowed but not required.
+ */
+int nesie_ball_query(int b, int n, int m, float min_radius, float max_radius, int nsample,
+                     const float *new_xyz, const float *xyz, int *idx, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * gather_points: out[b,c,j] = points[b,c,idx[b,j]].
+ * Replaces gather_points_kernel_launcher / gather_points_grad_kernel_launcher
+ *   ops/gather_points/src/gather_points_cuda.cu:28-49,72-95 (wrappers gather_points.cpp:28-59).
+ * points (b,c,n), idx (b,npoints) i32, out (b,c,npoints).  grad: grad_out (b,c,npoints) is
+ * scatter-added into grad_points (b,c,n), which the caller zero-fills (gather_points.py:44).
+ */
+int nesie_gather_points(int b, int c, int n, int npoints, const float *points, const int *idx,
+                        float *out, void *stream);
+int nesie_gather_points_grad(int b, int c, int n, int npoints, const float *grad_out,
+                             const int *idx, float *grad_points, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * grouping_operation: out[b,c,j,k] = points[b,c,idx[b,j,k]].
+ * Replaces group_points_kernel_launcher / group_points_grad_kernel_launcher
+ *   ops/group_points/src/group_points_cuda.cu:81-105,33-54 (wrappers group_points.cpp:31-62).
+ * points (b,c,n), idx (b,npoints,nsample) i32, out (b,c,npoints,nsample).  grad_points (b,c,n)
+ * is zero-filled by the caller (group_points.py:219).
+ */
+int nesie_group_points(int b, int c, int n, int npoints, int nsample, const float *points,
+                       const int *idx, float *out, void *stream);
+int nesie_group_points_grad(int b, int c, int n, int npoints, int nsample, const float *grad_out,
+                            const int *idx, float *grad_points, void *stream);
+
+/* QueryAndGroup's whole body after the ball query in ONE pass (ops/group_points/
+ * group_points.py:98-116): out (b, 3+c, npoints, nsample) with channels 0..2 =
+ * (xyz[idx] - center) [/ radius when normalize_xyz] and channels 3.. = features[idx].
+ * xyz (b,n,3), center_xyz (b,npoints,3), features (b,c,n) or NULL with c == 0.
+ * radius: pass max_radius (> 0) when normalize_xyz=True, or 0 to skip the scaling.  The
+ * scaling is x * (1.0f / radius) in fp32, which is what torch's CUDA `grouped_xyz /= radius`
+ * with a python-scalar divisor executes (ATen: "a * reciprocal(b)").
+ */
+int nesie_query_group_concat(int b, int c, int n, int npoints, int nsample, const float *xyz,
+                             const float *center_xyz, const float *features, const int *idx,
+                             float radius, float *out, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * three_nn.  Replaces three_nn_kernel_launcher(b,n,m,unknown,known,dist2,idx,stream)
+ *   ops/interpolate/src/three_nn_cuda.cu:67-90 (kernel :11-65), wrapper interpolate.cpp:46-56.
+ * unknown (b,n,3), known (b,m,3) -> dist2 (b,n,3) f32 SQUARED distances (python applies sqrt,
+ * three_nn.py:38), idx (b,n,3) i32.  Earliest index wins ties; with m < 3 the missing
+ * neighbours are reported as (inf, 0) exactly like the reference's (float)1e40 / 0.
+ */
+int nesie_three_nn(int b, int n, int m, const float *unknown, const float *known, float *dist2,
+                   int *idx, void *stream);
+
+/* three_interpolate: out[b,c,j] = fma(w2,p2,fma(w1,p1,w0*p0)), p_i = points[b,c,idx[b,j,i]].
+ * Replaces three_interpolate_kernel_launcher / three_interpolate_grad_kernel_launcher
+ *   ops/interpolate/src/three_interpolate_cuda.cu:37-59,86-110, wrappers interpolate.cpp:58-93.
+ * points (b,c,m), idx/weight (b,n,3), out (b,c,n).  grad_points (b,c,m) zero-filled by caller.
+ */
+int nesie_three_interpolate(int b, int c, int m, int n, const float *points, const int *idx,
+                            const float *weight, float *out, void *stream);
+int nesie_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out,
+                                 const int *idx, const float *weight, float *grad_points,
+                                 void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Batched class-aware axis-aligned 3D NMS, one scene per CTA.
+ * Replaces the per-scene python loop around aligned_3d_nms(boxes, scores, classes, thresh)
+ *   core/post_processing/box3d_nms.py:129-176, called from
+ *   models/dense_heads/nesie_head.py:715-724,759-762.
+ * boxes (nscenes,max_n,6) f32 [x1,y1,z1,x2,y2,z2]; scores (nscenes,max_n) f32; classes
+ * (nscenes,max_n) i32; counts (nscenes) i32 = valid boxes per scene (<= max_n <= 1024), or
+ * NULL for "all max_n".  keep (nscenes,max_n) i64 receives the picked indices in pick order
+ * (descending score), keep_cnt (nscenes) i32 how many.  IoU arithmetic is fp32 with one
+ * rounding per torch op (no FMA); equal scores are ordered by index (stable ascending sort).
+ */
+int nesie_aligned_3d_nms_batched(int nscenes, int max_n, const float *boxes, const float *scores,
+                                 const int *classes, const int *counts, float thresh,
+                                 long long *keep, int *keep_cnt, void *stream);
+
+/* Nesie's lenient train-time NMS (float64, volume + 1e-8, re-picks the top half of every
+ * suppressed set).  Replaces lhs_3d_faster_samecls(boxes, overlap_threshold, old_type)
+ *   models/detectors/votenet_nesie.py:733-779 and the numpy loop that feeds it (:238-258).
+ * boxes (nscenes,max_n,8) f64 rows [x1,y1,z1,x2,y2,z2,score,cls]; pick (nscenes, 2*max_n) i32
+ * receives the pick list in the reference's order, pick_cnt (nscenes) its length.
+ */
+int nesie_lhs_nms_batched(int nscenes, int max_n, const double *boxes, const int *counts,
+                          double overlap_threshold, int old_type, int *pick, int *pick_cnt,
+                          void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Per-side uncertainty box-regression loss (fused elementwise + reduction).
+ * Replaces models/dense_heads/nesie_head.py:332-349 (SurfaceLoss MSE branch,
+ * models/losses/surface_loss.py:57-61,90-100, with mmdet's weighted MSELoss):
+ *   tgt   = Bbox2Surface(box7);  L = loss_weight * w * (pred - tgt)^2
+ *   s     = side_scores[row, side, argmax_cls(sem_scores[row])]
+ *   sigma = 0.8 s^2 - 1.8 s + 1
+ *   loss  = sum( exp(-sigma) * L + alpha * sigma * w )
+ * surface_pred (rows,6); box_targets (rows,7); side_scores (rows,6,ncls); sem_scores
+ * (rows,ncls); weight (rows,6).  Outputs: loss_out (1) f32 is ACCUMULATED into (caller
+ * zero-fills), sigma_out (rows,6) f32 optional (NULL to skip).
+ * _grad: given the upstream scalar grad (device pointer, 1 element) and, optionally, an
+ * upstream grad for sigma_out (rows,6; NULL if sigma was not used), writes d/d surface_pred
+ * (rows,6) and scatter-writes d/d side_scores (rows,6,ncls; caller zero-fills).
+ */
+int nesie_side_uncertainty_loss(int rows, int ncls, const float *surface_pred,
+                                const float *box_targets, const float *side_scores,
+                                const float *sem_scores, const float *weight, float loss_weight,
+                                float alpha, float *loss_out, float *sigma_out, void *stream);
+int nesie_side_uncertainty_loss_grad(int rows, int ncls, const float *surface_pred,
+                                     const float *box_targets, const float *side_scores,
+                                     const float *sem_scores, const float *weight,
+                                     float loss_weight, float alpha, const float *grad_loss,
+                                     const float *grad_sigma, float *grad_surface_pred,
+                                     float *grad_side_scores, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Teacher EMA over one flat parameter buffer: ema = fma(momentum, param, ema * decay).
+ * Replaces the per-tensor loop SimiTeacherHook.hooks_after_train_iter
+ *   core/utils/simi_teacher_hook.py:54-64 (buffer.mul_(1-m).add_(param, alpha=m));
+ * the caller passes decay = (float)(1 - m) and momentum = (float)m, both rounded from the
+ * python doubles the way torch rounds its scalar arguments.
+ */
+int nesie_ema_update(long long count, float *ema, const float *param, float decay,
+                     float momentum, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NESIE_B200_H_ */

@@ -1,0 +1,82 @@
+"""ctypes binding of libnesie_b200.so (the C ABI declared in include/nesie_b200.h).
+
+The shared library is the product: there is no Python/torch fallback for any op.  If the
+library is missing, or a tensor is not on a CUDA device, the call raises.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnesie_b200.so")
+
+_i, _f, _d, _p, _ll = ctypes.c_int, ctypes.c_float, ctypes.c_double, ctypes.c_void_p, ctypes.c_longlong
+
+# name -> argtypes, exactly the prototypes of include/nesie_b200.h
+SIGNATURES = {
+    "nesie_abi_version": [],
+    "nesie_fps": [_i, _i, _i, _p, _p, _p, _p],
+    "nesie_fps_needs_temp": [_i, _i, _i],
+    "nesie_fps_with_dist": [_i, _i, _i, _p, _p, _p, _p],
+    "nesie_ball_query": [_i, _i, _i, _f, _f, _i, _p, _p, _p, _p],
+    "nesie_gather_points": [_i, _i, _i, _i, _p, _p, _p, _p],
+    "nesie_gather_points_grad": [_i, _i, _i, _i, _p, _p, _p, _p],
+    "nesie_group_points": [_i, _i, _i, _i, _i, _p, _p, _p, _p],
+    "nesie_group_points_grad": [_i, _i, _i, _i, _i, _p, _p, _p, _p],
+    "nesie_query_group_concat": [_i, _i, _i, _i, _i, _p, _p, _p, _p, _f, _p, _p],
+    "nesie_three_nn": [_i, _i, _i, _p, _p, _p, _p, _p],
+    "nesie_three_interpolate": [_i, _i, _i, _i, _p, _p, _p, _p, _p],
+    "nesie_three_interpolate_grad": [_i, _i, _i, _i, _p, _p, _p, _p, _p],
+    "nesie_aligned_3d_nms_batched": [_i, _i, _p, _p, _p, _p, _f, _p, _p, _p],
+    "nesie_lhs_nms_batched": [_i, _i, _p, _p, _d, _i, _p, _p, _p],
+    "nesie_side_uncertainty_loss": [_i, _i, _p, _p, _p, _p, _p, _f, _f, _p, _p, _p],
+    "nesie_side_uncertainty_loss_grad": [_i, _i, _p, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p],
+    "nesie_ema_update": [_ll, _p, _p, _f, _f, _p],
+}
+
+_lib = None
+
+
+def lib():
+    """Load (once) and return the shared library; raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m nesie_b200.build` "
+                "(there is no CPU or torch fallback)")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.argtypes = argtypes
+            fn.restype = _i
+        handle.nesie_last_error.restype = ctypes.c_char_p
+        handle.nesie_last_error.argtypes = []
+        _lib = handle
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().nesie_last_error().decode(errors="replace")
+        raise RuntimeError(f"{what} failed (status {rc}): {msg}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("nesie_b200 ops run on CUDA tensors only (no CPU fallback)")
+
+
+def call(name, *args):
+    check(getattr(lib(), name)(*args), name)

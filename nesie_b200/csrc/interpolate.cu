@@ -1,0 +1,172 @@
+// three_nn / three_interpolate (+ gradient) for the feature-propagation layers, sm_100a.
+//
+// Replaces three_nn_kernel (reference: ops/interpolate/src/three_nn_cuda.cu:11-65) and
+// three_interpolate_kernel / three_interpolate_grad_kernel
+// (reference: ops/interpolate/src/three_interpolate_cuda.cu:11-35,61-84).
+//
+// three_nn: the source set (<= a few thousand points) is staged in shared memory once per CTA
+// with coalesced loads; every thread owns one target and walks the tile with broadcast reads.
+// The strict '<' cascade keeps the earliest source on ties, as the reference does.  The
+// reference holds its running bests in doubles initialised to 1e40; every compared value is an
+// fp32 distance, so fp32 bests initialised to +inf select identically and the stored
+// (float)1e40 is +inf.
+//
+// three_interpolate: the reference puts the channel on gridDim.y and re-reads idx/weight for
+// every channel.  Here a thread owns one target point, loads its 3 indices + 3 weights once
+// and walks a slab of channels; stores are coalesced along n.  The arithmetic keeps the
+// reference's contraction  fma(w2,p2, fma(w1,p1, w0*p0)).
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace nesie {
+namespace {
+
+constexpr int NN_THREADS = 128;
+constexpr int NN_TILE = 1024;  // source points per smem tile (12 KB)
+
+__global__ void __launch_bounds__(NN_THREADS) three_nn_kernel(int n, int m,
+                                                              const float *__restrict__ unknown,
+                                                              const float *__restrict__ known,
+                                                              float *__restrict__ dist2,
+                                                              int *__restrict__ idx) {
+  __shared__ float s_k[NN_TILE * 3];
+  const int b = blockIdx.y;
+  const int pt = blockIdx.x * NN_THREADS + threadIdx.x;
+  unknown += (size_t)b * n * 3;
+  known += (size_t)b * m * 3;
+  const bool ok = pt < n;
+  const float ux = ok ? unknown[pt * 3 + 0] : 0.f;
+  const float uy = ok ? unknown[pt * 3 + 1] : 0.f;
+  const float uz = ok ? unknown[pt * 3 + 2] : 0.f;
+  float best1 = CUDART_INF_F, best2 = CUDART_INF_F, best3 = CUDART_INF_F;
+  int i1 = 0, i2 = 0, i3 = 0;
+  for (int t0 = 0; t0 < m; t0 += NN_TILE) {
+    const int tn = min(NN_TILE, m - t0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < tn * 3; i += NN_THREADS) s_k[i] = __ldg(known + (size_t)t0 * 3 + i);
+    __syncthreads();
+    if (ok) {
+#pragma unroll 4
+      for (int k = 0; k < tn; ++k) {
+        const float d = sqdist_ref(ux, uy, uz, s_k[k * 3 + 0], s_k[k * 3 + 1], s_k[k * 3 + 2]);
+        if (d < best1) {
+          best3 = best2; i3 = i2;
+          best2 = best1; i2 = i1;
+          best1 = d; i1 = t0 + k;
+        } else if (d < best2) {
+          best3 = best2; i3 = i2;
+          best2 = d; i2 = t0 + k;
+        } else if (d < best3) {
+          best3 = d; i3 = t0 + k;
+        }
+      }
+    }
+  }
+  if (ok) {
+    float *od = dist2 + ((size_t)b * n + pt) * 3;
+    int *oi = idx + ((size_t)b * n + pt) * 3;
+    od[0] = best1; od[1] = best2; od[2] = best3;
+    oi[0] = i1; oi[1] = i2; oi[2] = i3;
+  }
+}
+
+constexpr int TI_THREADS = 128;
+
+// grid: (ceil(n/128), channel slabs, b)
+__global__ void __launch_bounds__(TI_THREADS) three_interpolate_kernel(
+    int c, int m, int n, int slab, const float *__restrict__ points,
+    const int *__restrict__ idx, const float *__restrict__ weight, float *__restrict__ out) {
+  const int b = blockIdx.z;
+  const int pt = blockIdx.x * TI_THREADS + threadIdx.x;
+  if (pt >= n) return;
+  const int cbeg = blockIdx.y * slab, cend = min(c, cbeg + slab);
+  const int *id = idx + ((size_t)b * n + pt) * 3;
+  const float *w = weight + ((size_t)b * n + pt) * 3;
+  const int a0 = id[0], a1 = id[1], a2 = id[2];
+  const float w0 = w[0], w1 = w[1], w2 = w[2];
+  points += (size_t)b * c * m;
+  out += (size_t)b * c * n + pt;
+#pragma unroll 4
+  for (int ci = cbeg; ci < cend; ++ci) {
+    const float *row = points + (size_t)ci * m;
+    const float v = __fmaf_rn(w2, __ldg(row + a2),
+                              __fmaf_rn(w1, __ldg(row + a1), __fmul_rn(w0, __ldg(row + a0))));
+    out[(size_t)ci * n] = v;
+  }
+}
+
+__global__ void __launch_bounds__(TI_THREADS) three_interpolate_grad_kernel(
+    int c, int n, int m, int slab, const float *__restrict__ grad_out,
+    const int *__restrict__ idx, const float *__restrict__ weight,
+    float *__restrict__ grad_points) {
+  const int b = blockIdx.z;
+  const int pt = blockIdx.x * TI_THREADS + threadIdx.x;
+  if (pt >= n) return;
+  const int cbeg = blockIdx.y * slab, cend = min(c, cbeg + slab);
+  const int *id = idx + ((size_t)b * n + pt) * 3;
+  const float *w = weight + ((size_t)b * n + pt) * 3;
+  const int a0 = id[0], a1 = id[1], a2 = id[2];
+  const float w0 = w[0], w1 = w[1], w2 = w[2];
+  grad_points += (size_t)b * c * m;
+  grad_out += (size_t)b * c * n + pt;
+  for (int ci = cbeg; ci < cend; ++ci) {
+    float *row = grad_points + (size_t)ci * m;
+    const float g = grad_out[(size_t)ci * n];
+    atomicAdd(row + a0, __fmul_rn(g, w0));
+    atomicAdd(row + a1, __fmul_rn(g, w1));
+    atomicAdd(row + a2, __fmul_rn(g, w2));
+  }
+}
+
+int pick_slab_ti(int c, long long ctas) {
+  int slab = 32;
+  while (slab > 2 && ctas * ceil_div(c, slab) < 4LL * num_sms()) slab >>= 1;
+  return slab;
+}
+
+}  // namespace
+}  // namespace nesie
+
+using namespace nesie;
+
+extern "C" int nesie_three_nn(int b, int n, int m, const float *unknown, const float *known,
+                              float *dist2, int *idx, void *stream) {
+  NESIE_REQUIRE(b >= 0 && n >= 0 && m >= 0, "negative size");
+  NESIE_REQUIRE(unknown && known && dist2 && idx, "null pointer");
+  if (b == 0 || n == 0) return NESIE_OK;
+  NESIE_REQUIRE(b <= 65535, "b > 65535");
+  dim3 grid(ceil_div(n, NN_THREADS), b);
+  three_nn_kernel<<<grid, NN_THREADS, 0, (cudaStream_t)stream>>>(n, m, unknown, known, dist2, idx);
+  return check_launch("nesie_three_nn");
+}
+
+extern "C" int nesie_three_interpolate(int b, int c, int m, int n, const float *points,
+                                       const int *idx, const float *weight, float *out,
+                                       void *stream) {
+  NESIE_REQUIRE(b >= 0 && c >= 0 && n >= 0 && m >= 0, "negative size");
+  NESIE_REQUIRE(points && idx && weight && out, "null pointer");
+  if (b == 0 || c == 0 || n == 0) return NESIE_OK;
+  NESIE_REQUIRE(b <= 65535, "b > 65535");
+  const int gx = ceil_div(n, TI_THREADS);
+  const int slab = pick_slab_ti(c, (long long)gx * b);
+  dim3 grid(gx, ceil_div(c, slab), b);
+  three_interpolate_kernel<<<grid, TI_THREADS, 0, (cudaStream_t)stream>>>(c, m, n, slab, points,
+                                                                          idx, weight, out);
+  return check_launch("nesie_three_interpolate");
+}
+
+extern "C" int nesie_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out,
+                                            const int *idx, const float *weight,
+                                            float *grad_points, void *stream) {
+  NESIE_REQUIRE(b >= 0 && c >= 0 && n >= 0 && m >= 0, "negative size");
+  NESIE_REQUIRE(grad_out && idx && weight && grad_points, "null pointer");
+  if (b == 0 || c == 0 || n == 0) return NESIE_OK;
+  NESIE_REQUIRE(b <= 65535, "b > 65535");
+  const int gx = ceil_div(n, TI_THREADS);
+  const int slab = pick_slab_ti(c, (long long)gx * b);
+  dim3 grid(gx, ceil_div(c, slab), b);
+  three_interpolate_grad_kernel<<<grid, TI_THREADS, 0, (cudaStream_t)stream>>>(
+      c, n, m, slab, grad_out, idx, weight, grad_points);
+  return check_launch("nesie_three_interpolate_grad");
+}

@@ -1,0 +1,62 @@
+"""Mean-teacher EMA of the student parameters.
+
+Mirror of SimiTeacherHook (reference: mmdet3d/core/utils/simi_teacher_hook.py:39-64,86-92):
+  ema <- ema * (1 - m) + m * param,   m = min(momentum, (1 + step) / (warm_up + step))
+and the student<->teacher parameter swap.  The reference walks ~220 tensors with two tiny
+launches each (and 3 copies per tensor per swap, twice per step); here all parameters and all
+EMA copies live in two flat fp32 buffers, so the update is ONE launch (nesie_ema_update) and the
+swap is one 3-way flat copy.  Parameters only: BN running statistics are shared between student
+and teacher, as in the reference.
+"""
+import torch
+
+from . import _lib
+
+
+class TeacherEMA:
+
+    def __init__(self, model, momentum=0.001, interval=1, warm_up=10):
+        assert isinstance(interval, int) and interval > 0
+        assert 0 < momentum < 1
+        self.momentum = momentum ** interval
+        self.interval = interval
+        self.warm_up = warm_up
+        self.params = [p for _, p in model.named_parameters(recurse=True)]
+        self.names = [n for n, _ in model.named_parameters(recurse=True)]
+        total = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        _lib.need_cuda(self.params[0])
+        # re-home every parameter into one flat buffer (views keep the module API unchanged)
+        self.flat_param = torch.empty(total, dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            self.flat_param[off:off + n].copy_(p.data.reshape(-1))
+            p.data = self.flat_param[off:off + n].view_as(p.data)
+            off += n
+        self.flat_ema = self.flat_param.clone()
+
+    def ema_state_dict(self):
+        """EMA copies under the reference's buffer names `ema_<param name with dots -> _>`
+        (simi_teacher_hook.py:47-51)."""
+        out, off = {}, 0
+        for name, p in zip(self.names, self.params):
+            n = p.numel()
+            out[f"ema_{name.replace('.', '_')}"] = self.flat_ema[off:off + n].view_as(p.data)
+            off += n
+        return out
+
+    def after_train_iter(self, curr_step):
+        momentum = min(self.momentum, (1 + curr_step) / (self.warm_up + curr_step))
+        if curr_step % self.interval != 0:
+            return
+        with torch.cuda.device(self.flat_param.device):
+            _lib.call("nesie_ema_update", self.flat_param.numel(), _lib.ptr(self.flat_ema),
+                      _lib.ptr(self.flat_param), float(1 - momentum), float(momentum),
+                      _lib.stream())
+
+    def swap(self):
+        """Swap student and teacher weights in place (switch_to_teacher / switch_to_student)."""
+        tmp = self.flat_param.clone()
+        self.flat_param.copy_(self.flat_ema)
+        self.flat_ema.copy_(tmp)
