@@ -114,7 +114,7 @@ int nesie_query_group_concat(int b, int c, int n, int npoints, int nsample, cons
 int nesie_three_nn(int b, int n, int m, const float *unknown, const float *known, float *dist2,
                    int *idx, void *stream);
 
-/* three_interpolate: out[b,c,j] = fma(w2,p2,fma(w1,p1,w0*p0)), p_i = points[b,c,idx[b,j,i]].
+/* three_interpolate: out[b,c,j] = fma(w2,p2,fma(w0,p0,w1*p1)), p_i = points[b,c,idx[b,j,i]].
  * Replaces three_interpolate_kernel_launcher / three_interpolate_grad_kernel_launcher
  *   ops/interpolate/src/three_interpolate_cuda.cu:37-59,86-110, wrappers interpolate.cpp:58-93.
  * points (b,c,m), idx/weight (b,n,3), out (b,c,n).  grad_points (b,c,m) zero-filled by caller.

@@ -62,6 +62,47 @@ __device__ __forceinline__ int warp_argmax(unsigned &d, unsigned &p) {
   return __ffs(win) - 1;
 }
 
+// ---- cluster exchange primitives (sm_90+ PTX) -------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) {
+  return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ unsigned mapa_u32(unsigned addr, unsigned cta_rank) {
+  unsigned r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned mbar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned mbar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(mbar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// remote 16-byte / 4-byte stores that also signal `bytes` on the destination CTA's mbarrier
+__device__ __forceinline__ void st_async_v4(unsigned raddr, unsigned rmbar, unsigned a,
+                                            unsigned b, unsigned c, unsigned d) {
+  asm volatile(
+      "st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+      ::"r"(raddr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(rmbar)
+      : "memory");
+}
+__device__ __forceinline__ void st_async_b32(unsigned raddr, unsigned rmbar, unsigned a) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+               ::"r"(raddr), "r"(a), "r"(rmbar)
+               : "memory");
+}
+
 __device__ __forceinline__ int decode_key(unsigned p, int bs, int log2bs) {
   if (log2bs == 0) return (int)p;
   const unsigned r = __brev(p) & (unsigned)(bs - 1);
@@ -77,6 +118,7 @@ __device__ __forceinline__ int decode_key(unsigned p, int bs, int log2bs) {
 // ------------------------------------------------------------------------------------------
 template <int CL, int PPT, int MAXT>
 __global__ void __launch_bounds__(MAXT) fps_reg_kernel(int n, int m, int bs, int log2bs, int qp,
+                                                       int xmode,
                                                        const float *__restrict__ xyz,
                                                        float *__restrict__ temp,
                                                        int *__restrict__ idx) {
@@ -96,6 +138,7 @@ __global__ void __launch_bounds__(MAXT) fps_reg_kernel(int n, int m, int bs, int
   extern __shared__ float s_pts[];  // [3][qp][NT]
   __shared__ Cand s_wk[2][32];
   __shared__ Cand s_cl[2][CL];
+  __shared__ __align__(8) unsigned long long s_mbar[2];
 
   float px[PPT], py[PPT], pz[PPT], md[PPT];
 #pragma unroll
@@ -121,7 +164,14 @@ __global__ void __launch_bounds__(MAXT) fps_reg_kernel(int n, int m, int bs, int
   // old = 0 (furthest_point_sample_cuda.cu:46-47)
   float cx = xyz[0], cy = xyz[1], cz = xyz[2];
   if (rank == 0 && tid == 0) idx[0] = 0;
-  if constexpr (CL > 1) cg::this_cluster().sync();  // every CTA of the cluster is resident
+  if constexpr (CL > 1) {
+    if (tid == 0) {
+      mbar_init(smem_u32(&s_mbar[0]), 1);
+      mbar_init(smem_u32(&s_mbar[1]), 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    cg::this_cluster().sync();  // every CTA of the cluster is resident, barriers initialised
+  }
 
   for (int j = 1; j < m; ++j) {
     const int par = j & 1;
@@ -159,14 +209,25 @@ __global__ void __launch_bounds__(MAXT) fps_reg_kernel(int n, int m, int bs, int
         cx = x2; cy = y2; cz = z2;
         if (tid == 0) idx[j] = decode_key(p2, bs, log2bs);
       } else {
-        if (lane < CL) {
-          Cand *dst = cg::this_cluster().map_shared_rank(&s_cl[par][rank], lane);
-          store_cand(dst, d2, p2, x2, y2, z2);
+        if (xmode == 0) {  // plain DSMEM stores, published by the cluster barrier below
+          if (lane < CL) {
+            Cand *dst = cg::this_cluster().map_shared_rank(&s_cl[par][rank], lane);
+            store_cand(dst, d2, p2, x2, y2, z2);
+          }
+        } else {  // st.async: the 20 payload bytes arrive together with their mbarrier signal
+          if (lane == 0) mbar_arrive_expect_tx(smem_u32(&s_mbar[par]), CL * 20u);
+          if (lane < CL) {
+            const unsigned ra = mapa_u32(smem_u32(&s_cl[par][rank]), (unsigned)lane);
+            const unsigned rm = mapa_u32(smem_u32(&s_mbar[par]), (unsigned)lane);
+            st_async_v4(ra, rm, d2, p2, __float_as_uint(x2), __float_as_uint(y2));
+            st_async_b32(ra + 16, rm, __float_as_uint(z2));
+          }
         }
       }
     }
     if constexpr (CL > 1) {
-      cg::this_cluster().sync();
+      if (xmode == 0) cg::this_cluster().sync();
+      else while (!mbar_try_wait(smem_u32(&s_mbar[par]), (unsigned)((j - 1) >> 1) & 1u)) {}
       unsigned d3 = 0u, p3 = 0xffffffffu;
       float x3 = 0.f, y3 = 0.f, z3 = 0.f;
       if (lane < CL) {
@@ -248,7 +309,7 @@ int ref_block_size(int work_size) {
 }
 int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
-typedef void (*fps_fn)(int, int, int, int, int, const float *, float *, int *);
+typedef void (*fps_fn)(int, int, int, int, int, int, const float *, float *, int *);
 
 template <int CL, int MAXT>
 fps_fn pick_ppt(int qp, int *ppt_out) {
@@ -260,9 +321,9 @@ fps_fn pick_ppt(int qp, int *ppt_out) {
 }
 
 int launch_reg(fps_fn fn, int CL, int NT, int b, int n, int m, int bs, int log2bs, int qp,
-               const float *xyz, float *temp, int *idx, cudaStream_t st) {
+               int xmode, const float *xyz, float *temp, int *idx, cudaStream_t st) {
   const size_t smem = (size_t)3 * qp * NT * sizeof(float);
-  if (smem > 48 * 1024)
+  if (smem > 32 * 1024)  // static smem (candidate slots) counts against the 48 KB default too
     NESIE_CUDA(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)smem));
   cudaLaunchConfig_t cfg = {};
@@ -292,7 +353,7 @@ int launch_reg(fps_fn fn, int CL, int NT, int b, int n, int m, int bs, int log2b
       return NESIE_ERR_UNSUPPORTED;  // caller retries with a smaller cluster
     }
   }
-  NESIE_CUDA(cudaLaunchKernelEx(&cfg, fn, n, m, bs, log2bs, qp, xyz, temp, idx));
+  NESIE_CUDA(cudaLaunchKernelEx(&cfg, fn, n, m, bs, log2bs, qp, xmode, xyz, temp, idx));
   return NESIE_OK;
 }
 
@@ -318,8 +379,11 @@ extern "C" int nesie_fps(int b, int n, int m, const float *xyz, float *temp, int
   const int bs = ref_block_size(n), log2bs = ilog2(bs);
   const int Q = ceil_div(n, bs);
 
-  int force_cl = 0;
+  // tuning knobs (measurement only): cluster size, threads per CTA, exchange mechanism
+  int force_cl = 0, force_nt = 0, xmode = 1;
   if (const char *e = getenv("NESIE_FPS_CLUSTER")) force_cl = atoi(e);
+  if (const char *e = getenv("NESIE_FPS_THREADS")) force_nt = atoi(e);
+  if (const char *e = getenv("NESIE_FPS_XMODE")) xmode = atoi(e);
 
   if (n <= reg_capacity(16)) {
     int cl_min = 1;
@@ -333,7 +397,8 @@ extern "C" int nesie_fps(int b, int n, int m, const float *xyz, float *temp, int
     if (force_cl == 1 || force_cl == 4 || force_cl == 8 || force_cl == 16)
       if (force_cl >= cl_min) cl = force_cl;
     for (; cl >= cl_min; cl = (cl == 4 ? 1 : cl / 2)) {
-      const int NT = cl == 1 ? (bs < 32 ? 32 : bs) : 256;
+      int NT = cl == 1 ? (bs < 32 ? 32 : bs) : 256;
+      if (cl > 1 && (force_nt == 64 || force_nt == 128) && cl * force_nt >= bs) NT = force_nt;
       const int parts = cl * NT / bs;
       const int qp = ceil_div(Q, parts);
       int ppt = 0;
@@ -345,7 +410,7 @@ extern "C" int nesie_fps(int b, int n, int m, const float *xyz, float *temp, int
         case 16: fn = pick_ppt<16, 256>(qp, &ppt); break;
       }
       if (!fn) { if (cl == 1) break; continue; }
-      const int rc = launch_reg(fn, cl, NT, b, n, m, bs, log2bs, qp, xyz, temp, idx, st);
+      const int rc = launch_reg(fn, cl, NT, b, n, m, bs, log2bs, qp, xmode, xyz, temp, idx, st);
       if (rc != NESIE_ERR_UNSUPPORTED) return rc;
       if (cl == 1) break;
     }

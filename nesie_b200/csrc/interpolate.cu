@@ -14,7 +14,7 @@
 // three_interpolate: the reference puts the channel on gridDim.y and re-reads idx/weight for
 // every channel.  Here a thread owns one target point, loads its 3 indices + 3 weights once
 // and walks a slab of channels; stores are coalesced along n.  The arithmetic keeps the
-// reference's contraction  fma(w2,p2, fma(w1,p1, w0*p0)).
+// reference's contraction  fma(w2,p2, fma(w0,p0, w1*p1))  (verified in its sm_100a PTX).
 #include <math_constants.h>
 
 #include "common.cuh"
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(TI_THREADS) three_interpolate_kernel(
   for (int ci = cbeg; ci < cend; ++ci) {
     const float *row = points + (size_t)ci * m;
     const float v = __fmaf_rn(w2, __ldg(row + a2),
-                              __fmaf_rn(w1, __ldg(row + a1), __fmul_rn(w0, __ldg(row + a0))));
+                              __fmaf_rn(w0, __ldg(row + a0), __fmul_rn(w1, __ldg(row + a1))));
     out[(size_t)ci * n] = v;
   }
 }

@@ -107,14 +107,20 @@ def grouping_operation_grad(grad_out, indices, N):
     return g
 
 
-def three_nn(target, source):
-    """Returns (sqrt(dist2), idx) like the reference's python wrapper (three_nn.py:38)."""
+def three_nn_dist2(target, source):
+    """Raw kernel outputs: (squared distances, idx)."""
     target, source = _f32(target), _f32(source)
     B, n, _ = target.shape
     m = source.shape[1]
     dist2 = torch.empty((B, n, 3), dtype=torch.float32)
     idx = torch.empty((B, n, 3), dtype=torch.int32)
     lib().nesie_oracle_three_nn(B, n, m, _p(target), _p(source), _p(dist2), _p(idx))
+    return dist2, idx
+
+
+def three_nn(target, source):
+    """Returns (sqrt(dist2), idx) like the reference's python wrapper (three_nn.py:38)."""
+    dist2, idx = three_nn_dist2(target, source)
     return torch.sqrt(dist2), idx
 
 

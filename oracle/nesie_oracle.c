@@ -5,7 +5,7 @@
  * kernels, one loop iteration per reference CUDA thread, with the same fp32 contraction
  * nvcc emits for them under its default -fmad=true (verified in PTX for sm_100a):
  *     d = fmaf(dz, dz, fmaf(dx, dx, dy * dy))
- *     o = fmaf(w2, p2, fmaf(w1, p1, w0 * p0))
+ *     o = fmaf(w2, p2, fmaf(w0, p0, w1 * p1))
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
  * may load this library.  Parity status: pinned on the GPU box against the reference's own
  * kernels compiled unmodified (oracle/_ref, see oracle/build_ref.sh) and, on CPU, against the
@@ -246,7 +246,7 @@ void nesie_oracle_three_interpolate(int b, int c, int m, int n, const float *poi
       float *dst = out + ((size_t)bi * c + ci) * n;
       for (int j = 0; j < n; ++j)
         dst[j] = fmaf(w[j * 3 + 2], src[id[j * 3 + 2]],
-                      fmaf(w[j * 3 + 1], src[id[j * 3 + 1]], w[j * 3 + 0] * src[id[j * 3 + 0]]));
+                      fmaf(w[j * 3 + 0], src[id[j * 3 + 0]], w[j * 3 + 1] * src[id[j * 3 + 1]]));
     }
 }
 

@@ -105,12 +105,17 @@ def grouping_operation_grad(grad_out, indices, N):
     return g
 
 
-def three_nn(target, source):
+def three_nn_dist2(target, source):
     B, n, _ = target.shape
     m = source.shape[1]
     dist2 = torch.empty((B, n, 3), dtype=torch.float32, device=target.device)
     idx = torch.empty((B, n, 3), dtype=torch.int32, device=target.device)
     _fn("three_nn")(B, n, m, _p(target), _p(source), _p(dist2), _p(idx), _s())
+    return dist2, idx
+
+
+def three_nn(target, source):
+    dist2, idx = three_nn_dist2(target, source)
     return torch.sqrt(dist2), idx
 
 

@@ -49,7 +49,7 @@ def main(out_path):
         bq = ref_cuda.ball_query(r0, r1, K, xg, centres)
         grouped = ref_cuda.grouping_operation(fg, bq)
         gathered = ref_cuda.gather_points(fg, idx)
-        dist, i3 = ref_cuda.three_nn(xg, centres)
+        dist, i3 = ref_cuda.three_nn_dist2(xg, centres)
         interp = ref_cuda.three_interpolate(gathered, i3, wg)
         torch.cuda.synchronize()
         out.update({f"c{i}_xyz": xyz.numpy(), f"c{i}_m": np.int64(M), f"c{i}_nsample": np.int64(K),
@@ -57,7 +57,7 @@ def main(out_path):
                     f"c{i}_feats": feats.numpy(), f"c{i}_weight": w.numpy(),
                     f"c{i}_fps": idx.cpu().numpy(), f"c{i}_bq": bq.cpu().numpy(),
                     f"c{i}_grouped": grouped.cpu().numpy(), f"c{i}_gathered": gathered.cpu().numpy(),
-                    f"c{i}_nn_dist": dist.cpu().numpy(), f"c{i}_nn_idx": i3.cpu().numpy(),
+                    f"c{i}_nn_dist2": dist.cpu().numpy(), f"c{i}_nn_idx": i3.cpu().numpy(),
                     f"c{i}_interp": interp.cpu().numpy()})
     pts = torch.from_numpy(rng.standard_normal((1, 300, 6)).astype(np.float32))
     d = ((pts[:, :, None, :] - pts[:, None, :, :]) ** 2).sum(-1).contiguous()

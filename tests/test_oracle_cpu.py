@@ -61,9 +61,9 @@ def test_c_oracle_matches_reference_kernels(golden_ref):
         assert torch.equal(grouped, torch.from_numpy(g[f"c{i}_grouped"])), f"group case {i}"
         gathered = cpu.gather_points(feats, idx)
         assert torch.equal(gathered, torch.from_numpy(g[f"c{i}_gathered"])), f"gather case {i}"
-        dist, i3 = cpu.three_nn(xyz, centres)
+        dist2, i3 = cpu.three_nn_dist2(xyz, centres)
         assert torch.equal(i3, torch.from_numpy(g[f"c{i}_nn_idx"])), f"three_nn idx case {i}"
-        assert torch.equal(dist, torch.from_numpy(g[f"c{i}_nn_dist"])), f"three_nn dist case {i}"
+        assert torch.equal(dist2, torch.from_numpy(g[f"c{i}_nn_dist2"])), f"three_nn dist case {i}"
         w = torch.from_numpy(g[f"c{i}_weight"])
         interp = cpu.three_interpolate(gathered, i3, w)
         assert torch.equal(interp, torch.from_numpy(g[f"c{i}_interp"])), f"interpolate case {i}"
