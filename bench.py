@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""bench.py -- Nesie-VoteNet train scenes/s on synthetic 40k-point ScanNet-shaped scenes.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One step = forward + backward + AdamW update of the VoteNet harness (nesie_b200/votenet.py:
+PointNet2SASSG backbone, vote module, vote-aggregation SA, prediction head, losses incl. the
+side-uncertainty loss) on 8 scenes per GPU; scenes shard across ranks (DDP, one NCCL gradient
+all-reduce per step) -> weak scaling.  Prints ONE JSON line (rank 0).
+
+  value  : scenes/s with the batch already resident in HBM (CUDA events, max over ranks)
+  e2e    : scenes/s through the same public API with the batch in pinned host memory: every step
+           copies its inputs host->device and reads the loss back
+  roofline: the dominant hand-written kernel (FPS 40000->2048), timed live with CUDA events
+  cpu_baseline: the same step on the host cores with the oracle port of the reference kernels
+           (the reference has no CPU path of its own), bounded to 1 scene per step
+`--impl reference` times that CPU port alone (all host threads).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SCENES_PER_GPU = 8
+N_POINTS = 40000
+WORKLOAD = "votenet_pretrain_fwd_bwd_adamw_b8_per_gpu_40kpts_18cls"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return json.load(open(path)), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (profiling recipe's line)."""
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        clocks, reasons, mx = [], set(), None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                clocks.append(float(r[0]))
+                mx = float(r[1])
+            except (ValueError, IndexError):
+                continue
+            for nm, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        clocks.sort()
+        return {"sm_mhz": clocks[len(clocks) // 2] if clocks else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(clocks)}
+
+
+def cpu_reference_step_rate(steps, warmup, scenes=SCENES_PER_GPU):
+    """The oracle port of the step on the host cores (fwd + bwd + AdamW), `scenes` per step."""
+    from nesie_b200.synthetic import make_batch
+    from oracle.votenet_ref import VoteNetOracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    torch.manual_seed(0)
+    model = VoteNetOracle()
+    opt = torch.optim.AdamW(model.parameters(), lr=0.008, weight_decay=0.01)
+    pts, gb, gl = make_batch(scenes, N_POINTS, seed0=9000)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        loss, _ = model.train_step_loss(pts, gb, gl)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 10.0)
+        opt.step()
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    times.sort()
+    sec = times[len(times) // 2]
+    return scenes / sec, sec, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = min(args.steps, 2), min(args.warmup, 1)
+    rate, sec, cores = cpu_reference_step_rate(steps, warmup)
+    sample = (f"{SCENES_PER_GPU} scenes/step ({N_POINTS} pts each), fwd+bwd+AdamW, "
+              f"median of {steps} after {warmup} warm-up")
+    line = {"impl": "reference", "metric": "train_scenes_per_s", "value": rate, "unit": "scenes/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": WORKLOAD, "scenes_per_step": SCENES_PER_GPU},
+            "cpu_baseline": {"value": rate, "unit": "scenes/s", "cores": cores, "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": rate, "unit": "scenes/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0},
+            "note": "the reference has no CPU implementation of these ops; this is the oracle "
+                    "port (C/OpenMP restatement of its CUDA kernels + torch-CPU MLPs)"}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="nesie_b200", choices=["nesie_b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    import nesie_b200 as nb
+    from nesie_b200 import _lib
+    from nesie_b200.synthetic import make_batch
+    from nesie_b200.votenet import VoteNetHarness
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    W, K = max(args.warmup, 3), args.steps
+
+    torch.manual_seed(0)
+    model = VoteNetHarness().to(dev)
+    net = model
+    if world > 1:
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local],
+                                                        broadcast_buffers=False)
+    opt = torch.optim.AdamW(model.parameters(), lr=0.008, weight_decay=0.01, fused=True)
+
+    # a pool of distinct batches (so no step re-reads the previous step's inputs from L2)
+    NB = 4
+    host = [make_batch(SCENES_PER_GPU, N_POINTS, seed0=1000 * rank + 100 * i) for i in range(NB)]
+    host_pts = [h[0].pin_memory() for h in host]
+    gts = [([b.to(dev) for b in h[1]], [l.to(dev) for l in h[2]]) for h in host]
+    dev_pts = [p.to(dev) for p in host_pts]
+
+    class Step(torch.nn.Module):  # DDP wraps forward(); loss is computed inside it
+        def __init__(self, m):
+            super().__init__()
+            self.m = m
+
+        def forward(self, pts, gb, gl):
+            return self.m.train_step_loss(pts, gb, gl)[0]
+
+    step_mod = Step(model)
+    if world > 1:
+        step_mod = torch.nn.parallel.DistributedDataParallel(step_mod, device_ids=[local],
+                                                             broadcast_buffers=False)
+
+    def one_step(pts, gt):
+        opt.zero_grad(set_to_none=True)
+        loss = step_mod(pts, gt[0], gt[1])
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 10.0)
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, nsteps):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(nsteps):
+            fn(i)
+        b.record()
+        barrier()
+        ms = a.elapsed_time(b)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    # ---- device-resident throughput -----------------------------------------------------------
+    for i in range(W):
+        one_step(dev_pts[i % NB], gts[i % NB])
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.LAUNCHES
+    ms = timed(lambda i: one_step(dev_pts[i % NB], gts[i % NB]), K)
+    launches = _lib.LAUNCHES - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * SCENES_PER_GPU * K / (ms / 1e3)
+
+    # ---- end to end: pinned host -> device every step, loss read back every step ---------------
+    stage = torch.empty_like(dev_pts[0])
+    sink = torch.zeros(1).pin_memory()
+
+    def e2e_step(i):
+        stage.copy_(host_pts[i % NB], non_blocking=True)
+        loss = one_step(stage, gts[i % NB])
+        sink.copy_(loss.detach().reshape(1), non_blocking=False)
+
+    e2e_step(0)
+    ms_e2e = timed(e2e_step, K)
+    e2e_value = world * SCENES_PER_GPU * K / (ms_e2e / 1e3)
+    h2d = host_pts[0].numel() * 4
+    final_loss = float(sink[0])
+
+    # ---- dominant hand-written kernel, timed live ---------------------------------------------
+    xyz = dev_pts[0][..., :3].contiguous()
+    for _ in range(3):
+        nb.furthest_point_sample(xyz, 2048)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(max(K, 10)):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        nb.furthest_point_sample(xyz, 2048)
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    fps_ms = sum(ts) / len(ts)
+    pk, pk_kind = peaks()
+    alg_bytes = SCENES_PER_GPU * (12 * N_POINTS + 4 * 2048)  # B*(12N + 4M)
+    achieved = alg_bytes / (fps_ms * 1e-3) / 1e9
+    roofline = {"kernel": "fps_reg_kernel (FPS 40000->2048, batch 8)", "bound": "hbm",
+                "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk_kind,
+                "kernel_ms": fps_ms,
+                "point_updates_per_s": SCENES_PER_GPU * 2047 * N_POINTS / (fps_ms * 1e-3),
+                "note": "FPS is a chain of 2047 dependent argmax steps: latency/issue-bound, not "
+                        "HBM-bound (3.9 MB of algorithmic bytes); the HBM fraction is reported "
+                        "because the contract asks for it, the per-op table is in profiles/"}
+
+    line = {"metric": "train_scenes_per_s", "value": value, "unit": "scenes/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "scenes_per_gpu": SCENES_PER_GPU, "points": N_POINTS,
+                       "classes": 18, "parallelism": f"dp{world}",
+                       "l2": "4 distinct resident batches cycled; per-step activations exceed L2"},
+            "e2e": {"value": e2e_value, "unit": "scenes/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / K},
+            "gpu_launches": launches, "roofline": roofline, "clocks": clocks,
+            "final_loss": final_loss}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, sec, cores = cpu_reference_step_rate(1, 1)
+        line["cpu_baseline"] = {"value": rate, "unit": "scenes/s", "cores": cores, "kind": "port",
+                                "sample": f"{SCENES_PER_GPU} scenes/step ({N_POINTS} pts each), fwd+bwd+"
+                                          f"AdamW, 1 step after 1 warm-up ({sec:.2f} s/step)"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

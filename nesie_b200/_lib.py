@@ -78,5 +78,10 @@ def need_cuda(*tensors):
             raise RuntimeError("nesie_b200 ops run on CUDA tensors only (no CPU fallback)")
 
 
+LAUNCHES = 0  # kernels launched through the C ABI by this process (every entry point = 1 launch)
+
+
 def call(name, *args):
+    global LAUNCHES
+    LAUNCHES += 1
     check(getattr(lib(), name)(*args), name)

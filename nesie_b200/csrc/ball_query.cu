@@ -24,7 +24,7 @@ constexpr int BQ_WARPS = BQ_THREADS / 32;
 constexpr int BQ_TILE = 2048;  // points staged per step (24 KB)
 
 template <int C>
-__global__ void __launch_bounds__(BQ_THREADS) ball_query_kernel(
+__global__ void __launch_bounds__(BQ_THREADS, 4) ball_query_kernel(
     int n, int m, float min_r2, float max_r2, int nsample, const float *__restrict__ new_xyz,
     const float *__restrict__ xyz, int *__restrict__ idx) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -81,23 +81,31 @@ __global__ void __launch_bounds__(BQ_THREADS) ball_query_kernel(
         const float x = in ? s_xyz[kl * 3 + 0] : 0.f;
         const float y = in ? s_xyz[kl * 3 + 1] : 0.f;
         const float z = in ? s_xyz[kl * 3 + 2] : 0.f;
-        bool open = false;
+        bool hit[C];
+        bool any = false;
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-          if (cnt[c] < nsample) {  // warp-uniform
-            const float d2 = sqdist_ref(cx[c], cy[c], cz[c], x, y, z);
-            const bool hit = in && (d2 == 0.f || (d2 >= min_r2 && d2 < max_r2));
-            const unsigned b = __ballot_sync(0xffffffffu, hit);
-            if (b) {
+          const float d2 = sqdist_ref(cx[c], cy[c], cz[c], x, y, z);
+          hit[c] = in && (d2 == 0.f || (d2 >= min_r2 && d2 < max_r2));
+          any |= hit[c];
+        }
+        // a ball holds a few dozen of the n points: most 32-point steps have no hit at all, so
+        // one vote per step (not one per centre) is the common path
+        if (__any_sync(0xffffffffu, any)) {
+          bool open = false;
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            const unsigned b = __ballot_sync(0xffffffffu, hit[c]);
+            if (b && cnt[c] < nsample) {
               const int pos = cnt[c] + __popc(b & lt_mask);
-              if (hit && pos < nsample) hits[c * nsample + pos] = t0 + kl;
+              if (hit[c] && pos < nsample) hits[c * nsample + pos] = t0 + kl;
               if (cnt[c] == 0) first[c] = t0 + k0 + __ffs(b) - 1;
               cnt[c] += __popc(b);
             }
             open |= cnt[c] < nsample;
           }
+          if (!open) break;  // every centre of this warp is full
         }
-        if (!open) break;
       }
     }
   }

@@ -1,5 +1,5 @@
-"""Times nesie_fps at the BASELINE shape under the tuning knobs (cluster size, threads per CTA,
-exchange mechanism) and checks every variant against the default's indices."""
+"""Times nesie_fps under the tuning knobs (cluster size, threads per CTA) and checks every
+variant against the default's indices.  python tools/fps_variants.py [B] [N] [M]"""
 import itertools
 import json
 import os
@@ -31,22 +31,24 @@ def main():
     N = int(sys.argv[2]) if len(sys.argv) > 2 else 40000
     M = int(sys.argv[3]) if len(sys.argv) > 3 else 2048
     xyz = make_batch(B, N, seed0=0)[0][..., :3].contiguous().cuda()
-    for k in ("NESIE_FPS_CLUSTER", "NESIE_FPS_THREADS", "NESIE_FPS_XMODE"):
+    for k in ("NESIE_FPS_CLUSTER", "NESIE_FPS_THREADS"):
         os.environ.pop(k, None)
     base = nb.furthest_point_sample(xyz, M)
-    for cl, nt, xm in itertools.product([4, 8, 16], [128, 256], [0, 1]):
+    ms = timeit(lambda: nb.furthest_point_sample(xyz, M))
+    print(json.dumps({"B": B, "N": N, "M": M, "variant": "default", "ms": round(ms, 4),
+                      "us_per_iter": round(ms * 1000 / (M - 1), 3)}), flush=True)
+    for cl, nt in itertools.product([1, 2, 4, 8, 16], [32, 64, 128, 256]):
         os.environ["NESIE_FPS_CLUSTER"] = str(cl)
         os.environ["NESIE_FPS_THREADS"] = str(nt)
-        os.environ["NESIE_FPS_XMODE"] = str(xm)
         try:
             got = nb.furthest_point_sample(xyz, M)
             ok = bool(torch.equal(got, base))
             ms = timeit(lambda: nb.furthest_point_sample(xyz, M))
-            print(json.dumps({"B": B, "N": N, "M": M, "cluster": cl, "threads": nt, "xmode": xm,
+            print(json.dumps({"B": B, "N": N, "M": M, "cluster": cl, "threads": nt,
                               "ms": round(ms, 4), "us_per_iter": round(ms * 1000 / (M - 1), 3),
                               "same_as_default": ok}), flush=True)
         except RuntimeError as e:
-            print(json.dumps({"cluster": cl, "threads": nt, "xmode": xm, "error": str(e)[:120]}))
+            print(json.dumps({"cluster": cl, "threads": nt, "error": str(e)[-90:]}))
 
 
 if __name__ == "__main__":
