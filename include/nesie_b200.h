@@ -186,6 +186,31 @@ int nesie_side_uncertainty_loss_grad(int rows, int ncls, const float *surface_pr
 int nesie_ema_update(long long count, float *ema, const float *param, float decay,
                      float momentum, void *stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Fused set-abstraction forward for inference / folded BatchNorm (eval mode):
+ *   grouped gather -> (xyz - centre) * (1/radius) -> 3 x (1x1 conv + folded BN + ReLU) -> max
+ *   over the nsample axis, on tcgen05 tensor cores with TMEM accumulators (bf16 operands, fp32
+ *   accumulate).  Replaces the chain QueryAndGroup.forward (ops/group_points/group_points.py:
+ *   98-116) -> mlps[i] (ops/pointnet_modules/point_sa_module.py:272-289) -> _pool_features
+ *   (:136-158) for `normalize_xyz`/`use_xyz` max-pool SA modules with three MLP layers.
+ * features_pm_bf16: (b, n, c8) bf16 point-major table, c8 = c_in rounded up to 8 (0 -> 8), built
+ *   by nesie_pack_features_bf16 from the reference's (b, c_in, n) fp32 layout.
+ * idx (b, npoints, nsample) i32 from nesie_ball_query; npoints*nsample % 128 == 0.
+ * w{1,2,3}_img: weights pre-packed as byte images of the UMMA K-major SWIZZLE_128B shared-memory
+ *   layout, [K/64 slabs][C_out rows][128 B], 16-byte chunk c of row r stored at chunk c ^ (r & 7);
+ *   layer-1 columns ordered [features (c8) | xyz (3) | zero pad to a multiple of 16].
+ * scale_shift: fp32 [scale1 c1][shift1 c1][scale2 c2][shift2 c2][scale3 c3][shift3 c3].
+ * out (b, c3, npoints) fp32.  nesie_sa_fused_supported() says whether a layer shape is covered.
+ */
+int nesie_sa_fused_supported(int nsample, int c_in, int c1, int c2, int c3);
+int nesie_pack_features_bf16(int b, int c, int n, const float *features, void *table,
+                             void *stream);
+int nesie_sa_fused_forward(int b, int n, int npoints, int nsample, int c_in, int c1, int c2,
+                           int c3, const float *xyz, const float *center_xyz,
+                           const void *features_pm_bf16, const int *idx, float radius,
+                           const void *w1_img, const void *w2_img, const void *w3_img,
+                           const float *scale_shift, float *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

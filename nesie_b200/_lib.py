@@ -33,6 +33,9 @@ SIGNATURES = {
     "nesie_side_uncertainty_loss": [_i, _i, _p, _p, _p, _p, _p, _f, _f, _p, _p, _p],
     "nesie_side_uncertainty_loss_grad": [_i, _i, _p, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p],
     "nesie_ema_update": [_ll, _p, _p, _f, _f, _p],
+    "nesie_sa_fused_supported": [_i, _i, _i, _i, _i],
+    "nesie_pack_features_bf16": [_i, _i, _i, _p, _p, _p],
+    "nesie_sa_fused_forward": [_i] * 8 + [_p, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p],
 }
 
 _lib = None

@@ -1,0 +1,434 @@
+// Fused set-abstraction forward on 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
+//
+// Replaces, for inference / folded BatchNorm (eval mode), the reference chain
+//   QueryAndGroup.forward   ops/group_points/group_points.py:98-116   (gather xyz, subtract centre,
+//                                                                     /radius, gather feats, concat)
+//   mlps[i]                 ops/pointnet_modules/point_sa_module.py:272-289  (3 x Conv2d 1x1 + BN + ReLU)
+//   _pool_features          ops/pointnet_modules/point_sa_module.py:136-158  (max over nsample)
+// which launches ~20 kernels and round-trips the (B, C, M, K) grouped tensor and every activation
+// through HBM (137 MB per tensor at SA2, batch 8).  Here nothing but indices, the bf16 point table
+// and the (B, C3, M) result touches global memory.
+//
+// One CTA processes 128 grouped rows (= 128/nsample whole groups) at a time:
+//   gather   : 256 threads copy the rows' bf16 features (16-byte chunks) + the normalised xyz offset
+//              into shared memory in the UMMA K-major SWIZZLE_128B operand layout
+//   layer 1/2: tcgen05.mma  D[128 rows x C_out] (TMEM, fp32) = A[rows x K] * W^T, issued by one
+//              thread; epilogue = tcgen05.ld -> scale/shift (folded BN) -> ReLU -> bf16 -> written
+//              straight back to shared memory as the next layer's A operand
+//   layer 3  : computed TRANSPOSED, D3^T[C3 channels x 128 rows] = W3 * A2^T, so that a TMEM lane is
+//              a channel and the nsample rows of a group are consecutive TMEM columns: the max-pool
+//              is a register max over a tcgen05.ld, no shuffles, and scale/shift are per-thread
+// Operands are bf16 with fp32 accumulation (the north star's "bf16 MLP within 1e-2" mode).
+// Weights arrive pre-packed (nesie_b200/sa_fused.py) as byte images of their swizzled shared-memory
+// layout, so loading them is a linear copy.  W2 (and W1/W3 when everything fits in 227 KB) stay
+// resident across the CTA's tiles; otherwise W1 and W3 share one region and are re-read from L2.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace nesie {
+namespace {
+
+constexpr int TILE_ROWS = 128;
+constexpr int SLAB_BYTES = TILE_ROWS * 128;  // one 64-channel K-block of a 128-row operand
+constexpr int THREADS = 256;
+
+struct SaParams {
+  int b, n, m, nsample;
+  int cfeat8;             // feature channels rounded up to 8 (chunk granularity of the bf16 table)
+  int k0pad;              // layer-1 K, multiple of 16: cfeat8 + 3 -> padded
+  int c1, c2, c3;
+  int w_shared;           // 1: W1 and W3 share one smem region and are reloaded per tile
+  int tmem_cols;          // 256 or 512
+  float inv_radius;       // 0 = no normalisation
+  const float *xyz;       // (b, n, 3)
+  const float *center;    // (b, m, 3)
+  const __nv_bfloat16 *table;  // (b, n, cfeat8) point-major bf16 features
+  const int *idx;         // (b, m, nsample)
+  const uint4 *w1, *w2, *w3;   // swizzled smem images
+  const float *scale_shift;    // [scale1 c1][shift1 c1][scale2 c2][shift2 c2][scale3 c3][shift3 c3]
+  float *out;             // (b, c3, m)
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) {
+  return (unsigned)__cvta_generic_to_shared(p);
+}
+
+// 64-bit UMMA shared-memory descriptor: K-major, SWIZZLE_128B, 8-row atoms 1024 B apart
+// (cute::UMMA::SmemDescriptor: start>>4 | LBO(=1)<<16 | SBO(=64)<<32 | version(=1)<<46 | layout(=2)<<61)
+__device__ __forceinline__ unsigned long long umma_desc(unsigned smem_addr) {
+  return (unsigned long long)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) |
+         (1ull << 46) | (2ull << 61);
+}
+// 32-bit instruction descriptor, kind::f16: D=f32, A=B=bf16, both K-major, M x N
+__host__ __device__ constexpr unsigned umma_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(N >> 3) << 17) | ((unsigned)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(unsigned d_tmem, unsigned long long a, unsigned long long b,
+                                          unsigned idesc, unsigned accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(unsigned mbar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
+  unsigned ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(mbar), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tmem_ld16(unsigned taddr, float (&v)[16]) {
+  unsigned r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void fence_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ unsigned pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<unsigned *>(&h);
+}
+
+// byte offset of 16-byte chunk `chunk` (global chunk index along K) of row `row` inside an operand
+// stored as [K-block slabs][rows][128 B] with the 128-byte swizzle
+__device__ __forceinline__ unsigned operand_off(int row, int chunk, int rows_per_slab) {
+  return (unsigned)((chunk >> 3) * rows_per_slab * 128 + row * 128 + (((chunk & 7) ^ (row & 7)) << 4));
+}
+
+__device__ __forceinline__ void copy_image(unsigned char *dst, const uint4 *src, int bytes, int tid) {
+  uint4 *d = reinterpret_cast<uint4 *>(dst);
+  for (int i = tid; i < (bytes >> 4); i += THREADS) d[i] = __ldg(src + i);
+}
+
+// One linear layer on the tensor core: D[128 x N] (+)= A[128 x K] * B[N x K]^T, K = ksteps * 16.
+__device__ __forceinline__ void issue_layer(unsigned d_tmem, unsigned a_base, int a_rows,
+                                            unsigned b_base, int b_rows, int ksteps, unsigned idesc) {
+  for (int ks = 0; ks < ksteps; ++ks) {
+    const unsigned a = a_base + (unsigned)(ks >> 2) * (unsigned)(a_rows * 128) + (unsigned)(ks & 3) * 32u;
+    const unsigned b = b_base + (unsigned)(ks >> 2) * (unsigned)(b_rows * 128) + (unsigned)(ks & 3) * 32u;
+    umma_bf16(d_tmem, umma_desc(a), umma_desc(b), idesc, ks > 0 ? 1u : 0u);
+  }
+}
+
+__global__ void __launch_bounds__(THREADS, 1) sa_fused_kernel(SaParams p) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char *smem = reinterpret_cast<unsigned char *>(
+      (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) unsigned long long s_mbar;
+  __shared__ unsigned s_tmem;
+  __shared__ int s_idx[TILE_ROWS];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nslab0 = (p.k0pad + 63) >> 6;
+  const int nslab1 = p.c1 >> 6, nslab2 = p.c2 >> 6;
+  // regions (all 1024-byte aligned): R0 = A0 / A1, R1 = A2, then weights
+  unsigned char *r0 = smem;
+  unsigned char *r1 = r0 + (size_t)max(nslab0, nslab1) * SLAB_BYTES;
+  unsigned char *rw2 = r1 + (size_t)nslab2 * SLAB_BYTES;
+  unsigned char *rw1 = rw2 + (size_t)nslab1 * p.c2 * 128;
+  const int w1_bytes = nslab0 * p.c1 * 128, w3_bytes = nslab2 * p.c3 * 128;
+  unsigned char *rw3 = p.w_shared ? rw1 : rw1 + w1_bytes;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&s_tmem)),
+                 "r"((unsigned)p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    mbar_init(smem_u32(&s_mbar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  copy_image(rw2, p.w2, nslab1 * p.c2 * 128, tid);
+  if (!p.w_shared) {
+    copy_image(rw1, p.w1, w1_bytes, tid);
+    copy_image(rw3, p.w3, w3_bytes, tid);
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const unsigned tmem = s_tmem;
+  const unsigned d1 = tmem, d2 = tmem + (unsigned)p.c1, d3 = tmem + (unsigned)(p.c1 + p.c2);
+  const unsigned mbar = smem_u32(&s_mbar);
+  unsigned phase = 0;
+
+  const float *sc1 = p.scale_shift, *sh1 = sc1 + p.c1;
+  const float *sc2 = sh1 + p.c1, *sh2 = sc2 + p.c2;
+  const float *sc3 = sh2 + p.c2, *sh3 = sc3 + p.c3;
+
+  const int rows_per_scene = p.m * p.nsample;
+  const int tiles_per_scene = rows_per_scene / TILE_ROWS;
+  const int ntiles = p.b * tiles_per_scene;
+  const int nchunk = (p.cfeat8 >> 3) + 1;  // feature chunks + the xyz chunk
+  const int q = warp & 3, half = warp >> 2;
+  const int row = q * 32 + lane;           // this thread's TMEM lane in the epilogues
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int bi = tile / tiles_per_scene;
+    const int row0 = (tile - bi * tiles_per_scene) * TILE_ROWS;  // first grouped row in the scene
+    // ---- gather: build A0 -------------------------------------------------------------------
+    if (tid < TILE_ROWS) s_idx[tid] = p.idx[(size_t)bi * rows_per_scene + row0 + tid];
+    if (p.w_shared) copy_image(rw1, p.w1, w1_bytes, tid);
+    __syncthreads();
+    {
+      const __nv_bfloat16 *tab = p.table + (size_t)bi * p.n * p.cfeat8;
+      for (int i = tid; i < TILE_ROWS * nchunk; i += THREADS) {
+        const int r = i / nchunk, c = i - r * nchunk;
+        const int pt = s_idx[r];
+        uint4 v;
+        if (c < nchunk - 1) {
+          v = __ldg(reinterpret_cast<const uint4 *>(tab + (size_t)pt * p.cfeat8) + c);
+        } else {
+          const int g = (row0 + r) / p.nsample;
+          const float *px = p.xyz + ((size_t)bi * p.n + pt) * 3;
+          const float *cx = p.center + ((size_t)bi * p.m + g) * 3;
+          float dx = __fsub_rn(__ldg(px + 0), __ldg(cx + 0));
+          float dy = __fsub_rn(__ldg(px + 1), __ldg(cx + 1));
+          float dz = __fsub_rn(__ldg(px + 2), __ldg(cx + 2));
+          if (p.inv_radius > 0.f) { dx *= p.inv_radius; dy *= p.inv_radius; dz *= p.inv_radius; }
+          v = make_uint4(pack_bf16(dx, dy), pack_bf16(dz, 0.f), 0u, 0u);
+        }
+        *reinterpret_cast<uint4 *>(r0 + operand_off(r, c, TILE_ROWS)) = v;
+      }
+      // zero the K padding between the xyz chunk and k0pad (at most one 16-byte chunk)
+      const int kchunks = p.k0pad >> 3;
+      if (kchunks > nchunk) {
+        for (int i = tid; i < TILE_ROWS * (kchunks - nchunk); i += THREADS) {
+          const int r = i / (kchunks - nchunk), c = nchunk + (i - r * (kchunks - nchunk));
+          *reinterpret_cast<uint4 *>(r0 + operand_off(r, c, TILE_ROWS)) = make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    // ---- layer 1 ----------------------------------------------------------------------------
+    if (tid == 0) {
+      tc_fence_after();
+      issue_layer(d1, smem_u32(r0), TILE_ROWS, smem_u32(rw1), p.c1, p.k0pad >> 4,
+                  umma_idesc(128, p.c1));
+      umma_commit(mbar);
+    }
+    mbar_wait(mbar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    if (p.w_shared) copy_image(rw3, p.w3, w3_bytes, tid);  // W1 is dead now
+    {
+      const int cols = p.c1 >> 1;  // this warp-half's share of the output channels
+      for (int c0 = half * cols; c0 < (half + 1) * cols; c0 += 16) {
+        float v[16];
+        tmem_ld16(d1 + ((unsigned)(q * 32) << 16) + (unsigned)c0, v);
+        unsigned w[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float a = fmaxf(fmaf(v[2 * j], __ldg(sc1 + c0 + 2 * j), __ldg(sh1 + c0 + 2 * j)), 0.f);
+          const float b = fmaxf(fmaf(v[2 * j + 1], __ldg(sc1 + c0 + 2 * j + 1), __ldg(sh1 + c0 + 2 * j + 1)), 0.f);
+          w[j] = pack_bf16(a, b);
+        }
+        *reinterpret_cast<uint4 *>(r0 + operand_off(row, c0 >> 3, TILE_ROWS)) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4 *>(r0 + operand_off(row, (c0 >> 3) + 1, TILE_ROWS)) = make_uint4(w[4], w[5], w[6], w[7]);
+      }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    // ---- layer 2 ----------------------------------------------------------------------------
+    if (tid == 0) {
+      tc_fence_after();
+      issue_layer(d2, smem_u32(r0), TILE_ROWS, smem_u32(rw2), p.c2, p.c1 >> 4, umma_idesc(128, p.c2));
+      umma_commit(mbar);
+    }
+    mbar_wait(mbar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    {
+      const int cols = p.c2 >> 1;
+      for (int c0 = half * cols; c0 < (half + 1) * cols; c0 += 16) {
+        float v[16];
+        tmem_ld16(d2 + ((unsigned)(q * 32) << 16) + (unsigned)c0, v);
+        unsigned w[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float a = fmaxf(fmaf(v[2 * j], __ldg(sc2 + c0 + 2 * j), __ldg(sh2 + c0 + 2 * j)), 0.f);
+          const float b = fmaxf(fmaf(v[2 * j + 1], __ldg(sc2 + c0 + 2 * j + 1), __ldg(sh2 + c0 + 2 * j + 1)), 0.f);
+          w[j] = pack_bf16(a, b);
+        }
+        *reinterpret_cast<uint4 *>(r1 + operand_off(row, c0 >> 3, TILE_ROWS)) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4 *>(r1 + operand_off(row, (c0 >> 3) + 1, TILE_ROWS)) = make_uint4(w[4], w[5], w[6], w[7]);
+      }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    // ---- layer 3, transposed: D3^T[c3 x 128 rows] = W3 * A2^T --------------------------------
+    if (tid == 0) {
+      tc_fence_after();
+      for (int blk = 0; blk < (p.c3 >> 7); ++blk)
+        issue_layer(d3 + (unsigned)(blk * 128), smem_u32(rw3) + (unsigned)(blk * 128 * 128), p.c3,
+                    smem_u32(r1), TILE_ROWS, p.c2 >> 4, umma_idesc(128, 128));
+      umma_commit(mbar);
+    }
+    mbar_wait(mbar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    {
+      // c3 == 256: warps 0-3 take channel block 0, warps 4-7 block 1, all 128 columns each;
+      // c3 == 128: the two warp groups split the 128 columns (rows of the tile) in halves.
+      const int blk = (p.c3 == 256) ? half : 0;
+      const int col_beg = (p.c3 == 256) ? 0 : half * 64;
+      const int col_end = (p.c3 == 256) ? 128 : col_beg + 64;
+      const int ch = blk * 128 + row;
+      const float s = __ldg(sc3 + ch), t = __ldg(sh3 + ch);
+      float *o = p.out + ((size_t)bi * p.c3 + ch) * p.m + row0 / p.nsample;
+      const int lg_ns = 31 - __clz(p.nsample);
+      float gmax = 0.f;  // ReLU output is >= 0
+      for (int c0 = col_beg; c0 < col_end; c0 += 16) {
+        float v[16];
+        tmem_ld16(d3 + (unsigned)(blk * 128) + ((unsigned)(q * 32) << 16) + (unsigned)c0, v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          gmax = fmaxf(gmax, fmaf(v[j], s, t));
+          if (((c0 + j + 1) & (p.nsample - 1)) == 0) {  // last row of a group (nsample = 2^k)
+            o[(c0 + j) >> lg_ns] = gmax;
+            gmax = 0.f;
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();  // TMEM and the operand regions are free for the next tile
+  }
+
+  __syncthreads();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem),
+                 "r"((unsigned)p.tmem_cols)
+                 : "memory");
+}
+
+// (b, c, n) fp32 channel-major -> (b, n, c8) bf16 point-major (c8 = c rounded up to 8, zero padded)
+__global__ void __launch_bounds__(256) pack_table_kernel(int c, int n, int c8,
+                                                         const float *__restrict__ feat,
+                                                         __nv_bfloat16 *__restrict__ out) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  feat += (size_t)b * c * n;
+  out += (size_t)b * n * c8;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int cc = c0 + j, nn = n0 + threadIdx.x;
+    tile[j][threadIdx.x] = (cc < c && nn < n) ? feat[(size_t)cc * n + nn] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int nn = n0 + j, cc = c0 + threadIdx.x;
+    if (nn < n && cc < c8) out[(size_t)nn * c8 + cc] = __float2bfloat16_rn(tile[threadIdx.x][j]);
+  }
+}
+
+size_t smem_need(int k0pad, int c1, int c2, int c3, int w_shared) {
+  const int nslab0 = (k0pad + 63) >> 6, nslab1 = c1 >> 6, nslab2 = c2 >> 6;
+  size_t s = (size_t)(nslab0 > nslab1 ? nslab0 : nslab1) * SLAB_BYTES + (size_t)nslab2 * SLAB_BYTES;
+  s += (size_t)nslab1 * c2 * 128;
+  const size_t w1 = (size_t)nslab0 * c1 * 128, w3 = (size_t)nslab2 * c3 * 128;
+  s += w_shared ? (w1 > w3 ? w1 : w3) : w1 + w3;
+  return s + 1024;  // alignment slack
+}
+
+}  // namespace
+}  // namespace nesie
+
+using namespace nesie;
+
+extern "C" int nesie_sa_fused_supported(int nsample, int c_in, int c1, int c2, int c3) {
+  const int cfeat8 = (c_in + 7) & ~7;
+  const int k0pad = (cfeat8 + 3 + 15) & ~15;
+  if (nsample < 8 || nsample > 64 || (nsample & (nsample - 1))) return 0;
+  if ((c1 != 64 && c1 != 128) || (c2 != 64 && c2 != 128) || (c3 != 128 && c3 != 256)) return 0;
+  if (c1 + c2 + c3 > 512 || k0pad > 320) return 0;
+  return smem_need(k0pad, c1, c2, c3, 1) <= 227 * 1024 ? 1 : 0;
+}
+
+extern "C" int nesie_pack_features_bf16(int b, int c, int n, const float *features, void *table,
+                                        void *stream) {
+  NESIE_REQUIRE(b >= 0 && c >= 0 && n >= 0, "negative size");
+  if (b == 0 || n == 0) return NESIE_OK;
+  NESIE_REQUIRE(table && (c == 0 || features), "null pointer");
+  const int c8 = c == 0 ? 8 : (c + 7) & ~7;
+  dim3 grid(ceil_div(n, 32), ceil_div(c8, 32), b), block(32, 8);
+  pack_table_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(
+      c, n, c8, features, reinterpret_cast<__nv_bfloat16 *>(table));
+  return check_launch("nesie_pack_features_bf16");
+}
+
+extern "C" int nesie_sa_fused_forward(int b, int n, int npoints, int nsample, int c_in, int c1,
+                                      int c2, int c3, const float *xyz, const float *center_xyz,
+                                      const void *features_pm_bf16, const int *idx, float radius,
+                                      const void *w1_img, const void *w2_img, const void *w3_img,
+                                      const float *scale_shift, float *out, void *stream) {
+  NESIE_REQUIRE(b >= 0 && n >= 1 && npoints >= 0, "bad sizes");
+  NESIE_REQUIRE(nesie_sa_fused_supported(nsample, c_in, c1, c2, c3), "unsupported layer shape");
+  NESIE_REQUIRE(((long long)npoints * nsample) % TILE_ROWS == 0,
+                "npoints * nsample must be a multiple of 128");
+  NESIE_REQUIRE(xyz && center_xyz && features_pm_bf16 && idx && w1_img && w2_img && w3_img &&
+                    scale_shift && out,
+                "null pointer");
+  if (b == 0 || npoints == 0) return NESIE_OK;
+  SaParams p;
+  p.b = b; p.n = n; p.m = npoints; p.nsample = nsample;
+  p.cfeat8 = c_in == 0 ? 8 : (c_in + 7) & ~7;
+  p.k0pad = (p.cfeat8 + 3 + 15) & ~15;
+  p.c1 = c1; p.c2 = c2; p.c3 = c3;
+  p.w_shared = smem_need(p.k0pad, c1, c2, c3, 0) <= 227 * 1024 ? 0 : 1;
+  p.tmem_cols = (c1 + c2 + c3) <= 256 ? 256 : 512;
+  p.inv_radius = radius > 0.f ? 1.0f / radius : 0.f;
+  p.xyz = xyz; p.center = center_xyz;
+  p.table = reinterpret_cast<const __nv_bfloat16 *>(features_pm_bf16);
+  p.idx = idx;
+  p.w1 = reinterpret_cast<const uint4 *>(w1_img);
+  p.w2 = reinterpret_cast<const uint4 *>(w2_img);
+  p.w3 = reinterpret_cast<const uint4 *>(w3_img);
+  p.scale_shift = scale_shift;
+  p.out = out;
+  const size_t smem = smem_need(p.k0pad, c1, c2, c3, p.w_shared);
+  NESIE_CUDA(cudaFuncSetAttribute(sa_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+  const long long ntiles = (long long)b * npoints * nsample / TILE_ROWS;
+  int grid = num_sms();
+  // small layers (<= 110 KB of smem, 256 TMEM columns) can co-host two CTAs per SM
+  if (smem <= 110 * 1024 && p.tmem_cols <= 256) grid *= 2;
+  if (ntiles < grid) grid = (int)ntiles;
+  sa_fused_kernel<<<grid, THREADS, smem, (cudaStream_t)stream>>>(p);
+  return check_launch("nesie_sa_fused_forward");
+}

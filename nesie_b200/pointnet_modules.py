@@ -16,6 +16,8 @@ from .furthest_point_sample import Points_Sampler
 from .gather_points import gather_points
 from .group_points import GroupAll, QueryAndGroup
 from .interpolate import three_interpolate, three_nn
+from . import sa_fused
+from .ball_query import ball_query
 
 _NORMS = {'BN': nn.BatchNorm2d, 'BN1d': nn.BatchNorm1d, 'BN2d': nn.BatchNorm2d}
 _CONVS = {'Conv1d': nn.Conv1d, 'Conv2d': nn.Conv2d}
@@ -123,11 +125,39 @@ class BasePointSAModule(nn.Module):
             raise NotImplementedError
         return new_features.squeeze(-1).contiguous()
 
+    # ---- fused tcgen05 path (eval mode, folded BN, bf16 operands) ---------------------------
+    fused_bf16 = False  # opt-in: outputs then match the fp32 path within 1e-2 (bf16 MLP mode)
+
+    def _fused_ok(self, i, features):
+        g = self.groupers[i]
+        if self.training or not self.fused_bf16 or self.pool_mod != 'max' or features is None:
+            return False
+        if not isinstance(g, QueryAndGroup) or not g.use_xyz or len(self.mlps[i]) != 3:
+            return False
+        if (self.num_point[0] * g.sample_num) % 128 != 0:
+            return False
+        cs = [l.conv.out_channels for l in self.mlps[i]]
+        return sa_fused.supported(g.sample_num, features.shape[1], *cs)
+
+    def _fused_forward(self, i, points_xyz, new_xyz, features):
+        g = self.groupers[i]
+        key = tuple(int(t._version) for t in self.mlps[i].state_dict().values())
+        cache = self.__dict__.setdefault('_fused_cache', {})
+        if cache.get(i, (None,))[0] != key:
+            cache[i] = (key, sa_fused.fold_mlp(self.mlps[i], features.shape[1]))
+        idx = ball_query(g.min_radius, g.max_radius, g.sample_num, points_xyz.contiguous(),
+                         new_xyz.contiguous())
+        radius = g.max_radius if g.normalize_xyz else 0.0
+        return sa_fused.sa_fused_forward(points_xyz, new_xyz, features, idx, radius, cache[i][1])
+
     def forward(self, points_xyz, features=None, indices=None, target_xyz=None):
         """-> (new_xyz (B,M,3), new_features (B, sum C_out, M), indices (B,M) int32)."""
         new_features_list = []
         new_xyz, indices = self._sample_points(points_xyz, features, indices, target_xyz)
         for i in range(len(self.groupers)):
+            if self._fused_ok(i, features):
+                new_features_list.append(self._fused_forward(i, points_xyz, new_xyz, features))
+                continue
             grouped_results = self.groupers[i](points_xyz, new_xyz, features)
             new_features = self.mlps[i](grouped_results)
             new_features = self._pool_features(new_features)

@@ -4,7 +4,7 @@ Shape contract of the reference's input pipeline: (N, 4) fp32 = x, y, z, height 
 height = z - 0.99-percentile-floor (mmdet3d/datasets/pipelines/loading.py:418-420), N = 40000
 after IndoorPointSample (pipelines/transforms_3d.py:865-878); 18 ScanNet classes.  Geometry:
 a room box x,y in [-4,4], z in [0,2.5]; 70 % of the points on floor / walls / 6-12 axis-aligned
-cuboid surfaces (so r = 0.2 balls hold tens of points, as in real scans), 30 % uniform;
+cuboids (three quarters on their surfaces, one quarter inside, so some seeds lie near box centres) (so r = 0.2 balls hold tens of points, as in real scans), 30 % uniform;
 0.5 % exact duplicates (exercises d2 == 0 in ball query and tie-breaking in FPS).
 """
 import numpy as np
@@ -28,7 +28,8 @@ def make_scene(seed, n_points=40000, dup_frac=0.005):
     u = rng.uniform(-0.5, 0.5, (n_obj, 3)).astype(np.float32)
     face = rng.integers(0, 3, n_obj)
     sign = rng.choice([-0.5, 0.5], n_obj).astype(np.float32)
-    u[np.arange(n_obj), face] = sign
+    interior = rng.uniform(0, 1, n_obj) < 0.25  # a quarter of the object points fill the volume
+    u[np.arange(n_obj), face] = np.where(interior, u[np.arange(n_obj), face], sign)
     obj_pts = ctr[which] + u * size[which]
     # floor and walls
     n_floor = (n_surf - n_obj) // 2
