@@ -199,7 +199,9 @@ int nesie_ema_update(long long count, float *ema, const float *param, float deca
  * w{1,2,3}_img: weights pre-packed as byte images of the UMMA K-major SWIZZLE_128B shared-memory
  *   layout, [K/64 slabs][C_out rows][128 B], 16-byte chunk c of row r stored at chunk c ^ (r & 7);
  *   layer-1 columns ordered [features (c8) | xyz (3) | zero pad to a multiple of 16].
- * scale_shift: fp32 [scale1 c1][shift1 c1][scale2 c2][shift2 c2][scale3 c3][shift3 c3].
+ *   nsample must be 16, 32 or 64.
+ * bias: fp32 [bias1 c1][bias2 c2][bias3 c3] = the folded BN shift; the BN scale must already be
+ *   multiplied into the rows of w{1,2,3} (nesie_b200/sa_fused.py::fold_mlp).
  * out (b, c3, npoints) fp32.  nesie_sa_fused_supported() says whether a layer shape is covered.
  */
 int nesie_sa_fused_supported(int nsample, int c_in, int c1, int c2, int c3);
@@ -209,7 +211,7 @@ int nesie_sa_fused_forward(int b, int n, int npoints, int nsample, int c_in, int
                            int c3, const float *xyz, const float *center_xyz,
                            const void *features_pm_bf16, const int *idx, float radius,
                            const void *w1_img, const void *w2_img, const void *w3_img,
-                           const float *scale_shift, float *out, void *stream);
+                           const float *bias, float *out, void *stream);
 
 #ifdef __cplusplus
 }

@@ -13,11 +13,13 @@
 //   gather   : 256 threads copy the rows' bf16 features (16-byte chunks) + the normalised xyz offset
 //              into shared memory in the UMMA K-major SWIZZLE_128B operand layout
 //   layer 1/2: tcgen05.mma  D[128 rows x C_out] (TMEM, fp32) = A[rows x K] * W^T, issued by one
-//              thread; epilogue = tcgen05.ld -> scale/shift (folded BN) -> ReLU -> bf16 -> written
-//              straight back to shared memory as the next layer's A operand
+//              thread; epilogue = tcgen05.ld -> + bias (the BN scale is folded into W on the host,
+//              the BN shift is the bias) -> ReLU -> bf16 -> written straight back to shared memory
+//              as the next layer's A operand
 //   layer 3  : computed TRANSPOSED, D3^T[C3 channels x 128 rows] = W3 * A2^T, so that a TMEM lane is
 //              a channel and the nsample rows of a group are consecutive TMEM columns: the max-pool
-//              is a register max over a tcgen05.ld, no shuffles, and scale/shift are per-thread
+//              is a register max over a tcgen05.ld, no shuffles; bias + ReLU are applied once per
+//              group AFTER the max (both monotone), with a per-thread bias
 // Operands are bf16 with fp32 accumulation (the north star's "bf16 MLP within 1e-2" mode).
 // Weights arrive pre-packed (nesie_b200/sa_fused.py) as byte images of their swizzled shared-memory
 // layout, so loading them is a linear copy.  W2 (and W1/W3 when everything fits in 227 KB) stay
@@ -46,7 +48,7 @@ struct SaParams {
   const __nv_bfloat16 *table;  // (b, n, cfeat8) point-major bf16 features
   const int *idx;         // (b, m, nsample)
   const uint4 *w1, *w2, *w3;   // swizzled smem images
-  const float *scale_shift;    // [scale1 c1][shift1 c1][scale2 c2][shift2 c2][scale3 c3][shift3 c3]
+  const float *bias;           // [bias1 c1][bias2 c2][bias3 c3] (BN shift; the BN scale is folded into W)
   float *out;             // (b, c3, m)
 };
 
@@ -104,6 +106,22 @@ __device__ __forceinline__ void tmem_ld16(unsigned taddr, float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld32(unsigned taddr, float (&v)[32]) {
+  unsigned r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void fence_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
@@ -136,6 +154,29 @@ __device__ __forceinline__ void issue_layer(unsigned d_tmem, unsigned a_base, in
     const unsigned a = a_base + (unsigned)(ks >> 2) * (unsigned)(a_rows * 128) + (unsigned)(ks & 3) * 32u;
     const unsigned b = b_base + (unsigned)(ks >> 2) * (unsigned)(b_rows * 128) + (unsigned)(ks & 3) * 32u;
     umma_bf16(d_tmem, umma_desc(a), umma_desc(b), idesc, ks > 0 ? 1u : 0u);
+  }
+}
+
+// Layer-1/2 epilogue: TMEM accumulator (this thread's row, this warp-half's channels) -> + bias
+// -> ReLU -> bf16 -> the next layer's A operand in shared memory (BN scale is folded into W).
+__device__ __forceinline__ void epilogue_to_operand(unsigned d_tmem, int q, int half, int cout,
+                                                    const float *__restrict__ bias,
+                                                    unsigned char *dst, int row) {
+  const int cols = cout >> 1;  // 32 or 64
+  for (int c0 = half * cols; c0 < (half + 1) * cols; c0 += 32) {
+    float v[32];
+    tmem_ld32(d_tmem + ((unsigned)(q * 32) << 16) + (unsigned)c0, v);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const float4 b0 = __ldg(reinterpret_cast<const float4 *>(bias + c0 + g * 8));
+      const float4 b1 = __ldg(reinterpret_cast<const float4 *>(bias + c0 + g * 8 + 4));
+      const unsigned w0 = pack_bf16(fmaxf(v[g * 8 + 0] + b0.x, 0.f), fmaxf(v[g * 8 + 1] + b0.y, 0.f));
+      const unsigned w1 = pack_bf16(fmaxf(v[g * 8 + 2] + b0.z, 0.f), fmaxf(v[g * 8 + 3] + b0.w, 0.f));
+      const unsigned w2 = pack_bf16(fmaxf(v[g * 8 + 4] + b1.x, 0.f), fmaxf(v[g * 8 + 5] + b1.y, 0.f));
+      const unsigned w3 = pack_bf16(fmaxf(v[g * 8 + 6] + b1.z, 0.f), fmaxf(v[g * 8 + 7] + b1.w, 0.f));
+      *reinterpret_cast<uint4 *>(dst + operand_off(row, (c0 >> 3) + g, TILE_ROWS)) =
+          make_uint4(w0, w1, w2, w3);
+    }
   }
 }
 
@@ -183,14 +224,13 @@ __global__ void __launch_bounds__(THREADS, 1) sa_fused_kernel(SaParams p) {
   const unsigned mbar = smem_u32(&s_mbar);
   unsigned phase = 0;
 
-  const float *sc1 = p.scale_shift, *sh1 = sc1 + p.c1;
-  const float *sc2 = sh1 + p.c1, *sh2 = sc2 + p.c2;
-  const float *sc3 = sh2 + p.c2, *sh3 = sc3 + p.c3;
+  const float *bias1 = p.bias, *bias2 = bias1 + p.c1, *bias3 = bias2 + p.c2;
 
   const int rows_per_scene = p.m * p.nsample;
   const int tiles_per_scene = rows_per_scene / TILE_ROWS;
   const int ntiles = p.b * tiles_per_scene;
   const int nchunk = (p.cfeat8 >> 3) + 1;  // feature chunks + the xyz chunk
+  const int step_r = THREADS / nchunk, step_c = THREADS - step_r * nchunk;
   const int q = warp & 3, half = warp >> 2;
   const int row = q * 32 + lane;           // this thread's TMEM lane in the epilogues
 
@@ -203,8 +243,10 @@ __global__ void __launch_bounds__(THREADS, 1) sa_fused_kernel(SaParams p) {
     __syncthreads();
     {
       const __nv_bfloat16 *tab = p.table + (size_t)bi * p.n * p.cfeat8;
-      for (int i = tid; i < TILE_ROWS * nchunk; i += THREADS) {
-        const int r = i / nchunk, c = i - r * nchunk;
+      // flat (row, chunk) walk without a division per element
+      int r = tid / nchunk, c = tid - r * nchunk;
+      for (int i = tid; i < TILE_ROWS * nchunk; i += THREADS, r += step_r, c += step_c) {
+        if (c >= nchunk) { c -= nchunk; ++r; }
         const int pt = s_idx[r];
         uint4 v;
         if (c < nchunk - 1) {
@@ -244,22 +286,7 @@ __global__ void __launch_bounds__(THREADS, 1) sa_fused_kernel(SaParams p) {
     phase ^= 1;
     tc_fence_after();
     if (p.w_shared) copy_image(rw3, p.w3, w3_bytes, tid);  // W1 is dead now
-    {
-      const int cols = p.c1 >> 1;  // this warp-half's share of the output channels
-      for (int c0 = half * cols; c0 < (half + 1) * cols; c0 += 16) {
-        float v[16];
-        tmem_ld16(d1 + ((unsigned)(q * 32) << 16) + (unsigned)c0, v);
-        unsigned w[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float a = fmaxf(fmaf(v[2 * j], __ldg(sc1 + c0 + 2 * j), __ldg(sh1 + c0 + 2 * j)), 0.f);
-          const float b = fmaxf(fmaf(v[2 * j + 1], __ldg(sc1 + c0 + 2 * j + 1), __ldg(sh1 + c0 + 2 * j + 1)), 0.f);
-          w[j] = pack_bf16(a, b);
-        }
-        *reinterpret_cast<uint4 *>(r0 + operand_off(row, c0 >> 3, TILE_ROWS)) = make_uint4(w[0], w[1], w[2], w[3]);
-        *reinterpret_cast<uint4 *>(r0 + operand_off(row, (c0 >> 3) + 1, TILE_ROWS)) = make_uint4(w[4], w[5], w[6], w[7]);
-      }
-    }
+    epilogue_to_operand(d1, q, half, p.c1, bias1, r0, row);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -272,22 +299,7 @@ __global__ void __launch_bounds__(THREADS, 1) sa_fused_kernel(SaParams p) {
     mbar_wait(mbar, phase);
     phase ^= 1;
     tc_fence_after();
-    {
-      const int cols = p.c2 >> 1;
-      for (int c0 = half * cols; c0 < (half + 1) * cols; c0 += 16) {
-        float v[16];
-        tmem_ld16(d2 + ((unsigned)(q * 32) << 16) + (unsigned)c0, v);
-        unsigned w[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float a = fmaxf(fmaf(v[2 * j], __ldg(sc2 + c0 + 2 * j), __ldg(sh2 + c0 + 2 * j)), 0.f);
-          const float b = fmaxf(fmaf(v[2 * j + 1], __ldg(sc2 + c0 + 2 * j + 1), __ldg(sh2 + c0 + 2 * j + 1)), 0.f);
-          w[j] = pack_bf16(a, b);
-        }
-        *reinterpret_cast<uint4 *>(r1 + operand_off(row, c0 >> 3, TILE_ROWS)) = make_uint4(w[0], w[1], w[2], w[3]);
-        *reinterpret_cast<uint4 *>(r1 + operand_off(row, (c0 >> 3) + 1, TILE_ROWS)) = make_uint4(w[4], w[5], w[6], w[7]);
-      }
-    }
+    epilogue_to_operand(d2, q, half, p.c2, bias2, r1, row);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -309,19 +321,25 @@ __global__ void __launch_bounds__(THREADS, 1) sa_fused_kernel(SaParams p) {
       const int col_beg = (p.c3 == 256) ? 0 : half * 64;
       const int col_end = (p.c3 == 256) ? 128 : col_beg + 64;
       const int ch = blk * 128 + row;
-      const float s = __ldg(sc3 + ch), t = __ldg(sh3 + ch);
+      const float t = __ldg(bias3 + ch);
       float *o = p.out + ((size_t)bi * p.c3 + ch) * p.m + row0 / p.nsample;
       const int lg_ns = 31 - __clz(p.nsample);
-      float gmax = 0.f;  // ReLU output is >= 0
-      for (int c0 = col_beg; c0 < col_end; c0 += 16) {
-        float v[16];
-        tmem_ld16(d3 + (unsigned)(blk * 128) + ((unsigned)(q * 32) << 16) + (unsigned)c0, v);
+      float gmax = -3.0e38f;
+      // max over the raw accumulators first (bias + ReLU are monotone, applied once per group)
+      for (int c0 = col_beg; c0 < col_end; c0 += 32) {
+        float v[32];
+        tmem_ld32(d3 + (unsigned)(blk * 128) + ((unsigned)(q * 32) << 16) + (unsigned)c0, v);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          gmax = fmaxf(gmax, fmaf(v[j], s, t));
-          if (((c0 + j + 1) & (p.nsample - 1)) == 0) {  // last row of a group (nsample = 2^k)
-            o[(c0 + j) >> lg_ns] = gmax;
-            gmax = 0.f;
+        for (int h16 = 0; h16 < 2; ++h16) {
+          float m0 = fmaxf(v[h16 * 16 + 0], v[h16 * 16 + 1]), m1 = fmaxf(v[h16 * 16 + 2], v[h16 * 16 + 3]);
+          float m2 = fmaxf(v[h16 * 16 + 4], v[h16 * 16 + 5]), m3 = fmaxf(v[h16 * 16 + 6], v[h16 * 16 + 7]);
+          float m4 = fmaxf(v[h16 * 16 + 8], v[h16 * 16 + 9]), m5 = fmaxf(v[h16 * 16 + 10], v[h16 * 16 + 11]);
+          float m6 = fmaxf(v[h16 * 16 + 12], v[h16 * 16 + 13]), m7 = fmaxf(v[h16 * 16 + 14], v[h16 * 16 + 15]);
+          gmax = fmaxf(gmax, fmaxf(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)), fmaxf(fmaxf(m4, m5), fmaxf(m6, m7))));
+          const int cend = c0 + h16 * 16 + 16;  // nsample >= 16: groups end on 16-column bounds
+          if ((cend & (p.nsample - 1)) == 0) {
+            o[(cend - 1) >> lg_ns] = fmaxf(gmax + t, 0.f);
+            gmax = -3.0e38f;
           }
         }
       }
@@ -374,7 +392,7 @@ using namespace nesie;
 extern "C" int nesie_sa_fused_supported(int nsample, int c_in, int c1, int c2, int c3) {
   const int cfeat8 = (c_in + 7) & ~7;
   const int k0pad = (cfeat8 + 3 + 15) & ~15;
-  if (nsample < 8 || nsample > 64 || (nsample & (nsample - 1))) return 0;
+  if (nsample < 16 || nsample > 64 || (nsample & (nsample - 1))) return 0;
   if ((c1 != 64 && c1 != 128) || (c2 != 64 && c2 != 128) || (c3 != 128 && c3 != 256)) return 0;
   if (c1 + c2 + c3 > 512 || k0pad > 320) return 0;
   return smem_need(k0pad, c1, c2, c3, 1) <= 227 * 1024 ? 1 : 0;
@@ -419,7 +437,7 @@ extern "C" int nesie_sa_fused_forward(int b, int n, int npoints, int nsample, in
   p.w1 = reinterpret_cast<const uint4 *>(w1_img);
   p.w2 = reinterpret_cast<const uint4 *>(w2_img);
   p.w3 = reinterpret_cast<const uint4 *>(w3_img);
-  p.scale_shift = scale_shift;
+  p.bias = scale_shift;
   p.out = out;
   const size_t smem = smem_need(p.k0pad, c1, c2, c3, p.w_shared);
   NESIE_CUDA(cudaFuncSetAttribute(sa_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -54,8 +54,8 @@ def fold_mlp(mlp, c_in):
             w, kpad = w1, k0pad
         else:
             kpad = w.shape[1]
-        imgs.append(pack_weight_image(w, kpad))
-        ss += [scale, shift]
+        imgs.append(pack_weight_image(w * scale[:, None], kpad))  # BN scale folded into W
+        ss.append(shift)
         dims.append(w.shape[0])
     return dict(w1=imgs[0], w2=imgs[1], w3=imgs[2], scale_shift=torch.cat(ss).contiguous(),
                 c_in=c_in, c1=dims[0], c2=dims[1], c3=dims[2])
