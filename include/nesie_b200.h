@@ -68,6 +68,18 @@ int nesie_fps_with_dist(int b, int n, int m, const float *dist, float *temp, int
 int nesie_ball_query(int b, int n, int m, float min_radius, float max_radius, int nsample,
                      const float *new_xyz, const float *xyz, int *idx, void *stream);
 
+/* Same contract and bit-identical output, computed through a uniform grid (cells >= max_radius,
+ * 27-cell neighbourhoods, hits re-ranked by index): the formulation for large scenes, where the
+ * brute-force kernel is fp32-issue-bound (SA1: 655 M distance tests at batch 8).  Needs
+ * max_radius > 0 and a caller-provided, 16-byte aligned scratch buffer of
+ * nesie_ball_query_grid_workspace(b, n, m) bytes (the reference launchers never allocate; neither
+ * does this library).
+ */
+long long nesie_ball_query_grid_workspace(int b, int n, int m);
+int nesie_ball_query_grid(int b, int n, int m, float min_radius, float max_radius, int nsample,
+                          const float *new_xyz, const float *xyz, int *idx, void *workspace,
+                          long long workspace_bytes, void *stream);
+
 /* ---------------------------------------------------------------------------------------
  * gather_points: out[b,c,j] = points[b,c,idx[b,j]].
  * Replaces gather_points_kernel_launcher / gather_points_grad_kernel_launcher

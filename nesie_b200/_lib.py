@@ -20,6 +20,8 @@ SIGNATURES = {
     "nesie_fps_needs_temp": [_i, _i, _i],
     "nesie_fps_with_dist": [_i, _i, _i, _p, _p, _p, _p],
     "nesie_ball_query": [_i, _i, _i, _f, _f, _i, _p, _p, _p, _p],
+    "nesie_ball_query_grid_workspace": [_i, _i, _i],
+    "nesie_ball_query_grid": [_i, _i, _i, _f, _f, _i, _p, _p, _p, _p, _ll, _p],
     "nesie_gather_points": [_i, _i, _i, _i, _p, _p, _p, _p],
     "nesie_gather_points_grad": [_i, _i, _i, _i, _p, _p, _p, _p],
     "nesie_group_points": [_i, _i, _i, _i, _i, _p, _p, _p, _p],
@@ -53,7 +55,7 @@ def lib():
         for name, argtypes in SIGNATURES.items():
             fn = getattr(handle, name)
             fn.argtypes = argtypes
-            fn.restype = _i
+            fn.restype = _ll if name.endswith('_workspace') else _i
         handle.nesie_last_error.restype = ctypes.c_char_p
         handle.nesie_last_error.argtypes = []
         _lib = handle

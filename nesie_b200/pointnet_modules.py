@@ -150,6 +150,35 @@ class BasePointSAModule(nn.Module):
         radius = g.max_radius if g.normalize_xyz else 0.0
         return sa_fused.sa_fused_forward(points_xyz, new_xyz, features, idx, radius, cache[i][1])
 
+    # ---- shared MLP as row-major GEMMs ---------------------------------------------------------
+    # The reference runs the shared MLP as Conv2d(1x1)+BN2d+ReLU on the channel-major
+    # (B, C, M, K) tensor and max-pools with F.max_pool2d (point_sa_module.py:149-150,279-288).
+    # A 1x1 convolution over (B, C, M, K) is the GEMM (B*M*K, C_in) x (C_in, C_out), BN2d's batch
+    # statistics are the per-column statistics of that matrix and the pool is a max over K
+    # consecutive rows, so the same parameters are applied here to one point-major copy of the
+    # grouped tensor: cuBLAS GEMMs instead of cuDNN's slow fp32 1x1 wgrad/dgrad engines, and
+    # BatchNorm / ReLU / max over contiguous channel rows.  Same arithmetic, same state_dict.
+    rows_mlp = True
+
+    def _rows_ok(self, i, grouped):
+        return (grouped.is_cuda and self.pool_mod == 'max' and
+                all(isinstance(l.conv, nn.Conv2d) and l.conv.bias is None and l.with_norm and
+                    isinstance(l.bn, nn.BatchNorm2d) for l in self.mlps[i]))
+
+    def _mlp_rows(self, i, grouped):
+        B, C0, M, K = grouped.shape
+        x = grouped.permute(0, 2, 3, 1).reshape(B * M * K, C0)
+        for layer in self.mlps[i]:
+            bn = layer.bn
+            x = F.linear(x, layer.conv.weight.flatten(1))
+            if bn.training and bn.track_running_stats:
+                bn.num_batches_tracked.add_(1)
+            x = F.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias,
+                             bn.training or not bn.track_running_stats, bn.momentum, bn.eps)
+            x = F.relu(x, inplace=True)
+        x = x.view(B, M, K, -1).amax(dim=2)
+        return x.transpose(1, 2).contiguous()
+
     def forward(self, points_xyz, features=None, indices=None, target_xyz=None):
         """-> (new_xyz (B,M,3), new_features (B, sum C_out, M), indices (B,M) int32)."""
         new_features_list = []
@@ -159,8 +188,11 @@ class BasePointSAModule(nn.Module):
                 new_features_list.append(self._fused_forward(i, points_xyz, new_xyz, features))
                 continue
             grouped_results = self.groupers[i](points_xyz, new_xyz, features)
-            new_features = self.mlps[i](grouped_results)
-            new_features = self._pool_features(new_features)
+            if self.rows_mlp and self._rows_ok(i, grouped_results):
+                new_features = self._mlp_rows(i, grouped_results)
+            else:
+                new_features = self.mlps[i](grouped_results)
+                new_features = self._pool_features(new_features)
             new_features_list.append(new_features)
         return new_xyz, torch.cat(new_features_list, dim=1), indices
 
@@ -231,8 +263,25 @@ class PointFPModule(nn.Module):
             new_features = torch.cat([interpolated_feats, target_feats], dim=1)
         else:
             new_features = interpolated_feats
+        if self.rows_mlp and new_features.is_cuda:
+            return self._mlp_rows(new_features)
         new_features = self.mlps(new_features.unsqueeze(-1))
         return new_features.squeeze(-1)
+
+    rows_mlp = True  # see BasePointSAModule._mlp_rows: same parameters, GEMM formulation
+
+    def _mlp_rows(self, feats):
+        B, C, n = feats.shape
+        x = feats.transpose(1, 2).reshape(B * n, C)
+        for layer in self.mlps:
+            bn = layer.bn
+            x = F.linear(x, layer.conv.weight.flatten(1), layer.conv.bias)
+            if bn.training and bn.track_running_stats:
+                bn.num_batches_tracked.add_(1)
+            x = F.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias,
+                             bn.training or not bn.track_running_stats, bn.momentum, bn.eps)
+            x = F.relu(x, inplace=True)
+        return x.view(B, n, -1).transpose(1, 2).contiguous()
 
 
 SA_MODULES = {'PointSAModule': PointSAModule, 'PointSAModuleMSG': PointSAModuleMSG}

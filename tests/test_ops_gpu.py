@@ -255,3 +255,43 @@ def test_ops_refuse_cpu_tensors():
         nb.furthest_point_sample(torch.rand(1, 10, 3), 2)
     with pytest.raises(RuntimeError):
         nb.ball_query(0.0, 1.0, 4, torch.rand(1, 10, 3), torch.rand(1, 2, 3))
+
+
+# ---------------------------------------------------------------- grid ball query
+@pytest.mark.parametrize("B,N,M,K,r0,r1", [(2, 1500, 64, 16, 0.0, 0.3), (1, 4096, 128, 32, 0.0, 0.4),
+                                           (1, 1000, 100, 8, 0.1, 0.5), (2, 37, 37, 4, 0.0, 0.8),
+                                           (1, 1, 1, 3, 0.0, 0.2), (2, 20000, 700, 64, 0.0, 0.2),
+                                           (1, 3000, 5, 200, 0.0, 5.0), (1, 5000, 300, 16, 0.0, 0.01)])
+def test_ball_query_grid_matches_oracle(B, N, M, K, r0, r1, monkeypatch):
+    monkeypatch.setenv("NESIE_BALL_QUERY", "grid")
+    xyz = scene_xyz(B, N, 20 + K)
+    centres = xyz[:, torch.randperm(N, generator=torch.Generator().manual_seed(N))[:M]].contiguous()
+    centres[:, -1] += 50.0  # a centre far outside the cloud
+    want = cpu.ball_query(r0, r1, K, xyz, centres)
+    got = nb.ball_query(r0, r1, K, dev(xyz), dev(centres))
+    assert torch.equal(got.cpu(), want)
+
+
+def test_ball_query_grid_duplicates_overflow_and_full_size(monkeypatch):
+    # every point identical: each centre has N hits -> ordered-scan fallback
+    xyz = torch.ones(1, 3000, 3)
+    centres = torch.ones(1, 40, 3)
+    monkeypatch.setenv("NESIE_BALL_QUERY", "grid")
+    got = nb.ball_query(0.0, 0.2, 32, dev(xyz), dev(centres)).cpu()
+    assert torch.equal(got, cpu.ball_query(0.0, 0.2, 32, xyz, centres))
+    # integer grid (heavy duplicates, many > HMAX hit lists)
+    rng = np.random.default_rng(8)
+    xyz = torch.from_numpy(rng.integers(0, 6, (2, 9000, 3)).astype(np.float32))
+    centres = xyz[:, :200].contiguous()
+    got = nb.ball_query(0.0, 1.5, 64, dev(xyz), dev(centres)).cpu()
+    assert torch.equal(got, cpu.ball_query(0.0, 1.5, 64, xyz, centres))
+    # BASELINE shape: grid == brute force kernel == reference kernel
+    xyz = make_batch(8, 40000, seed0=0)[0][..., :3].contiguous().cuda()
+    idx = nb.furthest_point_sample(xyz, 2048)
+    centres = torch.gather(xyz, 1, idx.long().unsqueeze(-1).expand(-1, -1, 3)).contiguous()
+    grid = nb.ball_query(0.0, 0.2, 64, xyz, centres)
+    monkeypatch.setenv("NESIE_BALL_QUERY", "brute")
+    brute = nb.ball_query(0.0, 0.2, 64, xyz, centres)
+    assert torch.equal(grid, brute)
+    if ref_cuda.available():
+        assert torch.equal(grid, ref_cuda.ball_query(0.0, 0.2, 64, xyz, centres))

@@ -81,8 +81,13 @@ def main():
                lambda: ref_cuda.furthest_point_sample(x, M), B * (12 * N + 4 * M))
         idx = nb.furthest_point_sample(x, M)
         centres = torch.gather(x, 1, idx.long().unsqueeze(-1).expand(-1, -1, 3)).contiguous()
-        report(f"ball_query_{N}x{M}_k{K}", lambda: nb.ball_query(0.0, r, K, x, centres),
+        os.environ["NESIE_BALL_QUERY"] = "brute"
+        report(f"ball_query_brute_{N}x{M}_k{K}", lambda: nb.ball_query(0.0, r, K, x, centres),
                lambda: ref_cuda.ball_query(0.0, r, K, x, centres), B * (12 * N + 12 * M + 4 * M * K))
+        os.environ["NESIE_BALL_QUERY"] = "grid"
+        report(f"ball_query_grid_{N}x{M}_k{K}", lambda: nb.ball_query(0.0, r, K, x, centres),
+               None, B * (12 * N + 12 * M + 4 * M * K), "build + query")
+        os.environ["NESIE_BALL_QUERY"] = "auto"
         bq = nb.ball_query(0.0, r, K, x, centres)
         f = cur_feat if li == 0 else torch.randn(B, C, N, device="cuda")
         report(f"group_points_c{C}_{M}x{K}", lambda: nb.grouping_operation(f, bq),
