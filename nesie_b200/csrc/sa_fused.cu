@@ -142,9 +142,10 @@ __device__ __forceinline__ unsigned operand_off(int row, int chunk, int rows_per
   return (unsigned)((chunk >> 3) * rows_per_slab * 128 + row * 128 + (((chunk & 7) ^ (row & 7)) << 4));
 }
 
-__device__ __forceinline__ void copy_image(unsigned char *dst, const uint4 *src, int bytes, int tid) {
+__device__ __forceinline__ void copy_image(unsigned char *dst, const uint4 *src, int bytes, int tid,
+                                           int nthreads = THREADS) {
   uint4 *d = reinterpret_cast<uint4 *>(dst);
-  for (int i = tid; i < (bytes >> 4); i += THREADS) d[i] = __ldg(src + i);
+  for (int i = tid; i < (bytes >> 4); i += nthreads) d[i] = __ldg(src + i);
 }
 
 // One linear layer on the tensor core: D[128 x N] (+)= A[128 x K] * B[N x K]^T, K = ksteps * 16.
@@ -157,44 +158,88 @@ __device__ __forceinline__ void issue_layer(unsigned d_tmem, unsigned a_base, in
   }
 }
 
-// Layer-1/2 epilogue: TMEM accumulator (this thread's row, this warp-half's channels) -> + bias
+// ---- small sync helpers -----------------------------------------------------------------------
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned mbar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32_issue(unsigned taddr, unsigned (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+constexpr int NCOMPUTE = 128;  // warps 0-3: MMA issue + epilogues (thread = TMEM lane)
+constexpr int NGATHER = 128;   // warps 4-7: build the next tile's A operand
+
+// Layer-1/2 epilogue: TMEM accumulator row (all `cout` channels of this thread's row) -> + bias
 // -> ReLU -> bf16 -> the next layer's A operand in shared memory (BN scale is folded into W).
-__device__ __forceinline__ void epilogue_to_operand(unsigned d_tmem, int q, int half, int cout,
+// Two x32 TMEM loads are in flight per wait.
+__device__ __forceinline__ void epilogue_to_operand(unsigned d_tmem, int warp, int cout,
                                                     const float *__restrict__ bias,
                                                     unsigned char *dst, int row) {
-  const int cols = cout >> 1;  // 32 or 64
-  for (int c0 = half * cols; c0 < (half + 1) * cols; c0 += 32) {
-    float v[32];
-    tmem_ld32(d_tmem + ((unsigned)(q * 32) << 16) + (unsigned)c0, v);
+  for (int c0 = 0; c0 < cout; c0 += 64) {
+    unsigned v[2][32];
+    const unsigned base = d_tmem + ((unsigned)(warp * 32) << 16) + (unsigned)c0;
+    tmem_ld32_issue(base, v[0]);
+    tmem_ld32_issue(base + 32u, v[1]);
+    tmem_ld_wait();
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      const float4 b0 = __ldg(reinterpret_cast<const float4 *>(bias + c0 + g * 8));
-      const float4 b1 = __ldg(reinterpret_cast<const float4 *>(bias + c0 + g * 8 + 4));
-      const unsigned w0 = pack_bf16(fmaxf(v[g * 8 + 0] + b0.x, 0.f), fmaxf(v[g * 8 + 1] + b0.y, 0.f));
-      const unsigned w1 = pack_bf16(fmaxf(v[g * 8 + 2] + b0.z, 0.f), fmaxf(v[g * 8 + 3] + b0.w, 0.f));
-      const unsigned w2 = pack_bf16(fmaxf(v[g * 8 + 4] + b1.x, 0.f), fmaxf(v[g * 8 + 5] + b1.y, 0.f));
-      const unsigned w3 = pack_bf16(fmaxf(v[g * 8 + 6] + b1.z, 0.f), fmaxf(v[g * 8 + 7] + b1.w, 0.f));
-      *reinterpret_cast<uint4 *>(dst + operand_off(row, (c0 >> 3) + g, TILE_ROWS)) =
-          make_uint4(w0, w1, w2, w3);
+    for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int cc = c0 + hh * 32 + g * 8;
+        const float4 b0 = __ldg(reinterpret_cast<const float4 *>(bias + cc));
+        const float4 b1 = __ldg(reinterpret_cast<const float4 *>(bias + cc + 4));
+        const unsigned *u = &v[hh][g * 8];
+        const unsigned w0 = pack_bf16(fmaxf(__uint_as_float(u[0]) + b0.x, 0.f), fmaxf(__uint_as_float(u[1]) + b0.y, 0.f));
+        const unsigned w1 = pack_bf16(fmaxf(__uint_as_float(u[2]) + b0.z, 0.f), fmaxf(__uint_as_float(u[3]) + b0.w, 0.f));
+        const unsigned w2 = pack_bf16(fmaxf(__uint_as_float(u[4]) + b1.x, 0.f), fmaxf(__uint_as_float(u[5]) + b1.y, 0.f));
+        const unsigned w3 = pack_bf16(fmaxf(__uint_as_float(u[6]) + b1.z, 0.f), fmaxf(__uint_as_float(u[7]) + b1.w, 0.f));
+        *reinterpret_cast<uint4 *>(dst + operand_off(row, cc >> 3, TILE_ROWS)) = make_uint4(w0, w1, w2, w3);
+      }
     }
   }
 }
 
+__device__ __forceinline__ float max16(const unsigned *u) {
+  float m0 = fmaxf(__uint_as_float(u[0]), __uint_as_float(u[1])), m1 = fmaxf(__uint_as_float(u[2]), __uint_as_float(u[3]));
+  float m2 = fmaxf(__uint_as_float(u[4]), __uint_as_float(u[5])), m3 = fmaxf(__uint_as_float(u[6]), __uint_as_float(u[7]));
+  float m4 = fmaxf(__uint_as_float(u[8]), __uint_as_float(u[9])), m5 = fmaxf(__uint_as_float(u[10]), __uint_as_float(u[11]));
+  float m6 = fmaxf(__uint_as_float(u[12]), __uint_as_float(u[13])), m7 = fmaxf(__uint_as_float(u[14]), __uint_as_float(u[15]));
+  return fmaxf(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)), fmaxf(fmaxf(m4, m5), fmaxf(m6, m7)));
+}
+
+// Warp-specialised: warps 4-7 gather tile t+1 into A0 while warps 0-3 run the three layers of
+// tile t.  A0 is released to the gatherers by a tcgen05.commit as soon as layer 1 has consumed it;
+// A1 and A2 share one buffer (A2 is written after layer 2 has finished reading A1).
 __global__ void __launch_bounds__(THREADS, 1) sa_fused_kernel(SaParams p) {
   extern __shared__ unsigned char smem_dyn[];
   unsigned char *smem = reinterpret_cast<unsigned char *>(
       (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-  __shared__ __align__(8) unsigned long long s_mbar;
+  __shared__ __align__(8) unsigned long long s_mbar[3];  // 0: mma done, 1: A0 full, 2: A0 free
   __shared__ unsigned s_tmem;
   __shared__ int s_idx[TILE_ROWS];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nslab0 = (p.k0pad + 63) >> 6;
   const int nslab1 = p.c1 >> 6, nslab2 = p.c2 >> 6;
-  // regions (all 1024-byte aligned): R0 = A0 / A1, R1 = A2, then weights
-  unsigned char *r0 = smem;
-  unsigned char *r1 = r0 + (size_t)max(nslab0, nslab1) * SLAB_BYTES;
-  unsigned char *rw2 = r1 + (size_t)nslab2 * SLAB_BYTES;
+  // regions (all 1024-byte aligned): A0, A1/A2, then weights
+  unsigned char *ra0 = smem;
+  unsigned char *ra12 = ra0 + (size_t)nslab0 * SLAB_BYTES;
+  unsigned char *rw2 = ra12 + (size_t)max(nslab1, nslab2) * SLAB_BYTES;
   unsigned char *rw1 = rw2 + (size_t)nslab1 * p.c2 * 128;
   const int w1_bytes = nslab0 * p.c1 * 128, w3_bytes = nslab2 * p.c3 * 128;
   unsigned char *rw3 = p.w_shared ? rw1 : rw1 + w1_bytes;
@@ -207,145 +252,159 @@ __global__ void __launch_bounds__(THREADS, 1) sa_fused_kernel(SaParams p) {
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 0) {
-    mbar_init(smem_u32(&s_mbar), 1);
+    mbar_init(smem_u32(&s_mbar[0]), 1);
+    mbar_init(smem_u32(&s_mbar[1]), NGATHER);
+    mbar_init(smem_u32(&s_mbar[2]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   copy_image(rw2, p.w2, nslab1 * p.c2 * 128, tid);
-  if (!p.w_shared) {
-    copy_image(rw1, p.w1, w1_bytes, tid);
-    copy_image(rw3, p.w3, w3_bytes, tid);
-  }
+  copy_image(rw1, p.w1, w1_bytes, tid);  // shared mode: valid for the first tile
+  if (!p.w_shared) copy_image(rw3, p.w3, w3_bytes, tid);
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const unsigned tmem = s_tmem;
   const unsigned d1 = tmem, d2 = tmem + (unsigned)p.c1, d3 = tmem + (unsigned)(p.c1 + p.c2);
-  const unsigned mbar = smem_u32(&s_mbar);
-  unsigned phase = 0;
-
+  const unsigned mb_mma = smem_u32(&s_mbar[0]), mb_full = smem_u32(&s_mbar[1]),
+                 mb_free = smem_u32(&s_mbar[2]);
   const float *bias1 = p.bias, *bias2 = bias1 + p.c1, *bias3 = bias2 + p.c2;
 
   const int rows_per_scene = p.m * p.nsample;
   const int tiles_per_scene = rows_per_scene / TILE_ROWS;
   const int ntiles = p.b * tiles_per_scene;
-  const int nchunk = (p.cfeat8 >> 3) + 1;  // feature chunks + the xyz chunk
-  const int step_r = THREADS / nchunk, step_c = THREADS - step_r * nchunk;
-  const int q = warp & 3, half = warp >> 2;
-  const int row = q * 32 + lane;           // this thread's TMEM lane in the epilogues
+  const int lg_ns = 31 - __clz(p.nsample);
 
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int bi = tile / tiles_per_scene;
-    const int row0 = (tile - bi * tiles_per_scene) * TILE_ROWS;  // first grouped row in the scene
-    // ---- gather: build A0 -------------------------------------------------------------------
-    if (tid < TILE_ROWS) s_idx[tid] = p.idx[(size_t)bi * rows_per_scene + row0 + tid];
-    if (p.w_shared) copy_image(rw1, p.w1, w1_bytes, tid);
-    __syncthreads();
-    {
+  if (warp >= 4) {
+    // =========================== gather warps ===============================================
+    const int gt = tid - NCOMPUTE;
+    const int nfc = p.cfeat8 >> 3;  // feature chunks per row; chunk nfc is the xyz chunk
+    const int step_r = NGATHER / nfc, step_c = NGATHER - step_r * nfc;
+    const int r_start = gt / nfc, c_start = gt - r_start * nfc;
+    const int kchunks = p.k0pad >> 3;
+    unsigned it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int bi = tile / tiles_per_scene;
+      const int row0 = (tile - bi * tiles_per_scene) * TILE_ROWS;
+      // A0 is free once layer 1 of the previous tile has been committed
+      mbar_wait(mb_free, (it & 1u) ^ 1u);
+      const int my_pt = p.idx[(size_t)bi * rows_per_scene + row0 + gt];
+      s_idx[gt] = my_pt;
+      // xyz chunk of row gt: issue its loads before the barrier
+      const float *px = p.xyz + ((size_t)bi * p.n + my_pt) * 3;
+      const float *cx = p.center + ((size_t)bi * p.m + ((row0 + gt) >> lg_ns)) * 3;
+      float dx = __fsub_rn(__ldg(px + 0), __ldg(cx + 0));
+      float dy = __fsub_rn(__ldg(px + 1), __ldg(cx + 1));
+      float dz = __fsub_rn(__ldg(px + 2), __ldg(cx + 2));
+      named_bar_sync(2, NGATHER);
       const __nv_bfloat16 *tab = p.table + (size_t)bi * p.n * p.cfeat8;
-      // flat (row, chunk) walk without a division per element
-      int r = tid / nchunk, c = tid - r * nchunk;
-      for (int i = tid; i < TILE_ROWS * nchunk; i += THREADS, r += step_r, c += step_c) {
-        if (c >= nchunk) { c -= nchunk; ++r; }
-        const int pt = s_idx[r];
-        uint4 v;
-        if (c < nchunk - 1) {
-          v = __ldg(reinterpret_cast<const uint4 *>(tab + (size_t)pt * p.cfeat8) + c);
-        } else {
-          const int g = (row0 + r) / p.nsample;
-          const float *px = p.xyz + ((size_t)bi * p.n + pt) * 3;
-          const float *cx = p.center + ((size_t)bi * p.m + g) * 3;
-          float dx = __fsub_rn(__ldg(px + 0), __ldg(cx + 0));
-          float dy = __fsub_rn(__ldg(px + 1), __ldg(cx + 1));
-          float dz = __fsub_rn(__ldg(px + 2), __ldg(cx + 2));
-          if (p.inv_radius > 0.f) { dx *= p.inv_radius; dy *= p.inv_radius; dz *= p.inv_radius; }
-          v = make_uint4(pack_bf16(dx, dy), pack_bf16(dz, 0.f), 0u, 0u);
-        }
-        *reinterpret_cast<uint4 *>(r0 + operand_off(r, c, TILE_ROWS)) = v;
-      }
-      // zero the K padding between the xyz chunk and k0pad (at most one 16-byte chunk)
-      const int kchunks = p.k0pad >> 3;
-      if (kchunks > nchunk) {
-        for (int i = tid; i < TILE_ROWS * (kchunks - nchunk); i += THREADS) {
-          const int r = i / (kchunks - nchunk), c = nchunk + (i - r * (kchunks - nchunk));
-          *reinterpret_cast<uint4 *>(r0 + operand_off(r, c, TILE_ROWS)) = make_uint4(0u, 0u, 0u, 0u);
-        }
-      }
-    }
-    fence_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    // ---- layer 1 ----------------------------------------------------------------------------
-    if (tid == 0) {
-      tc_fence_after();
-      issue_layer(d1, smem_u32(r0), TILE_ROWS, smem_u32(rw1), p.c1, p.k0pad >> 4,
-                  umma_idesc(128, p.c1));
-      umma_commit(mbar);
-    }
-    mbar_wait(mbar, phase);
-    phase ^= 1;
-    tc_fence_after();
-    if (p.w_shared) copy_image(rw3, p.w3, w3_bytes, tid);  // W1 is dead now
-    epilogue_to_operand(d1, q, half, p.c1, bias1, r0, row);
-    fence_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    // ---- layer 2 ----------------------------------------------------------------------------
-    if (tid == 0) {
-      tc_fence_after();
-      issue_layer(d2, smem_u32(r0), TILE_ROWS, smem_u32(rw2), p.c2, p.c1 >> 4, umma_idesc(128, p.c2));
-      umma_commit(mbar);
-    }
-    mbar_wait(mbar, phase);
-    phase ^= 1;
-    tc_fence_after();
-    epilogue_to_operand(d2, q, half, p.c2, bias2, r1, row);
-    fence_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    // ---- layer 3, transposed: D3^T[c3 x 128 rows] = W3 * A2^T --------------------------------
-    if (tid == 0) {
-      tc_fence_after();
-      for (int blk = 0; blk < (p.c3 >> 7); ++blk)
-        issue_layer(d3 + (unsigned)(blk * 128), smem_u32(rw3) + (unsigned)(blk * 128 * 128), p.c3,
-                    smem_u32(r1), TILE_ROWS, p.c2 >> 4, umma_idesc(128, 128));
-      umma_commit(mbar);
-    }
-    mbar_wait(mbar, phase);
-    phase ^= 1;
-    tc_fence_after();
-    {
-      // c3 == 256: warps 0-3 take channel block 0, warps 4-7 block 1, all 128 columns each;
-      // c3 == 128: the two warp groups split the 128 columns (rows of the tile) in halves.
-      const int blk = (p.c3 == 256) ? half : 0;
-      const int col_beg = (p.c3 == 256) ? 0 : half * 64;
-      const int col_end = (p.c3 == 256) ? 128 : col_beg + 64;
-      const int ch = blk * 128 + row;
-      const float t = __ldg(bias3 + ch);
-      float *o = p.out + ((size_t)bi * p.c3 + ch) * p.m + row0 / p.nsample;
-      const int lg_ns = 31 - __clz(p.nsample);
-      float gmax = -3.0e38f;
-      // max over the raw accumulators first (bias + ReLU are monotone, applied once per group)
-      for (int c0 = col_beg; c0 < col_end; c0 += 32) {
-        float v[32];
-        tmem_ld32(d3 + (unsigned)(blk * 128) + ((unsigned)(q * 32) << 16) + (unsigned)c0, v);
+      int r = r_start, c = c_start;
+      for (int j0 = 0; j0 < nfc; j0 += 8) {
+        uint4 v[8];
+        unsigned off[8];
 #pragma unroll
-        for (int h16 = 0; h16 < 2; ++h16) {
-          float m0 = fmaxf(v[h16 * 16 + 0], v[h16 * 16 + 1]), m1 = fmaxf(v[h16 * 16 + 2], v[h16 * 16 + 3]);
-          float m2 = fmaxf(v[h16 * 16 + 4], v[h16 * 16 + 5]), m3 = fmaxf(v[h16 * 16 + 6], v[h16 * 16 + 7]);
-          float m4 = fmaxf(v[h16 * 16 + 8], v[h16 * 16 + 9]), m5 = fmaxf(v[h16 * 16 + 10], v[h16 * 16 + 11]);
-          float m6 = fmaxf(v[h16 * 16 + 12], v[h16 * 16 + 13]), m7 = fmaxf(v[h16 * 16 + 14], v[h16 * 16 + 15]);
-          gmax = fmaxf(gmax, fmaxf(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)), fmaxf(fmaxf(m4, m5), fmaxf(m6, m7))));
-          const int cend = c0 + h16 * 16 + 16;  // nsample >= 16: groups end on 16-column bounds
-          if ((cend & (p.nsample - 1)) == 0) {
-            o[(cend - 1) >> lg_ns] = fmaxf(gmax + t, 0.f);
-            gmax = -3.0e38f;
+        for (int u = 0; u < 8; ++u) {
+          if (j0 + u < nfc) {
+            v[u] = __ldg(reinterpret_cast<const uint4 *>(tab + (size_t)s_idx[r] * p.cfeat8) + c);
+            off[u] = operand_off(r, c, TILE_ROWS);
+            r += step_r; c += step_c;
+            if (c >= nfc) { c -= nfc; ++r; }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (j0 + u < nfc) *reinterpret_cast<uint4 *>(ra0 + off[u]) = v[u];
+      }
+      if (p.inv_radius > 0.f) { dx *= p.inv_radius; dy *= p.inv_radius; dz *= p.inv_radius; }
+      *reinterpret_cast<uint4 *>(ra0 + operand_off(gt, nfc, TILE_ROWS)) =
+          make_uint4(pack_bf16(dx, dy), pack_bf16(dz, 0.f), 0u, 0u);
+      for (int cz = nfc + 1; cz < kchunks; ++cz)  // K padding up to k0pad (at most one chunk)
+        *reinterpret_cast<uint4 *>(ra0 + operand_off(gt, cz, TILE_ROWS)) = make_uint4(0u, 0u, 0u, 0u);
+      fence_async_smem();
+      mbar_arrive(mb_full);
+      named_bar_sync(2, NGATHER);  // s_idx may be overwritten for the next tile
+    }
+  } else {
+    // =========================== compute warps ==============================================
+    const int row = tid;  // TMEM lane of this thread (warp w owns lanes 32w..32w+31)
+    unsigned it = 0, mma_phase = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int bi = tile / tiles_per_scene;
+      const int row0 = (tile - bi * tiles_per_scene) * TILE_ROWS;
+      // ---- layer 1 --------------------------------------------------------------------------
+      mbar_wait(mb_full, it & 1u);
+      if (tid == 0) {
+        tc_fence_after();
+        issue_layer(d1, smem_u32(ra0), TILE_ROWS, smem_u32(rw1), p.c1, p.k0pad >> 4,
+                    umma_idesc(128, p.c1));
+        umma_commit(mb_free);  // A0 may be refilled as soon as these MMAs have completed
+        umma_commit(mb_mma);
+      }
+      mbar_wait(mb_mma, mma_phase);
+      mma_phase ^= 1;
+      tc_fence_after();
+      if (p.w_shared) {  // W1 is dead: bring W3 into the shared weight region
+        copy_image(rw3, p.w3, w3_bytes, tid, NCOMPUTE);
+      }
+      epilogue_to_operand(d1, warp, p.c1, bias1, ra12, row);
+      fence_async_smem();
+      tc_fence_before();
+      named_bar_sync(1, NCOMPUTE);
+      // ---- layer 2 --------------------------------------------------------------------------
+      if (tid == 0) {
+        tc_fence_after();
+        issue_layer(d2, smem_u32(ra12), TILE_ROWS, smem_u32(rw2), p.c2, p.c1 >> 4,
+                    umma_idesc(128, p.c2));
+        umma_commit(mb_mma);
+      }
+      mbar_wait(mb_mma, mma_phase);
+      mma_phase ^= 1;
+      tc_fence_after();
+      epilogue_to_operand(d2, warp, p.c2, bias2, ra12, row);  // A2 overwrites A1 (layer 2 is done)
+      fence_async_smem();
+      tc_fence_before();
+      named_bar_sync(1, NCOMPUTE);
+      // ---- layer 3, transposed: D3^T[c3 x 128 rows] = W3 * A2^T ------------------------------
+      if (tid == 0) {
+        tc_fence_after();
+        for (int blk = 0; blk < (p.c3 >> 7); ++blk)
+          issue_layer(d3 + (unsigned)(blk * 128), smem_u32(rw3) + (unsigned)(blk * 128 * 128), p.c3,
+                      smem_u32(ra12), TILE_ROWS, p.c2 >> 4, umma_idesc(128, 128));
+        umma_commit(mb_mma);
+      }
+      mbar_wait(mb_mma, mma_phase);
+      mma_phase ^= 1;
+      tc_fence_after();
+      if (p.w_shared && tile + (int)gridDim.x < ntiles) {  // W3 is dead: W1 back for the next tile
+        copy_image(rw1, p.w1, w1_bytes, tid, NCOMPUTE);
+      }
+      for (int blk = 0; blk < (p.c3 >> 7); ++blk) {
+        const int ch = blk * 128 + row;
+        const float t = __ldg(bias3 + ch);
+        float *o = p.out + ((size_t)bi * p.c3 + ch) * p.m + (row0 >> lg_ns);
+        float gmax = -3.0e38f;
+        // max over the raw accumulators first (bias + ReLU are monotone, applied once per group)
+        for (int c0 = 0; c0 < TILE_ROWS; c0 += 64) {
+          unsigned v[2][32];
+          const unsigned base = d3 + (unsigned)(blk * 128) + ((unsigned)(warp * 32) << 16) + (unsigned)c0;
+          tmem_ld32_issue(base, v[0]);
+          tmem_ld32_issue(base + 32u, v[1]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int h16 = 0; h16 < 4; ++h16) {
+            gmax = fmaxf(gmax, max16(&v[h16 >> 1][(h16 & 1) * 16]));
+            const int cend = c0 + h16 * 16 + 16;  // nsample >= 16: groups end on 16-column bounds
+            if ((cend & (p.nsample - 1)) == 0) {
+              o[(cend - 1) >> lg_ns] = fmaxf(gmax + t, 0.f);
+              gmax = -3.0e38f;
+            }
           }
         }
       }
+      fence_async_smem();
+      tc_fence_before();
+      named_bar_sync(1, NCOMPUTE);  // TMEM and A1/A2 are free for the next tile
     }
-    tc_fence_before();
-    __syncthreads();  // TMEM and the operand regions are free for the next tile
   }
 
   __syncthreads();
@@ -377,7 +436,7 @@ __global__ void __launch_bounds__(256) pack_table_kernel(int c, int n, int c8,
 
 size_t smem_need(int k0pad, int c1, int c2, int c3, int w_shared) {
   const int nslab0 = (k0pad + 63) >> 6, nslab1 = c1 >> 6, nslab2 = c2 >> 6;
-  size_t s = (size_t)(nslab0 > nslab1 ? nslab0 : nslab1) * SLAB_BYTES + (size_t)nslab2 * SLAB_BYTES;
+  size_t s = (size_t)nslab0 * SLAB_BYTES + (size_t)(nslab1 > nslab2 ? nslab1 : nslab2) * SLAB_BYTES;
   s += (size_t)nslab1 * c2 * 128;
   const size_t w1 = (size_t)nslab0 * c1 * 128, w3 = (size_t)nslab2 * c3 * 128;
   s += w_shared ? (w1 > w3 ? w1 : w3) : w1 + w3;
@@ -443,9 +502,14 @@ extern "C" int nesie_sa_fused_forward(int b, int n, int npoints, int nsample, in
   NESIE_CUDA(cudaFuncSetAttribute(sa_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
   const long long ntiles = (long long)b * npoints * nsample / TILE_ROWS;
-  int grid = num_sms();
-  // small layers (<= 110 KB of smem, 256 TMEM columns) can co-host two CTAs per SM
-  if (smem <= 110 * 1024 && p.tmem_cols <= 256) grid *= 2;
+  int per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sa_fused_kernel, THREADS, smem) !=
+          cudaSuccess || per_sm < 1) {
+    cudaGetLastError();
+    per_sm = 1;
+  }
+  if (per_sm * p.tmem_cols > 512) per_sm = 512 / p.tmem_cols;  // TMEM columns are per SM
+  int grid = num_sms() * per_sm;
   if (ntiles < grid) grid = (int)ntiles;
   sa_fused_kernel<<<grid, THREADS, smem, (cudaStream_t)stream>>>(p);
   return check_launch("nesie_sa_fused_forward");
