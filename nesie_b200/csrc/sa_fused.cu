@@ -33,7 +33,7 @@ namespace {
 
 constexpr int TILE_ROWS = 128;
 constexpr int SLAB_BYTES = TILE_ROWS * 128;  // one 64-channel K-block of a 128-row operand
-constexpr int THREADS = 256;
+constexpr int THREADS = 384;
 
 struct SaParams {
   int b, n, m, nsample;
@@ -181,28 +181,28 @@ __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-constexpr int NCOMPUTE = 128;  // warps 0-3: MMA issue + epilogues (thread = TMEM lane)
-constexpr int NGATHER = 128;   // warps 4-7: build the next tile's A operand
+constexpr int NCOMPUTE = 256;  // warps 0-7: MMA issue + epilogues (2 warps per TMEM lane quarter)
+constexpr int NGATHER = 128;   // warps 8-11: build the next tile's A operand
 
-// Layer-1/2 epilogue: TMEM accumulator row (all `cout` channels of this thread's row) -> + bias
-// -> ReLU -> bf16 -> the next layer's A operand in shared memory (BN scale is folded into W).
-// Two x32 TMEM loads are in flight per wait.
-__device__ __forceinline__ void epilogue_to_operand(unsigned d_tmem, int warp, int cout,
-                                                    const float *__restrict__ bias,
-                                                    unsigned char *dst, int row) {
-  for (int c0 = 0; c0 < cout; c0 += 64) {
-    unsigned v[2][32];
-    const unsigned base = d_tmem + ((unsigned)(warp * 32) << 16) + (unsigned)c0;
-    tmem_ld32_issue(base, v[0]);
-    tmem_ld32_issue(base + 32u, v[1]);
-    tmem_ld_wait();
+// Layer-1/2 epilogue: `ncols` (32 or 64) accumulator columns starting at col0 of this thread's row
+// -> + bias (shared memory, broadcast) -> ReLU -> bf16 -> the next layer's A operand in shared
+// memory (BN scale is folded into W).  Both x32 TMEM loads are in flight before the single wait.
+__device__ __forceinline__ void epilogue_to_operand(unsigned d_tmem, int q, int col0, int ncols,
+                                                    const float *s_bias, unsigned char *dst,
+                                                    int row) {
+  unsigned v[2][32];
+  const unsigned base = d_tmem + ((unsigned)(q * 32) << 16) + (unsigned)col0;
+  tmem_ld32_issue(base, v[0]);
+  if (ncols > 32) tmem_ld32_issue(base + 32u, v[1]);
+  tmem_ld_wait();
 #pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
+  for (int hh = 0; hh < 2; ++hh) {
+    if (hh * 32 < ncols) {
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        const int cc = c0 + hh * 32 + g * 8;
-        const float4 b0 = __ldg(reinterpret_cast<const float4 *>(bias + cc));
-        const float4 b1 = __ldg(reinterpret_cast<const float4 *>(bias + cc + 4));
+        const int cc = col0 + hh * 32 + g * 8;
+        const float4 b0 = *reinterpret_cast<const float4 *>(s_bias + cc);
+        const float4 b1 = *reinterpret_cast<const float4 *>(s_bias + cc + 4);
         const unsigned *u = &v[hh][g * 8];
         const unsigned w0 = pack_bf16(fmaxf(__uint_as_float(u[0]) + b0.x, 0.f), fmaxf(__uint_as_float(u[1]) + b0.y, 0.f));
         const unsigned w1 = pack_bf16(fmaxf(__uint_as_float(u[2]) + b0.z, 0.f), fmaxf(__uint_as_float(u[3]) + b0.w, 0.f));
@@ -222,7 +222,7 @@ __device__ __forceinline__ float max16(const unsigned *u) {
   return fmaxf(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)), fmaxf(fmaxf(m4, m5), fmaxf(m6, m7)));
 }
 
-// Warp-specialised: warps 4-7 gather tile t+1 into A0 while warps 0-3 run the three layers of
+// Warp-specialised: warps 8-11 gather tile t+1 into A0 while warps 0-7 run the three layers of
 // tile t.  A0 is released to the gatherers by a tcgen05.commit as soon as layer 1 has consumed it;
 // A1 and A2 share one buffer (A2 is written after layer 2 has finished reading A1).
 __global__ void __launch_bounds__(THREADS, 1) sa_fused_kernel(SaParams p) {
@@ -232,6 +232,7 @@ __global__ void __launch_bounds__(THREADS, 1) sa_fused_kernel(SaParams p) {
   __shared__ __align__(8) unsigned long long s_mbar[3];  // 0: mma done, 1: A0 full, 2: A0 free
   __shared__ unsigned s_tmem;
   __shared__ int s_idx[TILE_ROWS];
+  __shared__ __align__(16) float s_bias12[256];  // layer-1 and layer-2 biases (c1, c2 <= 128)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nslab0 = (p.k0pad + 63) >> 6;
@@ -257,6 +258,8 @@ __global__ void __launch_bounds__(THREADS, 1) sa_fused_kernel(SaParams p) {
     mbar_init(smem_u32(&s_mbar[2]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (tid < p.c1) s_bias12[tid] = p.bias[tid];
+  if (tid < p.c2) s_bias12[128 + tid] = p.bias[p.c1 + tid];
   copy_image(rw2, p.w2, nslab1 * p.c2 * 128, tid);
   copy_image(rw1, p.w1, w1_bytes, tid);  // shared mode: valid for the first tile
   if (!p.w_shared) copy_image(rw3, p.w3, w3_bytes, tid);
@@ -268,14 +271,14 @@ __global__ void __launch_bounds__(THREADS, 1) sa_fused_kernel(SaParams p) {
   const unsigned d1 = tmem, d2 = tmem + (unsigned)p.c1, d3 = tmem + (unsigned)(p.c1 + p.c2);
   const unsigned mb_mma = smem_u32(&s_mbar[0]), mb_full = smem_u32(&s_mbar[1]),
                  mb_free = smem_u32(&s_mbar[2]);
-  const float *bias1 = p.bias, *bias2 = bias1 + p.c1, *bias3 = bias2 + p.c2;
+  const float *bias3 = p.bias + p.c1 + p.c2;
 
   const int rows_per_scene = p.m * p.nsample;
   const int tiles_per_scene = rows_per_scene / TILE_ROWS;
   const int ntiles = p.b * tiles_per_scene;
   const int lg_ns = 31 - __clz(p.nsample);
 
-  if (warp >= 4) {
+  if (warp >= NCOMPUTE / 32) {
     // =========================== gather warps ===============================================
     const int gt = tid - NCOMPUTE;
     const int nfc = p.cfeat8 >> 3;  // feature chunks per row; chunk nfc is the xyz chunk
@@ -326,7 +329,8 @@ __global__ void __launch_bounds__(THREADS, 1) sa_fused_kernel(SaParams p) {
     }
   } else {
     // =========================== compute warps ==============================================
-    const int row = tid;  // TMEM lane of this thread (warp w owns lanes 32w..32w+31)
+    const int q = warp & 3, half = warp >> 2;
+    const int row = q * 32 + lane;  // TMEM lane of this thread (warp w owns lanes 32(w%4)..+31)
     unsigned it = 0, mma_phase = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int bi = tile / tiles_per_scene;
@@ -346,7 +350,7 @@ __global__ void __launch_bounds__(THREADS, 1) sa_fused_kernel(SaParams p) {
       if (p.w_shared) {  // W1 is dead: bring W3 into the shared weight region
         copy_image(rw3, p.w3, w3_bytes, tid, NCOMPUTE);
       }
-      epilogue_to_operand(d1, warp, p.c1, bias1, ra12, row);
+      epilogue_to_operand(d1, q, half * (p.c1 >> 1), p.c1 >> 1, s_bias12, ra12, row);
       fence_async_smem();
       tc_fence_before();
       named_bar_sync(1, NCOMPUTE);
@@ -360,7 +364,7 @@ __global__ void __launch_bounds__(THREADS, 1) sa_fused_kernel(SaParams p) {
       mbar_wait(mb_mma, mma_phase);
       mma_phase ^= 1;
       tc_fence_after();
-      epilogue_to_operand(d2, warp, p.c2, bias2, ra12, row);  // A2 overwrites A1 (layer 2 is done)
+      epilogue_to_operand(d2, q, half * (p.c2 >> 1), p.c2 >> 1, s_bias12 + 128, ra12, row);  // A2 over A1
       fence_async_smem();
       tc_fence_before();
       named_bar_sync(1, NCOMPUTE);
@@ -378,22 +382,27 @@ __global__ void __launch_bounds__(THREADS, 1) sa_fused_kernel(SaParams p) {
       if (p.w_shared && tile + (int)gridDim.x < ntiles) {  // W3 is dead: W1 back for the next tile
         copy_image(rw1, p.w1, w1_bytes, tid, NCOMPUTE);
       }
-      for (int blk = 0; blk < (p.c3 >> 7); ++blk) {
+      {
+        // c3 == 256: warps 0-3 take channel block 0, warps 4-7 block 1 (128 columns each);
+        // c3 == 128: the two warp groups split the 128 columns (rows of the tile) in halves.
+        const int blk = (p.c3 == 256) ? half : 0;
+        const int col_beg = (p.c3 == 256) ? 0 : half * 64;
+        const int nld = (p.c3 == 256) ? 4 : 2;
         const int ch = blk * 128 + row;
         const float t = __ldg(bias3 + ch);
         float *o = p.out + ((size_t)bi * p.c3 + ch) * p.m + (row0 >> lg_ns);
         float gmax = -3.0e38f;
         // max over the raw accumulators first (bias + ReLU are monotone, applied once per group)
-        for (int c0 = 0; c0 < TILE_ROWS; c0 += 64) {
+        const unsigned base = d3 + (unsigned)(blk * 128 + col_beg) + ((unsigned)(q * 32) << 16);
+        for (int pr = 0; pr < nld; pr += 2) {
           unsigned v[2][32];
-          const unsigned base = d3 + (unsigned)(blk * 128) + ((unsigned)(warp * 32) << 16) + (unsigned)c0;
-          tmem_ld32_issue(base, v[0]);
-          tmem_ld32_issue(base + 32u, v[1]);
+          tmem_ld32_issue(base + (unsigned)(pr * 32), v[0]);
+          tmem_ld32_issue(base + (unsigned)(pr * 32 + 32), v[1]);
           tmem_ld_wait();
 #pragma unroll
           for (int h16 = 0; h16 < 4; ++h16) {
             gmax = fmaxf(gmax, max16(&v[h16 >> 1][(h16 & 1) * 16]));
-            const int cend = c0 + h16 * 16 + 16;  // nsample >= 16: groups end on 16-column bounds
+            const int cend = col_beg + pr * 32 + h16 * 16 + 16;  // nsample >= 16: 16-col bounds
             if ((cend & (p.nsample - 1)) == 0) {
               o[(cend - 1) >> lg_ns] = fmaxf(gmax + t, 0.f);
               gmax = -3.0e38f;
