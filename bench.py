@@ -91,7 +91,8 @@ def cpu_reference_step_rate(steps, warmup, scenes=SCENES_PER_GPU):
     from oracle.votenet_ref import VoteNetOracle
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    from oracle import cpu as oracle_cpu
+    oracle_cpu.set_threads(cores)  # torchrun exports OMP_NUM_THREADS=1
     torch.manual_seed(0)
     model = VoteNetOracle()
     opt = torch.optim.AdamW(model.parameters(), lr=0.008, weight_decay=0.01)
@@ -164,39 +165,69 @@ def main():
 
     torch.manual_seed(0)
     model = VoteNetHarness().to(dev)
-    net = model
-    if world > 1:
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local],
-                                                        broadcast_buffers=False)
-    opt = torch.optim.AdamW(model.parameters(), lr=0.008, weight_decay=0.01, fused=True)
+    params = [p for p in model.parameters()]
+    # one flat gradient buffer (every p.grad is a view): the DDP exchange of this path is ONE NCCL
+    # all-reduce over it per step, issued inside the step so that it is graph-capturable
+    flat_grad = torch.zeros(sum(p.numel() for p in params), device=dev)
+    off = 0
+    for p in params:
+        p.grad = flat_grad[off:off + p.numel()].view_as(p)
+        off += p.numel()
+    if world > 1:  # identical replicas to start from
+        for t in list(model.parameters()) + list(model.buffers()):
+            dist.broadcast(t.data, 0)
+    opt = torch.optim.AdamW(params, lr=0.008, weight_decay=0.01, fused=True, capturable=True)
 
     # a pool of distinct batches (so no step re-reads the previous step's inputs from L2)
-    NB = 4
+    NB, G = 4, 16
     host = [make_batch(SCENES_PER_GPU, N_POINTS, seed0=1000 * rank + 100 * i) for i in range(NB)]
     host_pts = [h[0].pin_memory() for h in host]
-    gts = [([b.to(dev) for b in h[1]], [l.to(dev) for l in h[2]]) for h in host]
+    padded = [model._pad_gt(h[1], h[2], torch.device("cpu"), pad_to=G) for h in host]
+    host_gt = [tuple(t.pin_memory() for t in pg) for pg in padded]
     dev_pts = [p.to(dev) for p in host_pts]
+    dev_gt = [tuple(t.to(dev) for t in pg) for pg in host_gt]
+    # static step inputs (CUDA-graph replay reads these addresses)
+    s_pts = torch.empty_like(dev_pts[0])
+    s_gt = tuple(torch.empty_like(t) for t in dev_gt[0])
+    s_loss = torch.zeros((), device=dev)
 
-    class Step(torch.nn.Module):  # DDP wraps forward(); loss is computed inside it
-        def __init__(self, m):
-            super().__init__()
-            self.m = m
-
-        def forward(self, pts, gb, gl):
-            return self.m.train_step_loss(pts, gb, gl)[0]
-
-    step_mod = Step(model)
-    if world > 1:
-        step_mod = torch.nn.parallel.DistributedDataParallel(step_mod, device_ids=[local],
-                                                             broadcast_buffers=False)
-
-    def one_step(pts, gt):
-        opt.zero_grad(set_to_none=True)
-        loss = step_mod(pts, gt[0], gt[1])
+    def step_body():
+        flat_grad.zero_()
+        loss, _ = model.train_step_loss_padded(s_pts, *s_gt)
         loss.backward()
-        torch.nn.utils.clip_grad_norm_(model.parameters(), 10.0)
+        if world > 1:
+            dist.all_reduce(flat_grad)
+            flat_grad.div_(world)
+        torch.nn.utils.clip_grad_norm_(params, 10.0)
         opt.step()
-        return loss
+        s_loss.copy_(loss.detach())
+
+    def load_inputs(pts, gt):
+        s_pts.copy_(pts, non_blocking=True)
+        for d, t in zip(s_gt, gt):
+            d.copy_(t, non_blocking=True)
+
+    # warm up eagerly on a side stream (also initialises NCCL), then capture the step once
+    load_inputs(dev_pts[0], dev_gt[0])
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            step_body()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph, mode = None, "eager"
+    if os.environ.get("NESIE_BENCH_GRAPH", "1") != "0":
+        try:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                step_body()
+            mode = "cuda_graph"
+        except Exception as e:  # noqa: BLE001 -- fall back to eager launches
+            graph = None
+            torch.cuda.synchronize()
+            sys.stderr.write(f"[bench] CUDA-graph capture failed, running eagerly: {e!r}\n")
+    run_step = graph.replay if graph is not None else step_body
 
     def barrier():
         if world > 1:
@@ -219,30 +250,39 @@ def main():
         return ms
 
     # ---- device-resident throughput -----------------------------------------------------------
+    def resident_step(i):
+        load_inputs(dev_pts[i % NB], dev_gt[i % NB])  # device -> device
+        run_step()
+
     for i in range(W):
-        one_step(dev_pts[i % NB], gts[i % NB])
+        resident_step(i)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     launches0 = _lib.LAUNCHES
-    ms = timed(lambda i: one_step(dev_pts[i % NB], gts[i % NB]), K)
+    ms = timed(resident_step, K)
     launches = _lib.LAUNCHES - launches0
+    if graph is not None:  # replayed launches are not counted by the python-side counter
+        l0 = _lib.LAUNCHES
+        with torch.cuda.stream(side):
+            step_body()
+        torch.cuda.synchronize()
+        launches = (_lib.LAUNCHES - l0) * K
     clocks = sampler.stop() if rank == 0 else None
     value = world * SCENES_PER_GPU * K / (ms / 1e3)
 
     # ---- end to end: pinned host -> device every step, loss read back every step ---------------
-    stage = torch.empty_like(dev_pts[0])
     sink = torch.zeros(1).pin_memory()
 
     def e2e_step(i):
-        stage.copy_(host_pts[i % NB], non_blocking=True)
-        loss = one_step(stage, gts[i % NB])
-        sink.copy_(loss.detach().reshape(1), non_blocking=False)
+        load_inputs(host_pts[i % NB], host_gt[i % NB])  # pinned host -> device
+        run_step()
+        sink.copy_(s_loss.reshape(1), non_blocking=False)  # device -> host, synchronises
 
     e2e_step(0)
     ms_e2e = timed(e2e_step, K)
     e2e_value = world * SCENES_PER_GPU * K / (ms_e2e / 1e3)
-    h2d = host_pts[0].numel() * 4
+    h2d = host_pts[0].numel() * 4 + sum(t.numel() * t.element_size() for t in host_gt[0])
     final_loss = float(sink[0])
 
     # ---- dominant hand-written kernel, timed live ---------------------------------------------
@@ -276,7 +316,8 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "scenes_per_gpu": SCENES_PER_GPU, "points": N_POINTS,
                        "classes": 18, "parallelism": f"dp{world}",
-                       "l2": "4 distinct resident batches cycled; per-step activations exceed L2"},
+                       "l2": "4 distinct resident batches cycled; per-step activations exceed L2",
+                       "launch": mode},
             "e2e": {"value": e2e_value, "unit": "scenes/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / K},
             "gpu_launches": launches, "roofline": roofline, "clocks": clocks,
@@ -288,8 +329,13 @@ def main():
                                           f"AdamW, 1 step after 1 warm-up ({sec:.2f} s/step)"}
     if rank == 0:
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    # Tear down without NCCL/graph destructors: a captured graph that holds an NCCL all-reduce can
+    # make destroy_process_group() hang at exit.  Everything is flushed and synchronised first.
+    sys.stdout.flush()
+    sys.stderr.flush()
+    del graph
+    barrier()
+    os._exit(0)
 
 
 if __name__ == "__main__":

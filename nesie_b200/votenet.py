@@ -75,6 +75,7 @@ class VoteNetHarness(nn.Module):
         self.conv_reg = nn.Conv1d(128, 6 * (REG_MAX + 1), 1)
         self.conv_quality = nn.Conv1d(128, num_classes + 6 * num_classes, 1)
         self.register_buffer('bins', torch.linspace(0, 1, REG_MAX + 1))
+        self.register_buffer('obj_class_weight', torch.tensor([0.2, 0.8]))
         self.max_side = 3.0  # a side lies within 3 m of its proposal point
 
     # ---- hot-path hooks (overridden by the CPU oracle harness) --------------------------------
@@ -111,8 +112,12 @@ class VoteNetHarness(nn.Module):
 
     # ---- targets + losses ---------------------------------------------------------------------
     @staticmethod
-    def _pad_gt(gt_boxes, gt_labels, device):
+    def _pad_gt(gt_boxes, gt_labels, device, pad_to=None):
+        """Per-scene GT lists -> padded (B,G,7) boxes, (B,G) labels, (B,G) validity mask."""
         G = max(b.shape[0] for b in gt_boxes)
+        if pad_to is not None:
+            assert pad_to >= G
+            G = pad_to
         B = len(gt_boxes)
         boxes = torch.zeros(B, G, 7, device=device)
         labels = torch.zeros(B, G, dtype=torch.long, device=device)
@@ -125,7 +130,10 @@ class VoteNetHarness(nn.Module):
 
     def loss(self, preds, gt_boxes, gt_labels):
         dev = preds['seed_points'].device
-        boxes, labels, valid = self._pad_gt(gt_boxes, gt_labels, dev)
+        return self.loss_padded(preds, *self._pad_gt(gt_boxes, gt_labels, dev))
+
+    def loss_padded(self, preds, boxes, labels, valid):
+        """Losses from pre-padded GT tensors (static shapes: usable under CUDA-graph capture)."""
         gc, gs = boxes[..., :3], boxes[..., 3:6]
         big = 1e6
 
@@ -147,7 +155,7 @@ class VoteNetHarness(nn.Module):
         obj_w = obj_w / (obj_w.sum() + 1e-6)
         box_w = obj_tgt.float() / (obj_tgt.float().sum() + 1e-6)
         objectness_loss = 5.0 * (F.cross_entropy(preds['obj_scores'].transpose(2, 1), obj_tgt,
-                                                 weight=preds['obj_scores'].new_tensor([0.2, 0.8]),
+                                                 weight=self.obj_class_weight,
                                                  reduction='none') * obj_w).sum()
         # centre loss: chamfer (l2) between predicted and GT centres
         pc = preds['bbox_preds'][..., :3]
@@ -184,11 +192,18 @@ class VoteNetHarness(nn.Module):
         losses = self.loss(self.forward(points), gt_boxes, gt_labels)
         return sum(losses.values()), losses
 
+    def train_step_loss_padded(self, points, boxes, labels, valid):
+        losses = self.loss_padded(self.forward(points), boxes, labels, valid)
+        return sum(losses.values()), losses
+
 
 def aligned_iou(a, b):
     """IoU of axis-aligned (cx,cy,cz,sx,sy,sz,·) boxes, row-wise."""
     amin, amax = a[:, :3] - 0.5 * a[:, 3:6], a[:, :3] + 0.5 * a[:, 3:6]
     bmin, bmax = b[:, :3] - 0.5 * b[:, 3:6], b[:, :3] + 0.5 * b[:, 3:6]
-    inter = (torch.min(amax, bmax) - torch.max(amin, bmin)).clamp(min=0).prod(-1)
-    union = (amax - amin).clamp(min=0).prod(-1) + (bmax - bmin).clamp(min=0).prod(-1) - inter
+    def vol(e):  # explicit product: Tensor.prod's backward synchronises with the host
+        e = e.clamp(min=0)
+        return e[:, 0] * e[:, 1] * e[:, 2]
+    inter = vol(torch.min(amax, bmax) - torch.max(amin, bmin))
+    union = vol(amax - amin) + vol(bmax - bmin) - inter
     return inter / (union + 1e-8)

@@ -29,6 +29,10 @@ def lib():
     return _lib
 
 
+def set_threads(n):
+    lib().nesie_oracle_set_threads(int(n))
+
+
 def _p(t):
     return ctypes.c_void_p(t.data_ptr())
 

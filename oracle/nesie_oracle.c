@@ -23,6 +23,18 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* torchrun exports OMP_NUM_THREADS=1; the bench sets the thread count explicitly. */
+void nesie_oracle_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
 
 /* furthest_point_sample_cuda.cu:11-15 -- block size the reference launcher picks. */
 int nesie_oracle_opt_n_threads(int work_size) {
