@@ -225,6 +225,21 @@ int nesie_sa_fused_forward(int b, int n, int npoints, int nsample, int c_in, int
                            const void *w1_img, const void *w2_img, const void *w3_img,
                            const float *bias, float *out, void *stream);
 
+/* ---------------------------------------------------------------------------------------
+ * fp32-accurate row GEMM on tcgen05 (kind::tf32, 3xTF32 split, fp32 TMEM accumulation):
+ *   C[r x n] = A[r x k] * B[n x k]^T,  A/C row-major fp32 with leading dimensions lda/ldc.
+ * The training-mode shared MLP of the SA / FP modules (the reference's cuDNN 1x1 Conv2d,
+ * ops/pointnet_modules/point_sa_module.py:279-288): forward Y = X W^T and dX = dY W.
+ * B (the small operand, n <= 256) is pre-split into TF32 hi/lo parts and pre-swizzled by
+ * nesie_gemm_pack_b into an image of nesie_gemm_b_image_bytes(n, k) bytes; element (i, j) of B is
+ * read from b[i*stride_n + j*stride_k], so W and W^T pack without a transpose.
+ */
+long long nesie_gemm_b_image_bytes(int n, int k);
+int nesie_gemm_pack_b(int n, int k, long long stride_n, long long stride_k, const float *b,
+                      void *image, void *stream);
+int nesie_gemm_nt_3xtf32(long long r, int n, int k, const float *a, long long lda,
+                         const void *b_image, float *c, long long ldc, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,6 +35,9 @@ SIGNATURES = {
     "nesie_side_uncertainty_loss": [_i, _i, _p, _p, _p, _p, _p, _f, _f, _p, _p, _p],
     "nesie_side_uncertainty_loss_grad": [_i, _i, _p, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p],
     "nesie_ema_update": [_ll, _p, _p, _f, _f, _p],
+    "nesie_gemm_b_image_bytes": [_i, _i],
+    "nesie_gemm_pack_b": [_i, _i, _ll, _ll, _p, _p, _p],
+    "nesie_gemm_nt_3xtf32": [_ll, _i, _i, _p, _ll, _p, _p, _ll, _p],
     "nesie_sa_fused_supported": [_i, _i, _i, _i, _i],
     "nesie_pack_features_bf16": [_i, _i, _i, _p, _p, _p],
     "nesie_sa_fused_forward": [_i] * 8 + [_p, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p],
@@ -55,7 +58,7 @@ def lib():
         for name, argtypes in SIGNATURES.items():
             fn = getattr(handle, name)
             fn.argtypes = argtypes
-            fn.restype = _ll if name.endswith('_workspace') else _i
+            fn.restype = _ll if name.endswith(('_workspace', '_bytes')) else _i
         handle.nesie_last_error.restype = ctypes.c_char_p
         handle.nesie_last_error.argtypes = []
         _lib = handle

@@ -1,0 +1,351 @@
+// fp32-accurate row GEMM on the 5th-generation tensor cores (tcgen05, kind::tf32, 3xTF32 split).
+//
+//   C[R x N] = A[R x K] * B[N x K]^T        A, B, C fp32;  R ~ 10^5..10^6 rows,  N, K <= 288
+//
+// This is the shared-MLP GEMM of the SA / FP modules in TRAINING (the reference runs it as cuDNN
+// 1x1 Conv2d, ops/pointnet_modules/point_sa_module.py:279-288): forward Y = X W^T and the data
+// gradient dX = dY W.  Parity with the fp32 reference has to hold at 1e-5, which a single TF32 MMA
+// (10-bit mantissa) cannot give, so every operand is split x = hi + lo with hi = x truncated to TF32
+// and the product is accumulated as  hi*hi + hi*lo + lo*hi  in the fp32 TMEM accumulator (the
+// dropped lo*lo term is 2^-22 relative).  That is 3 tensor-core MMAs per fp32 MMA -- still an order
+// of magnitude above the SIMT sgemm cuBLAS selects for strict fp32.
+//
+// Structure (one persistent CTA per SM, 672 threads):
+//   warps 4-19 loaders : four groups of 128 threads, each filling every fourth pipeline stage; A tile rows (fp32, coalesced float4) -> hi/lo -> UMMA K-major SWIZZLE_128B
+//                        slabs of 32 K-elements; the pre-split, pre-swizzled B image arrives by one
+//                        cp.async.bulk per part, counted on the same mbarrier
+//   warp  20   MMA     : 4 K-steps x 3 tcgen05.mma per slab, tcgen05.commit frees the stage; the
+//                        last commit of a tile publishes the accumulator
+//   warps 0-3  epilogue: tcgen05.ld -> float4 stores to C; two TMEM accumulators so the epilogue of
+//                        tile t overlaps the MMAs of tile t+1
+#include "common.cuh"
+
+namespace nesie {
+namespace {
+
+constexpr int G_TILE = 128;
+constexpr int G_SLABK = 32;            // fp32 elements per 128-byte swizzle row
+constexpr int G_MAXSTAGES = 4;
+constexpr int G_LGROUPS = 4;                       // loader groups of 128 threads (stage it -> group it % 4)
+constexpr int G_THREADS = 128 + 128 * G_LGROUPS + 32;  // epilogue + loaders + MMA warp
+constexpr int G_ASLAB = G_TILE * 128;  // bytes of one A part-slab
+
+struct GemmParams {
+  int R, N, K;        // logical sizes
+  int npad, nslab;    // N rounded up to 16, K slabs of 32
+  int nstages;        // smem pipeline depth (2..4)
+  long long lda, ldc;
+  const float *A;
+  const unsigned char *Bimg;  // [hi|lo][nslab][npad][128 B]
+  float *C;
+};
+
+__device__ __forceinline__ unsigned g_smem_u32(const void *p) {
+  return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ unsigned long long g_desc(unsigned smem_addr) {
+  return (unsigned long long)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) |
+         (1ull << 46) | (2ull << 61);
+}
+// kind::tf32: D = f32 (c_format 1), A = B = TF32 (format 2), K-major, M x N
+__host__ __device__ constexpr unsigned g_idesc(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(N >> 3) << 17) | ((unsigned)(M >> 4) << 24);
+}
+__device__ __forceinline__ void g_mma(unsigned d, unsigned long long a, unsigned long long b,
+                                      unsigned idesc, unsigned acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void g_commit(unsigned mbar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar)
+               : "memory");
+}
+__device__ __forceinline__ void g_mbar_init(unsigned mbar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void g_mbar_arrive(unsigned mbar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void g_mbar_expect_tx(unsigned mbar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void g_mbar_wait(unsigned mbar, unsigned parity) {
+  unsigned ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(mbar), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void g_bulk_g2s(unsigned dst, const void *src, unsigned bytes,
+                                           unsigned mbar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar)
+      : "memory");
+}
+__device__ __forceinline__ void g_tmem_ld32(unsigned taddr, unsigned (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+
+// x = hi + lo, hi = x with the 13 low mantissa bits cleared (exactly representable in TF32)
+__device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
+  hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  lo = x - hi;
+}
+
+__global__ void __launch_bounds__(G_THREADS, 1) gemm_nt_3xtf32_kernel(GemmParams p) {
+  extern __shared__ unsigned char g_smem_dyn[];
+  unsigned char *smem = reinterpret_cast<unsigned char *>(
+      (reinterpret_cast<uintptr_t>(g_smem_dyn) + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) unsigned long long s_full[G_MAXSTAGES], s_empty[G_MAXSTAGES], s_accf[2], s_acce[2];
+  __shared__ unsigned s_tmem;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int bslab = p.npad * 128;                       // bytes of one B part-slab
+  const int stage_bytes = 2 * G_ASLAB + 2 * bslab;      // A hi, A lo, B hi, B lo
+  const int ntiles = (p.R + G_TILE - 1) / G_TILE;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     g_smem_u32(&s_tmem)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    for (int s = 0; s < p.nstages; ++s) {
+      g_mbar_init(g_smem_u32(&s_full[s]), 128 + 1);  // 128 loader arrivals + the expect_tx arrive
+      g_mbar_init(g_smem_u32(&s_empty[s]), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      g_mbar_init(g_smem_u32(&s_accf[a]), 1);
+      g_mbar_init(g_smem_u32(&s_acce[a]), 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const unsigned tmem = s_tmem;
+
+  if (warp >= 4 && warp < 4 + 4 * G_LGROUPS) {
+    // ================================ loaders ================================================
+    // Bandwidth = bytes in flight / latency: one group only keeps 16 KB of loads in flight per SM
+    // (~2.4 TB/s chip-wide); four groups working on four consecutive stages keep 64 KB.
+    const int lg = (warp - 4) >> 2;
+    const int lt = (tid - 128) & 127;
+    unsigned it = 0;  // global stage counter
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const long long row0 = (long long)tile * G_TILE;
+      for (int ks = 0; ks < p.nslab; ++ks, ++it) {
+        // a group owns pipeline stage `lg` outright (groups beyond the stage count stay idle):
+        // mbarrier parity waits cannot tell phases two apart, so a stage must never be shared
+        if (lg >= p.nstages || (int)(it % p.nstages) != lg) continue;
+        const int st = it % p.nstages;
+        const unsigned ph = (it / p.nstages) & 1u;
+        unsigned char *sa_hi = smem + (size_t)st * stage_bytes;
+        unsigned char *sa_lo = sa_hi + G_ASLAB;
+        unsigned char *sb = sa_lo + G_ASLAB;
+        g_mbar_wait(g_smem_u32(&s_empty[st]), ph ^ 1u);
+        if (lt == 0) {
+          g_mbar_expect_tx(g_smem_u32(&s_full[st]), 2u * (unsigned)bslab);
+          g_bulk_g2s(g_smem_u32(sb), p.Bimg + (size_t)ks * bslab, (unsigned)bslab,
+                     g_smem_u32(&s_full[st]));
+          g_bulk_g2s(g_smem_u32(sb + bslab), p.Bimg + (size_t)(p.nslab + ks) * bslab,
+                     (unsigned)bslab, g_smem_u32(&s_full[st]));
+        }
+        // A slab: 128 rows x 8 chunks of 4 floats; thread lt owns chunk (lt & 7) of rows lt>>3 + 16j
+        const int c = lt & 7;
+        const int k0 = ks * G_SLABK + c * 4;
+        float4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int r = (lt >> 3) + 16 * j;
+          const long long gr = row0 + r;
+          v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (gr < p.R) {
+            const float *src = p.A + gr * p.lda + k0;
+            if (k0 + 3 < p.K && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+              v[j] = __ldg(reinterpret_cast<const float4 *>(src));
+            } else {
+              if (k0 + 0 < p.K) v[j].x = __ldg(src + 0);
+              if (k0 + 1 < p.K) v[j].y = __ldg(src + 1);
+              if (k0 + 2 < p.K) v[j].z = __ldg(src + 2);
+              if (k0 + 3 < p.K) v[j].w = __ldg(src + 3);
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int r = (lt >> 3) + 16 * j;
+          float4 hi, lo;
+          split_tf32(v[j].x, hi.x, lo.x);
+          split_tf32(v[j].y, hi.y, lo.y);
+          split_tf32(v[j].z, hi.z, lo.z);
+          split_tf32(v[j].w, hi.w, lo.w);
+          const unsigned off = (unsigned)(r * 128 + ((c ^ (r & 7)) << 4));
+          *reinterpret_cast<float4 *>(sa_hi + off) = hi;
+          *reinterpret_cast<float4 *>(sa_lo + off) = lo;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        g_mbar_arrive(g_smem_u32(&s_full[st]));
+      }
+    }
+  } else if (warp == 4 + 4 * G_LGROUPS) {
+    // ================================ MMA issuer =============================================
+    if (lane == 0) {
+      const unsigned idesc = g_idesc(128, p.npad);
+      unsigned it = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+        const int acc = tcount & 1;
+        const unsigned d = tmem + (unsigned)(acc * 256);
+        g_mbar_wait(g_smem_u32(&s_acce[acc]), ((tcount >> 1) & 1u) ^ 1u);  // epilogue drained it
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int ks = 0; ks < p.nslab; ++ks, ++it) {
+          const int st = it % p.nstages;
+          const unsigned ph = (it / p.nstages) & 1u;
+          g_mbar_wait(g_smem_u32(&s_full[st]), ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const unsigned a_hi = g_smem_u32(smem + (size_t)st * stage_bytes);
+          const unsigned a_lo = a_hi + G_ASLAB;
+          const unsigned b_hi = a_lo + G_ASLAB;
+          const unsigned b_lo = b_hi + (unsigned)bslab;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {  // UMMA_K = 8 tf32 = 32 bytes
+            const unsigned o = (unsigned)k * 32u;
+            g_mma(d, g_desc(a_hi + o), g_desc(b_hi + o), idesc, (ks | k) ? 1u : 0u);
+            g_mma(d, g_desc(a_hi + o), g_desc(b_lo + o), idesc, 1u);
+            g_mma(d, g_desc(a_lo + o), g_desc(b_hi + o), idesc, 1u);
+          }
+          g_commit(g_smem_u32(&s_empty[st]));  // stage reusable once these MMAs have read it
+        }
+        g_commit(g_smem_u32(&s_accf[acc]));    // accumulator complete
+      }
+    }
+  } else if (warp < 4) {
+    // ================================ epilogue ===============================================
+    unsigned tcount = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+      const int acc = tcount & 1;
+      const long long gr = (long long)tile * G_TILE + warp * 32 + lane;
+      g_mbar_wait(g_smem_u32(&s_accf[acc]), (tcount >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      float *crow = p.C + gr * p.ldc;
+      const bool vec = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+      for (int c0 = 0; c0 < p.npad; c0 += 32) {
+        unsigned v[32];
+        g_tmem_ld32(tmem + (unsigned)(acc * 256 + c0) + ((unsigned)(warp * 32) << 16), v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (gr < p.R) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const int cc = c0 + j;
+            if (vec && cc + 3 < p.N) {
+              *reinterpret_cast<float4 *>(crow + cc) =
+                  make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                              __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            } else {
+#pragma unroll
+              for (int t = 0; t < 4; ++t)
+                if (cc + t < p.N) crow[cc + t] = __uint_as_float(v[j + t]);
+            }
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      g_mbar_arrive(g_smem_u32(&s_acce[acc]));
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u)
+                 : "memory");
+}
+
+// B (N x K, element (n,k) at B[n*sn + k*sk]) -> image [hi|lo][nslab][npad][128 B], fp32 split,
+// 16-byte chunk c of row n at chunk position c ^ (n & 7); zero padding for n >= N, k >= K.
+__global__ void __launch_bounds__(256) pack_b_tf32_kernel(int N, int K, int npad, int nslab,
+                                                          long long sn, long long sk,
+                                                          const float *__restrict__ B,
+                                                          float *__restrict__ img) {
+  const int total = nslab * npad * 32;  // elements per part
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int e = i & 31, n = (i >> 5) % npad, s = (i >> 5) / npad;
+    const int k = s * 32 + e;
+    const float x = (n < N && k < K) ? B[n * sn + k * sk] : 0.f;
+    float hi, lo;
+    split_tf32(x, hi, lo);
+    const int chunk = e >> 2, w = e & 3;
+    const size_t off = ((size_t)s * npad + n) * 32 + (size_t)(((chunk ^ (n & 7)) << 2) + w);
+    img[off] = hi;
+    img[(size_t)total + off] = lo;
+  }
+}
+
+}  // namespace
+}  // namespace nesie
+
+using namespace nesie;
+
+extern "C" long long nesie_gemm_b_image_bytes(int n, int k) {
+  if (n <= 0 || k <= 0) return 0;
+  const long long npad = (n + 15) & ~15, nslab = (k + 31) / 32;
+  return 2 * nslab * npad * 128;
+}
+
+extern "C" int nesie_gemm_pack_b(int n, int k, long long stride_n, long long stride_k,
+                                 const float *b, void *image, void *stream) {
+  NESIE_REQUIRE(n >= 1 && n <= 256 && k >= 1, "need 1 <= n <= 256, k >= 1");
+  NESIE_REQUIRE(b && image, "null pointer");
+  const int npad = (n + 15) & ~15, nslab = (k + 31) / 32;
+  const int total = nslab * npad * 32;
+  pack_b_tf32_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      n, k, npad, nslab, stride_n, stride_k, b, reinterpret_cast<float *>(image));
+  return check_launch("nesie_gemm_pack_b");
+}
+
+extern "C" int nesie_gemm_nt_3xtf32(long long r, int n, int k, const float *a, long long lda,
+                                    const void *b_image, float *c, long long ldc, void *stream) {
+  NESIE_REQUIRE(r >= 0 && n >= 1 && n <= 256 && k >= 1, "need r >= 0, 1 <= n <= 256, k >= 1");
+  NESIE_REQUIRE(r < (1LL << 31) - 256, "too many rows");
+  if (r == 0) return NESIE_OK;
+  NESIE_REQUIRE(a && b_image && c, "null pointer");
+  NESIE_REQUIRE((reinterpret_cast<uintptr_t>(b_image) & 15) == 0, "b_image must be 16-byte aligned");
+  GemmParams p;
+  p.R = (int)r; p.N = n; p.K = k;
+  p.npad = (n + 15) & ~15;
+  p.nslab = (k + 31) / 32;
+  p.lda = lda; p.ldc = ldc;
+  p.A = a; p.Bimg = reinterpret_cast<const unsigned char *>(b_image); p.C = c;
+  const size_t stage = 2 * G_ASLAB + 2 * (size_t)p.npad * 128;
+  p.nstages = (int)((226 * 1024) / stage);
+  if (p.nstages > G_MAXSTAGES) p.nstages = G_MAXSTAGES;
+  const size_t smem = (size_t)p.nstages * stage + 1024;
+  NESIE_CUDA(cudaFuncSetAttribute(gemm_nt_3xtf32_kernel,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int ntiles = (p.R + G_TILE - 1) / G_TILE;
+  int grid = num_sms();
+  if (ntiles < grid) grid = ntiles;
+  gemm_nt_3xtf32_kernel<<<grid, G_THREADS, smem, (cudaStream_t)stream>>>(p);
+  return check_launch("nesie_gemm_nt_3xtf32");
+}

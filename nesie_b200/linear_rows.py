@@ -1,0 +1,72 @@
+"""Row-major linear layer on the tcgen05 3xTF32 GEMM (fp32 parity), with autograd.
+
+y = x @ w.T for x (R, K) and w (N, K): the training-mode 1x1 convolution of the SA / FP shared
+MLPs in its GEMM form.  Forward and the data gradient run on nesie_gemm_nt_3xtf32; the weight
+gradient (a reduction over the R rows) is a library GEMM."""
+import torch
+from torch.autograd import Function
+
+from . import _lib
+
+
+def _pack(w, n, k, stride_n, stride_k):
+    nbytes = _lib.lib().nesie_gemm_b_image_bytes(n, k)
+    img = torch.empty((nbytes,), dtype=torch.uint8, device=w.device)
+    _lib.call("nesie_gemm_pack_b", n, k, stride_n, stride_k, _lib.ptr(w), _lib.ptr(img),
+              _lib.stream())
+    return img
+
+
+def gemm_nt(a, w, transpose_w=False):
+    """a (R, K) fp32 contiguous; w (N, K) [or (K, N) with transpose_w] -> (R, N) fp32."""
+    _lib.need_cuda(a, w)
+    a = a.contiguous()
+    w = w.contiguous()
+    R, K = a.shape
+    if transpose_w:
+        assert w.shape[0] == K
+        N = w.shape[1]
+        sn, sk = 1, N
+    else:
+        assert w.shape[1] == K
+        N = w.shape[0]
+        sn, sk = K, 1
+    out = torch.empty((R, N), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        img = _pack(w, N, K, sn, sk)
+        _lib.call("nesie_gemm_nt_3xtf32", R, N, K, _lib.ptr(a), K, _lib.ptr(img), _lib.ptr(out), N,
+                  _lib.stream())
+    return out
+
+
+def supported(n, k):
+    return 1 <= n <= 256 and k >= 1
+
+
+class _LinearRows(Function):
+
+    @staticmethod
+    def forward(ctx, x, w):
+        ctx.save_for_backward(x, w)
+        return gemm_nt(x, w)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        gy = gy.contiguous()
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            if supported(w.shape[1], w.shape[0]):
+                gx = gemm_nt(gy, w, transpose_w=True)   # dX = dY W : B = W^T (K_in x K_out)
+            else:
+                gx = gy @ w
+        if ctx.needs_input_grad[1]:
+            gw = gy.t() @ x
+        return gx, gw
+
+
+def linear_rows(x, w):
+    """x (R, K) @ w (N, K)^T with fp32 parity on the tensor cores; falls back to torch for N > 256."""
+    if not supported(w.shape[0], w.shape[1]) or not x.is_cuda:
+        return torch.nn.functional.linear(x, w)
+    return _LinearRows.apply(x, w)

@@ -6,6 +6,7 @@ values and parameter names (`mlps.{i}.layer{j}.conv.weight`, `...bn.*`) are the 
 reference state_dict loads unchanged.  mmcv is not a dependency: `ConvModule` below is the
 (1x1 conv -> norm -> ReLU) block the reference builds through mmcv.cnn.ConvModule.
 """
+import os
 from typing import List
 
 import torch
@@ -17,7 +18,14 @@ from .gather_points import gather_points
 from .group_points import GroupAll, QueryAndGroup
 from .interpolate import three_interpolate, three_nn
 from . import sa_fused
+from .linear_rows import linear_rows
 from .ball_query import ball_query
+
+def _rows_linear(x, w):
+    if os.environ.get('NESIE_ROWS_GEMM', 'tcgen05') == 'cublas':
+        return F.linear(x, w)
+    return linear_rows(x, w)
+
 
 _NORMS = {'BN': nn.BatchNorm2d, 'BN1d': nn.BatchNorm1d, 'BN2d': nn.BatchNorm2d}
 _CONVS = {'Conv1d': nn.Conv1d, 'Conv2d': nn.Conv2d}
@@ -170,7 +178,8 @@ class BasePointSAModule(nn.Module):
         x = grouped.permute(0, 2, 3, 1).reshape(B * M * K, C0)
         for layer in self.mlps[i]:
             bn = layer.bn
-            x = F.linear(x, layer.conv.weight.flatten(1))
+            # fp32-parity GEMM on tcgen05 (3xTF32); NESIE_ROWS_GEMM=cublas selects the library GEMM
+            x = _rows_linear(x, layer.conv.weight.flatten(1))
             if bn.training and bn.track_running_stats:
                 bn.num_batches_tracked.add_(1)
             x = F.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias,
@@ -275,7 +284,9 @@ class PointFPModule(nn.Module):
         x = feats.transpose(1, 2).reshape(B * n, C)
         for layer in self.mlps:
             bn = layer.bn
-            x = F.linear(x, layer.conv.weight.flatten(1), layer.conv.bias)
+            x = _rows_linear(x, layer.conv.weight.flatten(1))
+            if layer.conv.bias is not None:
+                x = x + layer.conv.bias
             if bn.training and bn.track_running_stats:
                 bn.num_batches_tracked.add_(1)
             x = F.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias,
