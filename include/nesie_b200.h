@@ -239,6 +239,14 @@ int nesie_gemm_pack_b(int n, int k, long long stride_n, long long stride_k, cons
                       void *image, void *stream);
 int nesie_gemm_nt_3xtf32(long long r, int n, int k, const float *a, long long lda,
                          const void *b_image, float *c, long long ldc, void *stream);
+/* Weight gradient of the same layer, W'[n x k] = sum over the r rows of A[r, n] * B[r, k]
+ * (A = dY, B = X), split over the rows: the kernel writes nsplits partial [n x k] blocks
+ * (nsplits = nesie_gemm_wgrad_splits(r, n, k)) into `partials` and the caller sums them
+ * (deterministic; no atomics).  n <= 256, k <= 512. */
+int nesie_gemm_wgrad_splits(long long r, int n, int k);
+int nesie_gemm_wgrad_3xtf32(long long r, int n, int k, const float *a, long long lda,
+                            const float *b, long long ldb, float *partials, int nsplits,
+                            void *stream);
 
 #ifdef __cplusplus
 }

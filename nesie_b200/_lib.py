@@ -38,6 +38,8 @@ SIGNATURES = {
     "nesie_gemm_b_image_bytes": [_i, _i],
     "nesie_gemm_pack_b": [_i, _i, _ll, _ll, _p, _p, _p],
     "nesie_gemm_nt_3xtf32": [_ll, _i, _i, _p, _ll, _p, _p, _ll, _p],
+    "nesie_gemm_wgrad_splits": [_ll, _i, _i],
+    "nesie_gemm_wgrad_3xtf32": [_ll, _i, _i, _p, _ll, _p, _ll, _p, _i, _p],
     "nesie_sa_fused_supported": [_i, _i, _i, _i, _i],
     "nesie_pack_features_bf16": [_i, _i, _i, _p, _p, _p],
     "nesie_sa_fused_forward": [_i] * 8 + [_p, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p],

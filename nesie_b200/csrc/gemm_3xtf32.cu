@@ -18,6 +18,8 @@
 //                        last commit of a tile publishes the accumulator
 //   warps 0-3  epilogue: tcgen05.ld -> float4 stores to C; two TMEM accumulators so the epilogue of
 //                        tile t overlaps the MMAs of tile t+1
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace nesie {
@@ -105,10 +107,19 @@ __device__ __forceinline__ void g_tmem_ld32(unsigned taddr, unsigned (&r)[32]) {
       : "r"(taddr));
 }
 
-// x = hi + lo, hi = x with the 13 low mantissa bits cleared (exactly representable in TF32)
+// x = hi + lo with hi = x rounded to nearest TF32 and lo = (x - hi) rounded to nearest TF32.
+// Round-to-nearest (cvt.rna) instead of clearing the low mantissa bits keeps the split errors
+// sign-symmetric: with truncation every operand is biased towards zero and the bias accumulates
+// over a million-row reduction (5e-5 measured in the weight gradient); the tensor core itself
+// truncates operand bits beyond TF32, so lo is pre-rounded as well.
+__device__ __forceinline__ float to_tf32_rn(float x) {
+  unsigned r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
 __device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
-  hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-  lo = x - hi;
+  hi = to_tf32_rn(x);
+  lo = to_tf32_rn(x - hi);
 }
 
 __global__ void __launch_bounds__(G_THREADS, 1) gemm_nt_3xtf32_kernel(GemmParams p) {
@@ -282,6 +293,234 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_nt_3xtf32_kernel(GemmParams
                  : "memory");
 }
 
+// =============================================================================================
+// Weight gradient:  W'[n x k] = sum_r A[r, n] * B[r, k]    (A = dY (R x N), B = X (R x K))
+// The reduction runs over the ROWS, i.e. along the non-contiguous dimension of both operands.
+// kind::tf32 with MN-major descriptors (a_major = b_major = 1) returned all-zero accumulators on
+// this B200 whatever LBO/SBO were tried, so the loaders TRANSPOSE instead: a lane owns one reduction
+// row, reads float4s of it and scatters the four elements into four K-major operand rows (32
+// lanes -> 32 distinct words of a 128-byte row: conflict-free), SWIZZLE_128B as in the NT kernel.
+// 3xTF32 split as above.  Each CTA accumulates its share of the row slabs in TMEM (split-R) and writes one partial
+// [n x k] block; the caller sums the partials (deterministic, no atomics).
+// =============================================================================================
+struct WgradParams {
+  int R, N, K;
+  int kp;            // K rounded up to 32 (MN-block granularity)
+  int nstages;
+  long long lda, ldb;
+  const float *A, *B;
+  float *P;          // [nchunks][N][K] partial sums
+  int nchunks;       // row chunks of `chunk` slabs; one partial block each
+  int chunk;         // slabs (of 32 rows) accumulated per TMEM accumulator
+};
+
+// The tensor core's fp32 accumulation truncates: the error of a serial in-TMEM reduction grows
+// linearly with its length (measured vs float64: 3e-6 after 14 slabs, 1.3e-5 after 64, 5e-5 after
+// 220).  So an accumulator only ever sums <= 32 slabs (1024 rows); the partial blocks are then
+// added in ordinary round-to-nearest fp32 by the caller.
+constexpr int W_CHUNK_MAX = 32, W_CHUNK_MIN = 8;
+inline int wgrad_chunk(long long nslab, int mblocks) {
+  long long c = nslab / (2LL * (num_sms() / mblocks > 0 ? num_sms() / mblocks : 1));
+  if (c > W_CHUNK_MAX) c = W_CHUNK_MAX;
+  if (c < W_CHUNK_MIN) c = W_CHUNK_MIN;
+  return (int)c;
+}
+
+constexpr int W_THREADS = 128 + 128 * G_LGROUPS + 32;
+
+__global__ void __launch_bounds__(W_THREADS, 1) gemm_wgrad_3xtf32_kernel(WgradParams p) {
+  extern __shared__ unsigned char g_smem_dyn[];
+  unsigned char *smem = reinterpret_cast<unsigned char *>(
+      (reinterpret_cast<uintptr_t>(g_smem_dyn) + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) unsigned long long s_full[G_MAXSTAGES], s_empty[G_MAXSTAGES], s_accf[2], s_acce[2];
+  __shared__ unsigned s_tmem;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nacc = p.kp <= 256 ? 2 : 1;     // TMEM accumulators (double-buffered when they fit)
+  const int a_part = 128 * 128;             // 128 operand rows (channels) x 32 reduction elements
+  const int b_part = p.kp * 128;            // kp operand rows x 32 reduction elements
+  const int stage_bytes = 2 * a_part + 2 * b_part;
+  const int m0 = blockIdx.y * 128;          // first output row (channel of A) of this CTA
+  const int nslab = (p.R + 31) >> 5;        // reduction slabs of 32 rows
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     g_smem_u32(&s_tmem)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    for (int s = 0; s < p.nstages; ++s) {
+      g_mbar_init(g_smem_u32(&s_full[s]), 128);
+      g_mbar_init(g_smem_u32(&s_empty[s]), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      g_mbar_init(g_smem_u32(&s_accf[a]), 1);
+      g_mbar_init(g_smem_u32(&s_acce[a]), 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const unsigned tmem = s_tmem;
+
+  if (warp >= 4 && warp < 4 + 4 * G_LGROUPS) {
+    // ================================ loaders ================================================
+    const int lg = (warp - 4) >> 2;
+    const int lt = (tid - 128) & 127;
+    const int kq = p.kp >> 2;  // float4 columns of a B row
+    unsigned it = 0;
+    for (int chunk = blockIdx.x; chunk < p.nchunks; chunk += gridDim.x)
+    for (int slab = chunk * p.chunk; slab < min(nslab, (chunk + 1) * p.chunk); ++slab, ++it) {
+      if (lg >= p.nstages || (int)(it % p.nstages) != lg) continue;  // a group owns its stage
+      const int st = lg;
+      const unsigned ph = (it / p.nstages) & 1u;
+      unsigned char *sa_hi = smem + (size_t)st * stage_bytes;
+      unsigned char *sa_lo = sa_hi + a_part;
+      unsigned char *sb_hi = sa_lo + a_part;
+      unsigned char *sb_lo = sb_hi + b_part;
+      const long long r0 = (long long)slab * 32;
+      g_mbar_wait(g_smem_u32(&s_empty[st]), ph ^ 1u);
+      // Transposing loads: lane <-> reduction row (r0 + lane), so the four scalar stores of a
+      // float4 go to four operand rows (channels) at 32 distinct words each: conflict-free.
+      const int lw = lt >> 5, ll = lt & 31;       // warp of the group, lane
+      const long long gr = r0 + ll;
+      const bool rok = gr < p.R;
+      // ---- A tile: operand rows = 128 channels (m0..), 32 reduction elements per row
+      {
+        float4 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int ch = m0 + lw * 32 + i * 4;
+          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (rok && ch < p.N) {
+            const float *src = p.A + gr * p.lda + ch;
+            if (ch + 3 < p.N && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+              v[i] = __ldg(reinterpret_cast<const float4 *>(src));
+            } else {
+              v[i].x = __ldg(src);
+              if (ch + 1 < p.N) v[i].y = __ldg(src + 1);
+              if (ch + 2 < p.N) v[i].z = __ldg(src + 2);
+              if (ch + 3 < p.N) v[i].w = __ldg(src + 3);
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float e[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int n = lw * 32 + i * 4 + j;  // operand row
+            float hi, lo;
+            split_tf32(e[j], hi, lo);
+            const unsigned off = (unsigned)(n * 128 + ((((ll >> 2) ^ (n & 7))) << 4) + ((ll & 3) << 2));
+            *reinterpret_cast<float *>(sa_hi + off) = hi;
+            *reinterpret_cast<float *>(sa_lo + off) = lo;
+          }
+        }
+      }
+      // ---- B tile: operand rows = kp channels of X, 32 reduction elements per row
+      for (int c4 = lw; c4 < kq; c4 += 4) {
+        const int k0 = c4 * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rok && k0 < p.K) {
+          const float *src = p.B + gr * p.ldb + k0;
+          if (k0 + 3 < p.K && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+            v = __ldg(reinterpret_cast<const float4 *>(src));
+          } else {
+            v.x = __ldg(src);
+            if (k0 + 1 < p.K) v.y = __ldg(src + 1);
+            if (k0 + 2 < p.K) v.z = __ldg(src + 2);
+            if (k0 + 3 < p.K) v.w = __ldg(src + 3);
+          }
+        }
+        const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int n = k0 + j;
+          float hi, lo;
+          split_tf32(e[j], hi, lo);
+          const unsigned off = (unsigned)(n * 128 + ((((ll >> 2) ^ (n & 7))) << 4) + ((ll & 3) << 2));
+          *reinterpret_cast<float *>(sb_hi + off) = hi;
+          *reinterpret_cast<float *>(sb_lo + off) = lo;
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      g_mbar_arrive(g_smem_u32(&s_full[st]));
+    }
+  } else if (warp == 4 + 4 * G_LGROUPS) {
+    // ================================ MMA issuer =============================================
+    if (lane == 0) {
+      unsigned it = 0, ccount = 0;
+      for (int chunk = blockIdx.x; chunk < p.nchunks; chunk += gridDim.x, ++ccount) {
+      const int acc = nacc == 2 ? (int)(ccount & 1) : 0;
+      const unsigned dbase = tmem + (unsigned)(acc * 256);
+      const unsigned use = nacc == 2 ? (ccount >> 1) : ccount;  // how often this accumulator was used
+      g_mbar_wait(g_smem_u32(&s_acce[acc]), (use & 1u) ^ 1u);   // epilogue has drained it
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      bool first = true;
+      for (int slab = chunk * p.chunk; slab < min(nslab, (chunk + 1) * p.chunk); ++slab, ++it) {
+        const int st = it % p.nstages;
+        const unsigned ph = (it / p.nstages) & 1u;
+        g_mbar_wait(g_smem_u32(&s_full[st]), ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const unsigned a_hi = g_smem_u32(smem + (size_t)st * stage_bytes);
+        const unsigned a_lo = a_hi + (unsigned)a_part;
+        const unsigned b_hi = a_lo + (unsigned)a_part;
+        const unsigned b_lo = b_hi + (unsigned)b_part;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {  // UMMA_K = 8 reduction rows = 32 bytes along the operand rows
+          const unsigned o = (unsigned)ks * 32u;
+          for (int n0 = 0; n0 < p.kp; n0 += 256) {
+            const int nn = min(256, p.kp - n0);
+            const unsigned idesc = g_idesc(128, nn);
+            const unsigned bo = (unsigned)n0 * 128u + o;  // operand rows n0.. of the B tile
+            const unsigned d = dbase + (unsigned)n0;
+            g_mma(d, g_desc(a_hi + o), g_desc(b_hi + bo), idesc, first ? 0u : 1u);
+            g_mma(d, g_desc(a_hi + o), g_desc(b_lo + bo), idesc, 1u);
+            g_mma(d, g_desc(a_lo + o), g_desc(b_hi + bo), idesc, 1u);
+          }
+          first = false;
+        }
+        g_commit(g_smem_u32(&s_empty[st]));
+      }
+      g_commit(g_smem_u32(&s_accf[acc]));
+      }
+    }
+  } else if (warp < 4) {
+    // ================================ epilogue ===============================================
+    const int n = m0 + warp * 32 + lane;
+    unsigned ccount = 0;
+    for (int chunk = blockIdx.x; chunk < p.nchunks; chunk += gridDim.x, ++ccount) {
+      const int acc = nacc == 2 ? (int)(ccount & 1) : 0;
+      const unsigned use = nacc == 2 ? (ccount >> 1) : ccount;
+      g_mbar_wait(g_smem_u32(&s_accf[acc]), use & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      float *prow = p.P + ((size_t)chunk * p.N + n) * p.K;
+      for (int c0 = 0; c0 < p.kp; c0 += 32) {
+        unsigned v[32];
+        g_tmem_ld32(tmem + (unsigned)(acc * 256 + c0) + ((unsigned)(warp * 32) << 16), v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (n < p.N) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c0 + j < p.K) prow[c0 + j] = __uint_as_float(v[j]);
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      g_mbar_arrive(g_smem_u32(&s_acce[acc]));
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u)
+                 : "memory");
+}
+
 // B (N x K, element (n,k) at B[n*sn + k*sk]) -> image [hi|lo][nslab][npad][128 B], fp32 split,
 // 16-byte chunk c of row n at chunk position c ^ (n & 7); zero padding for n >= N, k >= K.
 __global__ void __launch_bounds__(256) pack_b_tf32_kernel(int N, int K, int npad, int nslab,
@@ -348,4 +587,42 @@ extern "C" int nesie_gemm_nt_3xtf32(long long r, int n, int k, const float *a, l
   if (ntiles < grid) grid = ntiles;
   gemm_nt_3xtf32_kernel<<<grid, G_THREADS, smem, (cudaStream_t)stream>>>(p);
   return check_launch("nesie_gemm_nt_3xtf32");
+}
+
+extern "C" int nesie_gemm_wgrad_splits(long long r, int n, int k) {
+  (void)k;
+  if (r <= 0 || n <= 0) return 0;
+  const long long nslab = (r + 31) / 32;
+  const int c = wgrad_chunk(nslab, (n + 127) / 128);
+  return (int)((nslab + c - 1) / c);  // one partial block per chunk
+}
+
+extern "C" int nesie_gemm_wgrad_3xtf32(long long r, int n, int k, const float *a, long long lda,
+                                       const float *b, long long ldb, float *partials,
+                                       int nsplits, void *stream) {
+  NESIE_REQUIRE(r >= 1 && n >= 1 && n <= 256 && k >= 1 && k <= 512, "need r>=1, n<=256, k<=512");
+  NESIE_REQUIRE(r < (1LL << 31) - 256, "too many rows");
+  NESIE_REQUIRE(a && b && partials, "null pointer");
+  NESIE_REQUIRE(nsplits == nesie_gemm_wgrad_splits(r, n, k), "nsplits must come from nesie_gemm_wgrad_splits");
+  WgradParams p;
+  p.R = (int)r; p.N = n; p.K = k;
+  p.kp = (k + 31) & ~31;
+  p.lda = lda; p.ldb = ldb;
+  p.A = a; p.B = b; p.P = partials;
+  const size_t stage = 2 * (size_t)(4 * 4096) + 2 * (size_t)(p.kp >> 5) * 4096;
+  p.nstages = (int)((226 * 1024) / stage);
+  if (p.nstages > G_MAXSTAGES) p.nstages = G_MAXSTAGES;
+  NESIE_REQUIRE(p.nstages >= 1, "k too large for shared memory");
+  const size_t smem = (size_t)p.nstages * stage + 1024;
+  NESIE_CUDA(cudaFuncSetAttribute(gemm_wgrad_3xtf32_kernel,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  p.nchunks = nsplits;
+  p.chunk = wgrad_chunk((r + 31) / 32, (n + 127) / 128);
+  const int mblocks = (n + 127) / 128;
+  int gx = num_sms() / mblocks;
+  if (gx < 1) gx = 1;
+  if (gx > nsplits) gx = nsplits;
+  dim3 grid(gx, mblocks);
+  gemm_wgrad_3xtf32_kernel<<<grid, W_THREADS, smem, (cudaStream_t)stream>>>(p);
+  return check_launch("nesie_gemm_wgrad_3xtf32");
 }

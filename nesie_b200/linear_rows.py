@@ -39,6 +39,19 @@ def gemm_nt(a, w, transpose_w=False):
     return out
 
 
+def wgrad(gy, x):
+    """gy (R, N), x (R, K) fp32 contiguous -> gy^T @ x (N, K) on the tensor cores (3xTF32)."""
+    _lib.need_cuda(gy, x)
+    R, N = gy.shape
+    K = x.shape[1]
+    ns = _lib.lib().nesie_gemm_wgrad_splits(R, N, K)
+    parts = torch.empty((ns, N, K), dtype=torch.float32, device=gy.device)
+    with torch.cuda.device(gy.device):
+        _lib.call("nesie_gemm_wgrad_3xtf32", R, N, K, _lib.ptr(gy), N, _lib.ptr(x), K,
+                  _lib.ptr(parts), ns, _lib.stream())
+    return parts.sum(dim=0)
+
+
 def supported(n, k):
     return 1 <= n <= 256 and k >= 1
 
@@ -61,7 +74,10 @@ class _LinearRows(Function):
             else:
                 gx = gy @ w
         if ctx.needs_input_grad[1]:
-            gw = gy.t() @ x
+            if gy.shape[1] <= 256 and x.shape[1] <= 512 and gy.shape[0] >= 1:
+                gw = wgrad(gy, x.contiguous())
+            else:
+                gw = gy.t() @ x
         return gx, gw
 
 

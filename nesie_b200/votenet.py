@@ -25,11 +25,37 @@ from torch import nn as nn
 from torch.nn import functional as F
 
 from .pointnet2_sa_ssg import PointNet2SASSG
-from .pointnet_modules import ConvModule, PointSAModule
+from .pointnet_modules import ConvModule, PointSAModule, _rows_linear
 from .side_loss import side_uncertainty_loss
 
 NUM_CLASSES = 18
 REG_MAX = 32
+
+
+def conv1d_rows(seq, x):
+    """Apply a stack of 1x1 Conv1d (+BN1d+ReLU) modules to (B, C, n) as row GEMMs on (B*n, C):
+    the same parameters and arithmetic as the Conv1d modules (cuDNN's fp32 1x1 wgrad engines are
+    slow), used on CUDA tensors; plain module calls otherwise (CPU oracle twin)."""
+    mods = list(seq) if isinstance(seq, nn.Sequential) else [seq]
+    if not x.is_cuda:
+        for m in mods:
+            x = m(x)
+        return x
+    B, C, n = x.shape
+    r = x.transpose(1, 2).reshape(B * n, C)
+    for m in mods:
+        conv = m.conv if isinstance(m, ConvModule) else m
+        r = _rows_linear(r, conv.weight.flatten(1))
+        if conv.bias is not None:
+            r = r + conv.bias
+        if isinstance(m, ConvModule):
+            bn = m.bn
+            if bn.training and bn.track_running_stats:
+                bn.num_batches_tracked.add_(1)
+            r = F.batch_norm(r, bn.running_mean, bn.running_var, bn.weight, bn.bias,
+                             bn.training or not bn.track_running_stats, bn.momentum, bn.eps)
+            r = F.relu(r, inplace=True)
+    return r.view(B, n, -1).transpose(1, 2)
 
 
 class VoteModule(nn.Module):
@@ -46,7 +72,7 @@ class VoteModule(nn.Module):
         self.conv_out = nn.Conv1d(prev, 3 + in_channels, 1)
 
     def forward(self, seed_points, seed_feats):
-        votes = self.conv_out(self.vote_conv(seed_feats)).transpose(2, 1)
+        votes = conv1d_rows(self.conv_out, conv1d_rows(self.vote_conv, seed_feats)).transpose(2, 1)
         offset = votes[..., 0:3]
         vote_points = (seed_points + offset).contiguous()
         vote_feats = (seed_feats.transpose(2, 1) + votes[..., 3:]).transpose(2, 1).contiguous()
@@ -95,15 +121,15 @@ class VoteNetHarness(nn.Module):
         seed_points, seed_feats = feat['fp_xyz'][-1], feat['fp_features'][-1]
         vote_points, vote_feats, _ = self.vote_module(seed_points, seed_feats)
         agg_points, agg_feats, _ = self._aggregate(vote_points, vote_feats)
-        x = self.shared_convs(agg_feats)
-        cls = self.conv_cls(x).transpose(2, 1)
+        x = conv1d_rows(self.shared_convs, agg_feats)
+        cls = conv1d_rows(self.conv_cls, x).transpose(2, 1)
         B, P = cls.shape[:2]
-        prob = F.softmax(self.conv_reg(x).reshape(B, 6, REG_MAX + 1, P), dim=2)
+        prob = F.softmax(conv1d_rows(self.conv_reg, x).reshape(B, 6, REG_MAX + 1, P), dim=2)
         dist = (prob * self.bins.view(1, 1, -1, 1)).sum(2).transpose(2, 1) * self.max_side
         surface_pred = torch.cat([agg_points - dist[..., :3], agg_points + dist[..., 3:]], dim=-1)
         size = surface_pred[..., 3:] - surface_pred[..., :3]
         center = 0.5 * (surface_pred[..., 3:] + surface_pred[..., :3])
-        q = self.conv_quality(x).transpose(2, 1).sigmoid()
+        q = conv1d_rows(self.conv_quality, x).transpose(2, 1).sigmoid()
         return dict(seed_points=seed_points, vote_points=vote_points, aggregated_points=agg_points,
                     obj_scores=cls[..., :2], sem_scores=cls[..., 2:], surface_pred=surface_pred,
                     bbox_preds=torch.cat([center, size, torch.zeros_like(center[..., :1])], -1),

@@ -36,4 +36,18 @@ def test_linear_rows_autograd():
     rel = lambda a, b: ((a.double() - b).abs().max() / b.abs().max()).item()  # noqa: E731
     assert rel(y.detach(), yd.detach()) < 6e-6
     assert rel(x.grad, xd.grad) < 6e-6
-    assert rel(w.grad, wd.grad) < 1e-5
+    assert rel(w.grad, wd.grad) < 2e-5
+
+
+@pytest.mark.parametrize("R,N,K", [(64, 128, 32), (1000, 64, 64), (4096, 128, 131), (300, 256, 128),
+                                   (65536, 128, 259), (5000, 64, 4), (33, 16, 8), (70000, 256, 128),
+                                   (200000, 64, 64)])
+def test_wgrad_matches_float64(R, N, K):
+    from nesie_b200.linear_rows import wgrad
+    torch.manual_seed(R + N + K)
+    gy = torch.randn(R, N, device="cuda")
+    x = torch.randn(R, K, device="cuda")
+    want = gy.double().t() @ x.double()
+    got = wgrad(gy, x)
+    err = ((got.double() - want).abs().max() / want.abs().max()).item()
+    assert err < 2e-5, err  # weight gradient: in-TMEM accumulation truncates (see gemm_3xtf32.cu)

@@ -27,3 +27,14 @@ for name, R, N, K in [("SA1.l1 fwd", 1048576, 64, 4), ("SA1.l2 fwd", 1048576, 64
     print(json.dumps({"gemm": name, "R": R, "N": N, "K": K, "ms": round(t_mine, 4), "cublas_fp32_ms": round(t_ref, 4),
                       "speedup": round(t_ref / t_mine, 2), "fp32_TFLOPs": round(fl / t_mine / 1e9, 1),
                       "GBps": round((R * K + R * N) * 4 / t_mine / 1e6, 0), "err": f"{e_mine:.1e}", "cublas_err": f"{e_ref:.1e}"}), flush=True)
+from nesie_b200.linear_rows import wgrad  # noqa: E402
+for name, R, N, K in [("SA1.l2 wgrad", 1048576, 64, 64), ("SA1.l3 wgrad", 1048576, 128, 64), ("SA2.l1 wgrad", 262144, 128, 131),
+                      ("SA2.l3 wgrad", 262144, 256, 128), ("SA3.l1 wgrad", 65536, 128, 259)]:
+    gy = torch.randn(R, N, device="cuda"); x = torch.randn(R, K, device="cuda")
+    t_mine = timeit(lambda: wgrad(gy, x)); t_ref = timeit(lambda: gy.t() @ x)
+    want = gy.double().t() @ x.double()
+    e_mine = ((wgrad(gy, x).double() - want).abs().max() / want.abs().max()).item()
+    e_ref = (((gy.t() @ x).double() - want).abs().max() / want.abs().max()).item()
+    print(json.dumps({"gemm": name, "R": R, "N": N, "K": K, "ms": round(t_mine, 4), "cublas_fp32_ms": round(t_ref, 4),
+                      "speedup": round(t_ref / t_mine, 2), "GBps": round((R * K + R * N) * 4 / t_mine / 1e6, 0),
+                      "err": f"{e_mine:.1e}", "cublas_err": f"{e_ref:.1e}"}), flush=True)
