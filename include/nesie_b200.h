@@ -116,6 +116,18 @@ int nesie_query_group_concat(int b, int c, int n, int npoints, int nsample, cons
                              const float *center_xyz, const float *features, const int *idx,
                              float radius, float *out, void *stream);
 
+/* The same grouped tensor in ROW-major GEMM layout for the training path of the shared MLP:
+ * rows ((b*npoints + j)*nsample + k, 3 + c) = [ (xyz[idx] - center) * (1/radius) | table[idx, :] ],
+ * with `table_pm` the point-major (b, n, c) copy of the features (one contiguous read and write
+ * per row).  _grad scatter-adds grad_rows into grad_table_pm (b, n, c), grad_xyz (b, n, 3) and
+ * grad_center (b, npoints, 3); each may be NULL to skip it; all are zero-filled by the caller. */
+int nesie_group_rows(int b, int c, int n, int npoints, int nsample, const float *xyz,
+                     const float *center_xyz, const float *table_pm, const int *idx, float radius,
+                     float *rows, void *stream);
+int nesie_group_rows_grad(int b, int c, int n, int npoints, int nsample, const float *grad_rows,
+                          const int *idx, float radius, float *grad_table_pm, float *grad_xyz,
+                          float *grad_center, void *stream);
+
 /* ---------------------------------------------------------------------------------------
  * three_nn.  Replaces three_nn_kernel_launcher(b,n,m,unknown,known,dist2,idx,stream)
  *   ops/interpolate/src/three_nn_cuda.cu:67-90 (kernel :11-65), wrapper interpolate.cpp:46-56.

@@ -27,6 +27,8 @@ SIGNATURES = {
     "nesie_group_points": [_i, _i, _i, _i, _i, _p, _p, _p, _p],
     "nesie_group_points_grad": [_i, _i, _i, _i, _i, _p, _p, _p, _p],
     "nesie_query_group_concat": [_i, _i, _i, _i, _i, _p, _p, _p, _p, _f, _p, _p],
+    "nesie_group_rows": [_i, _i, _i, _i, _i, _p, _p, _p, _p, _f, _p, _p],
+    "nesie_group_rows_grad": [_i, _i, _i, _i, _i, _p, _p, _f, _p, _p, _p, _p],
     "nesie_three_nn": [_i, _i, _i, _p, _p, _p, _p, _p],
     "nesie_three_interpolate": [_i, _i, _i, _i, _p, _p, _p, _p, _p],
     "nesie_three_interpolate_grad": [_i, _i, _i, _i, _p, _p, _p, _p, _p],

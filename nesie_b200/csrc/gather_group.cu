@@ -236,3 +236,103 @@ extern "C" int nesie_query_group_concat(int b, int c, int n, int npoints, int ns
       radius > 0.f ? 1.0f / radius : 0.f, out);
   return check_launch("nesie_query_group_concat");
 }
+
+// ---------------------------------------------------------------------------------------------
+// Row-major grouped tensor for the GEMM formulation of the shared MLP (training path):
+//   rows[(b*npoints + j)*nsample + k, :] = [ (xyz[b, i] - center[b, j]) * inv_radius (3) | table[b, i, :] (c) ]
+// with i = idx[b, j, k] and `table` the POINT-major (b, n, c) copy of the features, so a row is one
+// contiguous read and one contiguous write.  The channel-major (B, C, M, K) grouped tensor of the
+// reference (group_points.py:98-116) and its transposing copy into GEMM layout are never built.
+// ---------------------------------------------------------------------------------------------
+namespace nesie {
+namespace {
+
+__global__ void __launch_bounds__(256) group_rows_kernel(
+    int c, int n, int npoints, int nsample, const float *__restrict__ xyz,
+    const float *__restrict__ center, const float *__restrict__ table,
+    const int *__restrict__ idx, float inv_radius, float *__restrict__ out, long long nrows_scene) {
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int c0 = 3 + c;
+  const long long warp_global = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * 8;
+  idx += (size_t)b * nrows_scene;
+  out += (size_t)b * nrows_scene * c0;
+  for (long long row = warp_global; row < nrows_scene; row += nwarps) {
+    const int pt = __ldg(idx + row);
+    float *o = out + row * c0;
+    if (lane < 3) {
+      const int grp = (int)(row / nsample);
+      float d = __fsub_rn(__ldg(xyz + ((size_t)b * n + pt) * 3 + lane),
+                          __ldg(center + ((size_t)b * npoints + grp) * 3 + lane));
+      if (inv_radius > 0.f) d = __fmul_rn(d, inv_radius);
+      o[lane] = d;
+    }
+    const float *t = table + ((size_t)b * n + pt) * c;
+    for (int j = lane; j < c; j += 32) o[3 + j] = __ldg(t + j);
+  }
+}
+
+// grad_rows (.., 3+c) -> grad_table (b, n, c) [+= by index], grad_xyz (b, n, 3), grad_center (b, m, 3)
+__global__ void __launch_bounds__(256) group_rows_grad_kernel(
+    int c, int n, int npoints, int nsample, const float *__restrict__ grad_rows,
+    const int *__restrict__ idx, float inv_radius, float *__restrict__ grad_table,
+    float *__restrict__ grad_xyz, float *__restrict__ grad_center, long long nrows_scene) {
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int c0 = 3 + c;
+  const long long warp_global = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * 8;
+  idx += (size_t)b * nrows_scene;
+  grad_rows += (size_t)b * nrows_scene * c0;
+  for (long long row = warp_global; row < nrows_scene; row += nwarps) {
+    const int pt = __ldg(idx + row);
+    const float *g = grad_rows + row * c0;
+    if (lane < 3 && (grad_xyz || grad_center)) {
+      float v = g[lane];
+      if (inv_radius > 0.f) v = __fmul_rn(v, inv_radius);
+      if (grad_xyz) atomicAdd(grad_xyz + ((size_t)b * n + pt) * 3 + lane, v);
+      if (grad_center) atomicAdd(grad_center + ((size_t)b * npoints + (int)(row / nsample)) * 3 + lane, -v);
+    }
+    if (grad_table) {
+      float *t = grad_table + ((size_t)b * n + pt) * c;
+      for (int j = lane; j < c; j += 32) atomicAdd(t + j, g[3 + j]);
+    }
+  }
+}
+
+}  // namespace
+}  // namespace nesie
+
+extern "C" int nesie_group_rows(int b, int c, int n, int npoints, int nsample, const float *xyz,
+                                const float *center_xyz, const float *table_pm, const int *idx,
+                                float radius, float *rows, void *stream) {
+  NESIE_REQUIRE(b >= 0 && c >= 0 && n >= 0 && npoints >= 0 && nsample >= 0, "negative size");
+  NESIE_REQUIRE(xyz && center_xyz && idx && rows && (c == 0 || table_pm), "null pointer");
+  if (b == 0 || npoints == 0 || nsample == 0) return NESIE_OK;
+  NESIE_REQUIRE(b <= 65535, "b > 65535");
+  const long long nr = (long long)npoints * nsample;
+  int gx = (int)((nr + 7) / 8);
+  if (gx > 8 * nesie::num_sms()) gx = 8 * nesie::num_sms();
+  nesie::group_rows_kernel<<<dim3(gx, b), 256, 0, (cudaStream_t)stream>>>(
+      c, n, npoints, nsample, xyz, center_xyz, table_pm, idx, radius > 0.f ? 1.0f / radius : 0.f,
+      rows, nr);
+  return nesie::check_launch("nesie_group_rows");
+}
+
+extern "C" int nesie_group_rows_grad(int b, int c, int n, int npoints, int nsample,
+                                     const float *grad_rows, const int *idx, float radius,
+                                     float *grad_table_pm, float *grad_xyz, float *grad_center,
+                                     void *stream) {
+  NESIE_REQUIRE(b >= 0 && c >= 0 && n >= 0 && npoints >= 0 && nsample >= 0, "negative size");
+  NESIE_REQUIRE(grad_rows && idx, "null pointer");
+  if (b == 0 || npoints == 0 || nsample == 0) return NESIE_OK;
+  NESIE_REQUIRE(b <= 65535, "b > 65535");
+  const long long nr = (long long)npoints * nsample;
+  int gx = (int)((nr + 7) / 8);
+  if (gx > 8 * nesie::num_sms()) gx = 8 * nesie::num_sms();
+  nesie::group_rows_grad_kernel<<<dim3(gx, b), 256, 0, (cudaStream_t)stream>>>(
+      c, n, npoints, nsample, grad_rows, idx, radius > 0.f ? 1.0f / radius : 0.f,
+      c > 0 ? grad_table_pm : nullptr, grad_xyz, grad_center, nr);
+  return nesie::check_launch("nesie_group_rows_grad");
+}

@@ -106,6 +106,52 @@ class _QueryGroupConcat(Function):
         return g_xyz, g_center, g_feat, None, None
 
 
+class _QueryGroupRows(Function):
+    """Row-major grouped tensor (B*npoint*nsample, 3 + C) for the GEMM formulation of the shared
+    MLP: [ (xyz[idx] - centre) * (1/radius) | features[idx] ] per row.  Same values as
+    _QueryGroupConcat, different layout; gradients to features, points_xyz and center_xyz."""
+
+    @staticmethod
+    def forward(ctx, points_xyz, center_xyz, features, idx, radius):
+        _lib.need_cuda(points_xyz, center_xyz, features, idx)
+        points_xyz = points_xyz.contiguous()
+        center_xyz = center_xyz.contiguous()
+        B, N, _ = points_xyz.shape
+        npoint, nsample = idx.shape[1], idx.shape[2]
+        C = 0 if features is None else features.shape[1]
+        table = None if features is None else features.transpose(1, 2).contiguous()  # (B, N, C)
+        rows = torch.empty((B * npoint * nsample, 3 + C), dtype=torch.float32,
+                           device=points_xyz.device)
+        with torch.cuda.device(points_xyz.device):
+            _lib.call("nesie_group_rows", B, C, N, npoint, nsample, _lib.ptr(points_xyz),
+                      _lib.ptr(center_xyz), _lib.ptr(table), _lib.ptr(idx), float(radius),
+                      _lib.ptr(rows), _lib.stream())
+        ctx.save_for_backward(idx)
+        ctx.shape = (B, C, N, npoint, nsample)
+        ctx.radius = float(radius)
+        return rows
+
+    @staticmethod
+    def backward(ctx, grad_rows):
+        (idx,) = ctx.saved_tensors
+        B, C, N, npoint, nsample = ctx.shape
+        dev = grad_rows.device
+        grad_rows = grad_rows.contiguous()
+        g_table = torch.zeros((B, N, C), dtype=torch.float32, device=dev) \
+            if (ctx.needs_input_grad[2] and C > 0) else None
+        g_xyz = torch.zeros((B, N, 3), dtype=torch.float32, device=dev) \
+            if ctx.needs_input_grad[0] else None
+        g_center = torch.zeros((B, npoint, 3), dtype=torch.float32, device=dev) \
+            if ctx.needs_input_grad[1] else None
+        if g_table is not None or g_xyz is not None or g_center is not None:
+            with torch.cuda.device(dev):
+                _lib.call("nesie_group_rows_grad", B, C, N, npoint, nsample, _lib.ptr(grad_rows),
+                          _lib.ptr(idx), ctx.radius, _lib.ptr(g_table), _lib.ptr(g_xyz),
+                          _lib.ptr(g_center), _lib.stream())
+        g_feat = g_table.transpose(1, 2).contiguous() if g_table is not None else None
+        return g_xyz, g_center, g_feat, None, None
+
+
 class QueryAndGroup(nn.Module):
     """Ball query + grouping.  Constructor arguments, assertions and return values as in the
     reference (group_points.py:36-128).  kNN grouping (max_radius=None) and uniform_sample are
@@ -133,6 +179,13 @@ class QueryAndGroup(nn.Module):
             raise NotImplementedError('kNN grouping (max_radius=None) is outside the Nesie hot path')
         if self.uniform_sample:
             raise NotImplementedError('uniform_sample is outside the Nesie hot path')
+
+    def forward_rows(self, points_xyz, center_xyz, features):
+        """Row-major variant for the GEMM-form shared MLP: (B*npoint*sample_num, 3+C) rows."""
+        idx = ball_query(self.min_radius, self.max_radius, self.sample_num,
+                         points_xyz.contiguous(), center_xyz.contiguous())
+        radius = self.max_radius if self.normalize_xyz else 0.0
+        return _QueryGroupRows.apply(points_xyz, center_xyz, features, idx, radius)
 
     def forward(self, points_xyz, center_xyz, features=None):
         """points_xyz (B,N,3), center_xyz (B,npoint,3), features (B,C,N) ->

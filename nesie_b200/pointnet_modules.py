@@ -169,13 +169,15 @@ class BasePointSAModule(nn.Module):
     rows_mlp = True
 
     def _rows_ok(self, i, grouped):
-        return (grouped.is_cuda and self.pool_mod == 'max' and
+        g = self.groupers[i]
+        if grouped is None and not (isinstance(g, QueryAndGroup) and g.use_xyz and
+                                    not g.return_grouped_xyz and not g.return_grouped_idx):
+            return False
+        return ((grouped is None or grouped.is_cuda) and self.pool_mod == 'max' and
                 all(isinstance(l.conv, nn.Conv2d) and l.conv.bias is None and l.with_norm and
                     isinstance(l.bn, nn.BatchNorm2d) for l in self.mlps[i]))
 
-    def _mlp_rows(self, i, grouped):
-        B, C0, M, K = grouped.shape
-        x = grouped.permute(0, 2, 3, 1).reshape(B * M * K, C0)
+    def _mlp_rows(self, i, x, B, M, K):
         for layer in self.mlps[i]:
             bn = layer.bn
             # fp32-parity GEMM on tcgen05 (3xTF32); NESIE_ROWS_GEMM=cublas selects the library GEMM
@@ -196,9 +198,18 @@ class BasePointSAModule(nn.Module):
             if self._fused_ok(i, features):
                 new_features_list.append(self._fused_forward(i, points_xyz, new_xyz, features))
                 continue
+            if self.rows_mlp and points_xyz.is_cuda and features is not None and \
+                    self._rows_ok(i, None):
+                g = self.groupers[i]
+                rows = g.forward_rows(points_xyz, new_xyz, features)
+                new_features_list.append(self._mlp_rows(i, rows, points_xyz.shape[0],
+                                                        new_xyz.shape[1], g.sample_num))
+                continue
             grouped_results = self.groupers[i](points_xyz, new_xyz, features)
             if self.rows_mlp and self._rows_ok(i, grouped_results):
-                new_features = self._mlp_rows(i, grouped_results)
+                B_, C0_, M_, K_ = grouped_results.shape
+                rows = grouped_results.permute(0, 2, 3, 1).reshape(B_ * M_ * K_, C0_)
+                new_features = self._mlp_rows(i, rows, B_, M_, K_)
             else:
                 new_features = self.mlps[i](grouped_results)
                 new_features = self._pool_features(new_features)
