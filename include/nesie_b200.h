@@ -260,6 +260,27 @@ int nesie_gemm_wgrad_3xtf32(long long r, int n, int k, const float *a, long long
                             const float *b, long long ldb, float *partials, int nsplits,
                             void *stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Training-mode BatchNorm (batch statistics) + ReLU [+ max-pool over k consecutive rows] on
+ * row-major activations y (r x c, c % 4 == 0): the BN2d / ReLU / max_pool2d tail of the SA shared
+ * MLP (ops/pointnet_modules/point_sa_module.py:149-150,279-288) in the GEMM formulation.
+ * forward : k == 0 -> a (r, c) = relu(bn(y));  k > 0 -> pooled (r/k, c) = max over each group's k
+ *           rows, arg (r/k, c) u8 = first maximising row (255: non-positive maximum).  stats (4c)
+ *           receives mean | invstd | scale | shift; running_mean/var (nullable) are updated with
+ *           `momentum` (unbiased variance), like torch.nn.BatchNorm.
+ * backward: d_a is (r, c) for k == 0 or the pooled gradient (r/k, c); writes d_y (r, c),
+ *           d_gamma (c), d_beta (c).
+ * workspace: nesie_bn_rows_workspace_bytes(c) bytes of scratch, caller-provided.
+ */
+long long nesie_bn_rows_workspace_bytes(int c);
+int nesie_bn_relu_rows_forward(long long r, int c, int k, const float *y, const float *gamma,
+                               const float *beta, float eps, float momentum, float *running_mean,
+                               float *running_var, float *stats, float *a_or_pooled,
+                               unsigned char *arg, void *workspace, void *stream);
+int nesie_bn_relu_rows_backward(long long r, int c, int k, const float *y, const float *d_a,
+                                const unsigned char *arg, const float *stats, float *d_y,
+                                float *d_gamma, float *d_beta, void *workspace, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

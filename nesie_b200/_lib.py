@@ -42,6 +42,9 @@ SIGNATURES = {
     "nesie_gemm_nt_3xtf32": [_ll, _i, _i, _p, _ll, _p, _p, _ll, _p],
     "nesie_gemm_wgrad_splits": [_ll, _i, _i],
     "nesie_gemm_wgrad_3xtf32": [_ll, _i, _i, _p, _ll, _p, _ll, _p, _i, _p],
+    "nesie_bn_rows_workspace_bytes": [_i],
+    "nesie_bn_relu_rows_forward": [_ll, _i, _i, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p],
+    "nesie_bn_relu_rows_backward": [_ll, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     "nesie_sa_fused_supported": [_i, _i, _i, _i, _i],
     "nesie_pack_features_bf16": [_i, _i, _i, _p, _p, _p],
     "nesie_sa_fused_forward": [_i] * 8 + [_p, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p],

@@ -19,12 +19,17 @@ from .group_points import GroupAll, QueryAndGroup
 from .interpolate import three_interpolate, three_nn
 from . import sa_fused
 from .linear_rows import linear_rows
+from . import bn_rows
 from .ball_query import ball_query
 
 def _rows_linear(x, w):
     if os.environ.get('NESIE_ROWS_GEMM', 'tcgen05') == 'cublas':
         return F.linear(x, w)
     return linear_rows(x, w)
+
+
+def _fused_bn():
+    return os.environ.get('NESIE_ROWS_BN', 'fused') != 'aten'
 
 
 _NORMS = {'BN': nn.BatchNorm2d, 'BN1d': nn.BatchNorm1d, 'BN2d': nn.BatchNorm2d}
@@ -178,10 +183,18 @@ class BasePointSAModule(nn.Module):
                     isinstance(l.bn, nn.BatchNorm2d) for l in self.mlps[i]))
 
     def _mlp_rows(self, i, x, B, M, K):
-        for layer in self.mlps[i]:
+        layers = list(self.mlps[i])
+        for li, layer in enumerate(layers):
             bn = layer.bn
             # fp32-parity GEMM on tcgen05 (3xTF32); NESIE_ROWS_GEMM=cublas selects the library GEMM
             x = _rows_linear(x, layer.conv.weight.flatten(1))
+            last = li == len(layers) - 1
+            if _fused_bn() and bn_rows.supported(x, bn, K if last else 0):
+                # fused BatchNorm(batch stats) + ReLU (+ the max-pool over the K rows of a group)
+                x = bn_rows.bn_relu_rows(x, bn, K if last else 0)
+                if last:
+                    return x.view(B, M, -1).transpose(1, 2).contiguous()
+                continue
             if bn.training and bn.track_running_stats:
                 bn.num_batches_tracked.add_(1)
             x = F.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias,
@@ -298,6 +311,9 @@ class PointFPModule(nn.Module):
             x = _rows_linear(x, layer.conv.weight.flatten(1))
             if layer.conv.bias is not None:
                 x = x + layer.conv.bias
+            if _fused_bn() and bn_rows.supported(x, bn):
+                x = bn_rows.bn_relu_rows(x, bn)
+                continue
             if bn.training and bn.track_running_stats:
                 bn.num_batches_tracked.add_(1)
             x = F.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias,

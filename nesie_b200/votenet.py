@@ -25,7 +25,8 @@ from torch import nn as nn
 from torch.nn import functional as F
 
 from .pointnet2_sa_ssg import PointNet2SASSG
-from .pointnet_modules import ConvModule, PointSAModule, _rows_linear
+from . import bn_rows
+from .pointnet_modules import ConvModule, PointSAModule, _fused_bn, _rows_linear
 from .side_loss import side_uncertainty_loss
 
 NUM_CLASSES = 18
@@ -50,6 +51,9 @@ def conv1d_rows(seq, x):
             r = r + conv.bias
         if isinstance(m, ConvModule):
             bn = m.bn
+            if _fused_bn() and bn_rows.supported(r, bn):
+                r = bn_rows.bn_relu_rows(r, bn)
+                continue
             if bn.training and bn.track_running_stats:
                 bn.num_batches_tracked.add_(1)
             r = F.batch_norm(r, bn.running_mean, bn.running_var, bn.weight, bn.bias,

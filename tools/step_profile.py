@@ -1,4 +1,4 @@
-"""Kernel-time table of one VoteNet harness train step (torch.profiler, CUDA activities)."""
+"""Per-kernel GPU time of one VoteNet harness train step (torch.profiler, CUDA kernels only)."""
 import os
 import sys
 
@@ -10,9 +10,8 @@ sys.path.insert(0, ROOT)
 from nesie_b200.synthetic import make_batch  # noqa: E402
 from nesie_b200.votenet import VoteNetHarness  # noqa: E402
 
-tf32 = "--tf32" in sys.argv
-torch.backends.cuda.matmul.allow_tf32 = tf32
-torch.backends.cudnn.allow_tf32 = tf32
+torch.backends.cuda.matmul.allow_tf32 = False
+torch.backends.cudnn.allow_tf32 = False
 torch.manual_seed(0)
 model = VoteNetHarness().cuda()
 opt = torch.optim.AdamW(model.parameters(), lr=0.008, weight_decay=0.01, fused=True)
@@ -33,8 +32,16 @@ def step():
 for _ in range(3):
     step()
 torch.cuda.synchronize()
-with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
-    for _ in range(3):
+NS = 3
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    for _ in range(NS):
         step()
     torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=120, max_name_column_width=70))
+rows = [(e.key, e.self_device_time_total / NS, e.count / NS) for e in prof.key_averages()
+        if e.self_device_time_total > 0]
+rows.sort(key=lambda r: -r[1])
+total = sum(r[1] for r in rows)
+print(f"total kernel time per step: {total / 1000:.2f} ms over {sum(r[2] for r in rows):.0f} launches")
+print("| kernel | us/step | launches/step | share |\n|---|---:|---:|---:|")
+for k, us, n in rows[:40]:
+    print(f"| `{k[:110]}` | {us:.0f} | {n:.0f} | {100 * us / total:.1f}% |")
