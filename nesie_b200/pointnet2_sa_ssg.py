@@ -91,8 +91,24 @@ class PointNet2SASSG(nn.Module):
                 idx.record_stream(main)
         return out
 
-    def forward(self, points):
-        """points (B, N, 3 + input_feature_dim) -> dict of lists, as the reference returns."""
+    def fps_chain(self, points):
+        """The SA levels' FPS indices [(B, num_points[i]) int32] for `points`, on the current
+        stream.  They depend on coordinates only, so an input pipeline can compute them for batch
+        t+1 while batch t trains and hand them to forward(points, fps_indices=...)."""
+        cur = points[..., 0:3].contiguous()
+        out = []
+        with torch.no_grad():
+            for i in range(self.num_sa):
+                idx = furthest_point_sample(cur, self.num_points[i])
+                out.append(idx)
+                if i + 1 < self.num_sa:
+                    cur = gather_points(cur.transpose(1, 2).contiguous(), idx) \
+                        .transpose(1, 2).contiguous()
+        return out
+
+    def forward(self, points, fps_indices=None):
+        """points (B, N, 3 + input_feature_dim) -> dict of lists, as the reference returns.
+        fps_indices: optional precomputed result of fps_chain(points)."""
         xyz, features = self._split_point_feats(points)
         batch, num_points = xyz.shape[:2]
         indices = torch.arange(num_points, device=xyz.device, dtype=torch.long) \
@@ -102,9 +118,9 @@ class PointNet2SASSG(nn.Module):
         use_chain = self.overlap_fps and all(
             getattr(m, 'fps_mod_list', None) == ['D-FPS'] and
             list(getattr(m, 'fps_sample_range_list', [])) == [-1] for m in self.SA_modules)
-        chain = self._fps_chain(xyz) if use_chain else None
+        chain = self._fps_chain(xyz) if (use_chain and fps_indices is None) else None
         for i in range(self.num_sa):
-            pre = None
+            pre = fps_indices[i] if fps_indices is not None else None
             if chain is not None:
                 pre, ev = chain[i]
                 torch.cuda.current_stream(xyz.device).wait_event(ev)
