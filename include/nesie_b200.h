@@ -120,13 +120,15 @@ int nesie_query_group_concat(int b, int c, int n, int npoints, int nsample, cons
  * rows ((b*npoints + j)*nsample + k, 3 + c) = [ (xyz[idx] - center) * (1/radius) | table[idx, :] ],
  * with `table_pm` the point-major (b, n, c) copy of the features (one contiguous read and write
  * per row).  _grad scatter-adds grad_rows into grad_table_pm (b, n, c), grad_xyz (b, n, 3) and
- * grad_center (b, npoints, 3); each may be NULL to skip it; all are zero-filled by the caller. */
+ * grad_center (b, npoints, 3); each may be NULL to skip it; all are zero-filled by the caller.
+ * `ld` is the row stride in floats (3 + c <= ld <= 3 + c + 32): columns [3 + c, ld) are written as
+ * zeros, so a caller can pad rows to a multiple of 4 floats for 16-byte aligned GEMM loads. */
 int nesie_group_rows(int b, int c, int n, int npoints, int nsample, const float *xyz,
                      const float *center_xyz, const float *table_pm, const int *idx, float radius,
-                     float *rows, void *stream);
+                     float *rows, int ld, void *stream);
 int nesie_group_rows_grad(int b, int c, int n, int npoints, int nsample, const float *grad_rows,
                           const int *idx, float radius, float *grad_table_pm, float *grad_xyz,
-                          float *grad_center, void *stream);
+                          float *grad_center, int ld, void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * three_nn.  Replaces three_nn_kernel_launcher(b,n,m,unknown,known,dist2,idx,stream)
@@ -251,6 +253,9 @@ int nesie_gemm_pack_b(int n, int k, long long stride_n, long long stride_k, cons
                       void *image, void *stream);
 int nesie_gemm_nt_3xtf32(long long r, int n, int k, const float *a, long long lda,
                          const void *b_image, float *c, long long ldc, void *stream);
+/* Diagnostic only: per-role cycle counters of CTA 0 collected by launches made with the environment
+ * variable NESIE_GEMM_DBG & 128 (16 values; reading resets them). */
+int nesie_gemm_debug_profile(long long *out16);
 /* Weight gradient of the same layer, W'[n x k] = sum over the r rows of A[r, n] * B[r, k]
  * (A = dY, B = X), split over the rows: the kernel writes nsplits partial [n x k] blocks
  * (nsplits = nesie_gemm_wgrad_splits(r, n, k)) into `partials` and the caller sums them

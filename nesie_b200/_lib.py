@@ -27,8 +27,8 @@ SIGNATURES = {
     "nesie_group_points": [_i, _i, _i, _i, _i, _p, _p, _p, _p],
     "nesie_group_points_grad": [_i, _i, _i, _i, _i, _p, _p, _p, _p],
     "nesie_query_group_concat": [_i, _i, _i, _i, _i, _p, _p, _p, _p, _f, _p, _p],
-    "nesie_group_rows": [_i, _i, _i, _i, _i, _p, _p, _p, _p, _f, _p, _p],
-    "nesie_group_rows_grad": [_i, _i, _i, _i, _i, _p, _p, _f, _p, _p, _p, _p],
+    "nesie_group_rows": [_i, _i, _i, _i, _i, _p, _p, _p, _p, _f, _p, _i, _p],
+    "nesie_group_rows_grad": [_i, _i, _i, _i, _i, _p, _p, _f, _p, _p, _p, _i, _p],
     "nesie_three_nn": [_i, _i, _i, _p, _p, _p, _p, _p],
     "nesie_three_interpolate": [_i, _i, _i, _i, _p, _p, _p, _p, _p],
     "nesie_three_interpolate_grad": [_i, _i, _i, _i, _p, _p, _p, _p, _p],
@@ -40,6 +40,7 @@ SIGNATURES = {
     "nesie_gemm_b_image_bytes": [_i, _i],
     "nesie_gemm_pack_b": [_i, _i, _ll, _ll, _p, _p, _p],
     "nesie_gemm_nt_3xtf32": [_ll, _i, _i, _p, _ll, _p, _p, _ll, _p],
+    "nesie_gemm_debug_profile": [_p],
     "nesie_gemm_wgrad_splits": [_ll, _i, _i],
     "nesie_gemm_wgrad_3xtf32": [_ll, _i, _i, _p, _ll, _p, _ll, _p, _i, _p],
     "nesie_bn_rows_workspace_bytes": [_i],

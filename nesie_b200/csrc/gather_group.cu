@@ -250,10 +250,10 @@ namespace {
 __global__ void __launch_bounds__(256) group_rows_kernel(
     int c, int n, int npoints, int nsample, const float *__restrict__ xyz,
     const float *__restrict__ center, const float *__restrict__ table,
-    const int *__restrict__ idx, float inv_radius, float *__restrict__ out, long long nrows_scene) {
+    const int *__restrict__ idx, float inv_radius, float *__restrict__ out, long long nrows_scene,
+    int c0 /* row stride >= 3 + c; the padding columns are written as zeros */) {
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31;
-  const int c0 = 3 + c;
   const long long warp_global = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * 8;
   idx += (size_t)b * nrows_scene;
@@ -270,6 +270,7 @@ __global__ void __launch_bounds__(256) group_rows_kernel(
     }
     const float *t = table + ((size_t)b * n + pt) * c;
     for (int j = lane; j < c; j += 32) o[3 + j] = __ldg(t + j);
+    if (lane < c0 - 3 - c) o[3 + c + lane] = 0.f;
   }
 }
 
@@ -277,10 +278,9 @@ __global__ void __launch_bounds__(256) group_rows_kernel(
 __global__ void __launch_bounds__(256) group_rows_grad_kernel(
     int c, int n, int npoints, int nsample, const float *__restrict__ grad_rows,
     const int *__restrict__ idx, float inv_radius, float *__restrict__ grad_table,
-    float *__restrict__ grad_xyz, float *__restrict__ grad_center, long long nrows_scene) {
+    float *__restrict__ grad_xyz, float *__restrict__ grad_center, long long nrows_scene, int c0) {
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31;
-  const int c0 = 3 + c;
   const long long warp_global = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * 8;
   idx += (size_t)b * nrows_scene;
@@ -306,8 +306,9 @@ __global__ void __launch_bounds__(256) group_rows_grad_kernel(
 
 extern "C" int nesie_group_rows(int b, int c, int n, int npoints, int nsample, const float *xyz,
                                 const float *center_xyz, const float *table_pm, const int *idx,
-                                float radius, float *rows, void *stream) {
+                                float radius, float *rows, int ld, void *stream) {
   NESIE_REQUIRE(b >= 0 && c >= 0 && n >= 0 && npoints >= 0 && nsample >= 0, "negative size");
+  NESIE_REQUIRE(ld >= 3 + c && ld <= 3 + c + 32, "row stride must be in [3 + c, 3 + c + 32]");
   NESIE_REQUIRE(xyz && center_xyz && idx && rows && (c == 0 || table_pm), "null pointer");
   if (b == 0 || npoints == 0 || nsample == 0) return NESIE_OK;
   NESIE_REQUIRE(b <= 65535, "b > 65535");
@@ -316,15 +317,16 @@ extern "C" int nesie_group_rows(int b, int c, int n, int npoints, int nsample, c
   if (gx > 8 * nesie::num_sms()) gx = 8 * nesie::num_sms();
   nesie::group_rows_kernel<<<dim3(gx, b), 256, 0, (cudaStream_t)stream>>>(
       c, n, npoints, nsample, xyz, center_xyz, table_pm, idx, radius > 0.f ? 1.0f / radius : 0.f,
-      rows, nr);
+      rows, nr, ld);
   return nesie::check_launch("nesie_group_rows");
 }
 
 extern "C" int nesie_group_rows_grad(int b, int c, int n, int npoints, int nsample,
                                      const float *grad_rows, const int *idx, float radius,
                                      float *grad_table_pm, float *grad_xyz, float *grad_center,
-                                     void *stream) {
+                                     int ld, void *stream) {
   NESIE_REQUIRE(b >= 0 && c >= 0 && n >= 0 && npoints >= 0 && nsample >= 0, "negative size");
+  NESIE_REQUIRE(ld >= 3 + c, "row stride must be >= 3 + c");
   NESIE_REQUIRE(grad_rows && idx, "null pointer");
   if (b == 0 || npoints == 0 || nsample == 0) return NESIE_OK;
   NESIE_REQUIRE(b <= 65535, "b > 65535");
@@ -333,6 +335,6 @@ extern "C" int nesie_group_rows_grad(int b, int c, int n, int npoints, int nsamp
   if (gx > 8 * nesie::num_sms()) gx = 8 * nesie::num_sms();
   nesie::group_rows_grad_kernel<<<dim3(gx, b), 256, 0, (cudaStream_t)stream>>>(
       c, n, npoints, nsample, grad_rows, idx, radius > 0.f ? 1.0f / radius : 0.f,
-      c > 0 ? grad_table_pm : nullptr, grad_xyz, grad_center, nr);
+      c > 0 ? grad_table_pm : nullptr, grad_xyz, grad_center, nr, ld);
   return nesie::check_launch("nesie_group_rows_grad");
 }

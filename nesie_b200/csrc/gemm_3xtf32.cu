@@ -31,6 +31,10 @@ constexpr int G_MAXSTAGES = 4;
 constexpr int G_LGROUPS = 4;                       // loader groups of 128 threads (stage it -> group it % 4)
 constexpr int G_THREADS = 128 + 128 * G_LGROUPS + 32;  // epilogue + loaders + MMA warp
 constexpr int G_ASLAB = G_TILE * 128;  // bytes of one A part-slab
+constexpr int G_EPI_STAGE = 4 * 4096;  // epilogue transpose staging: 32 rows x 128 B per warp
+
+// cycle counters of CTA 0 (NESIE_GEMM_DBG bit 128), read back by nesie_gemm_debug_profile
+__device__ long long g_gemm_prof[16];
 
 struct GemmParams {
   int R, N, K;        // logical sizes
@@ -40,6 +44,8 @@ struct GemmParams {
   const float *A;
   const unsigned char *Bimg;  // [hi|lo][nslab][npad][128 B]
   float *C;
+  int fast;           // rows 16-byte aligned and K % 4 == 0: float4 loads without per-element checks
+  int dbg;            // NESIE_GEMM_DBG experiment bits: 1 no A loads, 2 no C stores, 4 no MMAs
 };
 
 __device__ __forceinline__ unsigned g_smem_u32(const void *p) {
@@ -48,6 +54,14 @@ __device__ __forceinline__ unsigned g_smem_u32(const void *p) {
 __device__ __forceinline__ unsigned long long g_desc(unsigned smem_addr) {
   return (unsigned long long)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) |
          (1ull << 46) | (2ull << 61);
+}
+// MN-major tf32 operands have exactly one legal shared-memory layout: 128-byte swizzle with 32-byte
+// atomicity (layout type 1; CUTLASS calls it SW128_32B).  An atom is 4 reduction rows x 128 bytes
+// (32 elements along M/N); byte-address bits [5,7) are XORed with bits [7,9).  LBO = stride between
+// atoms along M/N, SBO = stride between atoms along K.
+__device__ __forceinline__ unsigned long long g_desc_mn(unsigned smem_addr, unsigned lbo, unsigned sbo) {
+  return (unsigned long long)((smem_addr & 0x3FFFF) >> 4) | ((unsigned long long)(lbo >> 4) << 16) |
+         ((unsigned long long)(sbo >> 4) << 32) | (1ull << 46) | (1ull << 61);
 }
 // kind::tf32: D = f32 (c_format 1), A = B = TF32 (format 2), K-major, M x N
 __host__ __device__ constexpr unsigned g_idesc(int M, int N) {
@@ -121,6 +135,31 @@ __device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
   hi = to_tf32_rn(x);
   lo = to_tf32_rn(x - hi);
 }
+// The same split for the loaders' inner loops.  cvt.rna.tf32 compiles to four instructions (add half
+// an ulp, Inf/NaN test, select, mask); the test is dropped here (Inf stays Inf, NaN stays NaN under
+// add-and-mask), which makes the split 5 instructions per element instead of 9 -- the loaders'
+// issue slots, not HBM, were the limit of these kernels.
+__device__ __forceinline__ float tf32_rn_fast(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+}
+__device__ __forceinline__ void split_tf32_fast(float x, float &hi, float &lo) {
+  hi = tf32_rn_fast(x);
+  lo = tf32_rn_fast(x - hi);
+}
+__device__ __forceinline__ void g_sts128(unsigned addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ float4 g_lds128(unsigned addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void g_sts32(unsigned addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
 
 __global__ void __launch_bounds__(G_THREADS, 1) gemm_nt_3xtf32_kernel(GemmParams p) {
   extern __shared__ unsigned char g_smem_dyn[];
@@ -163,6 +202,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_nt_3xtf32_kernel(GemmParams
     // (~2.4 TB/s chip-wide); four groups working on four consecutive stages keep 64 KB.
     const int lg = (warp - 4) >> 2;
     const int lt = (tid - 128) & 127;
+    const unsigned smem_base = g_smem_u32(smem);
     unsigned it = 0;  // global stage counter
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const long long row0 = (long long)tile * G_TILE;
@@ -172,31 +212,52 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_nt_3xtf32_kernel(GemmParams
         if (lg >= p.nstages || (int)(it % p.nstages) != lg) continue;
         const int st = it % p.nstages;
         const unsigned ph = (it / p.nstages) & 1u;
-        unsigned char *sa_hi = smem + (size_t)st * stage_bytes;
-        unsigned char *sa_lo = sa_hi + G_ASLAB;
-        unsigned char *sb = sa_lo + G_ASLAB;
+        const unsigned sa_hi = smem_base + (unsigned)(st * stage_bytes);
+        const unsigned sa_lo = sa_hi + G_ASLAB;
+        const unsigned sb = sa_lo + G_ASLAB;
+        const long long t0 = clock64();
         g_mbar_wait(g_smem_u32(&s_empty[st]), ph ^ 1u);
-        if (lt == 0) {
+        const long long t1 = clock64();
+        if (lt == 0 && (p.dbg & 8)) g_mbar_arrive(g_smem_u32(&s_full[st]));
+        if (lt == 0 && !(p.dbg & 8)) {
           g_mbar_expect_tx(g_smem_u32(&s_full[st]), 2u * (unsigned)bslab);
-          g_bulk_g2s(g_smem_u32(sb), p.Bimg + (size_t)ks * bslab, (unsigned)bslab,
+          g_bulk_g2s(sb, p.Bimg + (size_t)ks * bslab, (unsigned)bslab, g_smem_u32(&s_full[st]));
+          g_bulk_g2s(sb + bslab, p.Bimg + (size_t)(p.nslab + ks) * bslab, (unsigned)bslab,
                      g_smem_u32(&s_full[st]));
-          g_bulk_g2s(g_smem_u32(sb + bslab), p.Bimg + (size_t)(p.nslab + ks) * bslab,
-                     (unsigned)bslab, g_smem_u32(&s_full[st]));
         }
-        // A slab: 128 rows x 8 chunks of 4 floats; thread lt owns chunk (lt & 7) of rows lt>>3 + 16j
-        const int c = lt & 7;
+        // A slab: 128 rows x 8 chunks of 4 floats; thread lt owns chunk (lt & 7) of rows lt>>3 + 16j.
+        // r & 7 is the same for all eight rows, so the swizzled offsets differ by j * 2048 only.
+        const int c = lt & 7, rb = lt >> 3;
         const int k0 = ks * G_SLABK + c * 4;
+        const unsigned soff = (unsigned)(rb * 128 + ((c ^ (rb & 7)) << 4));
         float4 v[8];
+        if (p.fast) {
+          // rows are 16-byte aligned and K is a multiple of 4: a chunk is loaded whole or not at all
+          if (k0 < p.K && !(p.dbg & 1)) {
+            if (row0 + G_TILE <= p.R) {
+              const float *src = p.A + (row0 + rb) * p.lda + k0;
+              const long long step = 16 * p.lda;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int r = (lt >> 3) + 16 * j;
-          const long long gr = row0 + r;
-          v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (gr < p.R) {
-            const float *src = p.A + gr * p.lda + k0;
-            if (k0 + 3 < p.K && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
-              v[j] = __ldg(reinterpret_cast<const float4 *>(src));
-            } else {
+              for (int j = 0; j < 8; ++j, src += step) v[j] = __ldg(reinterpret_cast<const float4 *>(src));
+            } else {  // ragged last tile: clamp the row (rows >= R are never stored)
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                long long gr = row0 + rb + 16 * j;
+                gr = gr < p.R ? gr : (long long)p.R - 1;
+                v[j] = __ldg(reinterpret_cast<const float4 *>(p.A + gr * p.lda + k0));
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const long long gr = row0 + rb + 16 * j;
+            v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gr < p.R) {
+              const float *src = p.A + gr * p.lda + k0;
               if (k0 + 0 < p.K) v[j].x = __ldg(src + 0);
               if (k0 + 1 < p.K) v[j].y = __ldg(src + 1);
               if (k0 + 2 < p.K) v[j].z = __ldg(src + 2);
@@ -204,20 +265,24 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_nt_3xtf32_kernel(GemmParams
             }
           }
         }
+        if (!(p.dbg & 16))
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const int r = (lt >> 3) + 16 * j;
           float4 hi, lo;
-          split_tf32(v[j].x, hi.x, lo.x);
-          split_tf32(v[j].y, hi.y, lo.y);
-          split_tf32(v[j].z, hi.z, lo.z);
-          split_tf32(v[j].w, hi.w, lo.w);
-          const unsigned off = (unsigned)(r * 128 + ((c ^ (r & 7)) << 4));
-          *reinterpret_cast<float4 *>(sa_hi + off) = hi;
-          *reinterpret_cast<float4 *>(sa_lo + off) = lo;
+          split_tf32_fast(v[j].x, hi.x, lo.x);
+          split_tf32_fast(v[j].y, hi.y, lo.y);
+          split_tf32_fast(v[j].z, hi.z, lo.z);
+          split_tf32_fast(v[j].w, hi.w, lo.w);
+          g_sts128(sa_hi + soff + j * 2048, hi);
+          g_sts128(sa_lo + soff + j * 2048, lo);
         }
+        const long long t2 = clock64();
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         g_mbar_arrive(g_smem_u32(&s_full[st]));
+        if ((p.dbg & 128) && blockIdx.x == 0 && lt == 0 && lg == 0) {
+          g_gemm_prof[0] += t1 - t0; g_gemm_prof[1] += t2 - t1; g_gemm_prof[2] += clock64() - t2;
+          g_gemm_prof[3] += 1;
+        }
       }
     }
   } else if (warp == 4 + 4 * G_LGROUPS) {
@@ -225,15 +290,21 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_nt_3xtf32_kernel(GemmParams
     if (lane == 0) {
       const unsigned idesc = g_idesc(128, p.npad);
       unsigned it = 0, tcount = 0;
+      long long w_acce = 0, w_full = 0, w_issue = 0, t_begin = clock64();
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
         const int acc = tcount & 1;
         const unsigned d = tmem + (unsigned)(acc * 256);
+        long long ta = clock64();
         g_mbar_wait(g_smem_u32(&s_acce[acc]), ((tcount >> 1) & 1u) ^ 1u);  // epilogue drained it
+        w_acce += clock64() - ta;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         for (int ks = 0; ks < p.nslab; ++ks, ++it) {
           const int st = it % p.nstages;
           const unsigned ph = (it / p.nstages) & 1u;
+          ta = clock64();
           g_mbar_wait(g_smem_u32(&s_full[st]), ph);
+          const long long tb = clock64();
+          w_full += tb - ta;
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const unsigned a_hi = g_smem_u32(smem + (size_t)st * stage_bytes);
           const unsigned a_lo = a_hi + G_ASLAB;
@@ -241,14 +312,22 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_nt_3xtf32_kernel(GemmParams
           const unsigned b_lo = b_hi + (unsigned)bslab;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {  // UMMA_K = 8 tf32 = 32 bytes
+            if (p.dbg & 4) break;
             const unsigned o = (unsigned)k * 32u;
             g_mma(d, g_desc(a_hi + o), g_desc(b_hi + o), idesc, (ks | k) ? 1u : 0u);
             g_mma(d, g_desc(a_hi + o), g_desc(b_lo + o), idesc, 1u);
             g_mma(d, g_desc(a_lo + o), g_desc(b_hi + o), idesc, 1u);
           }
-          g_commit(g_smem_u32(&s_empty[st]));  // stage reusable once these MMAs have read it
+          if (p.dbg & 64) g_mbar_arrive(g_smem_u32(&s_empty[st]));
+          else g_commit(g_smem_u32(&s_empty[st]));  // stage reusable once these MMAs have read it
+          w_issue += clock64() - tb;
         }
-        g_commit(g_smem_u32(&s_accf[acc]));    // accumulator complete
+        if (p.dbg & 64) g_mbar_arrive(g_smem_u32(&s_accf[acc]));
+        else g_commit(g_smem_u32(&s_accf[acc]));    // accumulator complete
+      }
+      if ((p.dbg & 128) && blockIdx.x == 0) {
+        g_gemm_prof[4] = w_acce; g_gemm_prof[5] = w_full; g_gemm_prof[6] = w_issue;
+        g_gemm_prof[7] = clock64() - t_begin;
       }
     }
   } else if (warp < 4) {
@@ -257,32 +336,52 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_nt_3xtf32_kernel(GemmParams
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
       const int acc = tcount & 1;
       const long long gr = (long long)tile * G_TILE + warp * 32 + lane;
+      const long long te0 = clock64();
       g_mbar_wait(g_smem_u32(&s_accf[acc]), (tcount >> 1) & 1u);
+      const long long te1 = clock64();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       float *crow = p.C + gr * p.ldc;
-      const bool vec = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+      const bool vec = ((p.ldc & 3) == 0) && ((p.N & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+      // A thread owns an accumulator ROW, so storing straight from registers scatters every warp
+      // store over 32 rows (32 half-filled sectors per instruction; the LSU time of those stores
+      // starved the loaders).  Instead each warp transposes its 32 x 32 block through 4 KB of
+      // shared memory and writes 128 contiguous bytes per quarter-warp.
+      const unsigned stg = g_smem_u32(smem) + (unsigned)(p.nstages * stage_bytes) + (unsigned)(warp * 4096);
+      const int qr = lane >> 3, qc = lane & 7;   // read-back: row qr + 4i, 16-byte chunk qc
       for (int c0 = 0; c0 < p.npad; c0 += 32) {
         unsigned v[32];
+        if (p.dbg & 32) break;
         g_tmem_ld32(tmem + (unsigned)(acc * 256 + c0) + ((unsigned)(warp * 32) << 16), v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (gr < p.R) {
+        if (p.dbg & 2) continue;
+        if (vec) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const int cc = c0 + j;
-            if (vec && cc + 3 < p.N) {
-              *reinterpret_cast<float4 *>(crow + cc) =
-                  make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                              __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-            } else {
+          for (int j = 0; j < 8; ++j)
+            g_sts128(stg + (unsigned)(lane * 128 + ((j ^ (lane & 7)) << 4)),
+                     make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                 __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
+          __syncwarp();
+          const int cc = c0 + qc * 4;
+          const long long grow = (long long)tile * G_TILE + warp * 32 + qr;
+          float *dst = p.C + grow * p.ldc + cc;
 #pragma unroll
-              for (int t = 0; t < 4; ++t)
-                if (cc + t < p.N) crow[cc + t] = __uint_as_float(v[j + t]);
-            }
+          for (int i = 0; i < 8; ++i) {
+            const int rr = qr + 4 * i;
+            const float4 o = g_lds128(stg + (unsigned)(rr * 128 + ((qc ^ (rr & 7)) << 4)));
+            if (grow + 4 * i < p.R && cc < p.N) *reinterpret_cast<float4 *>(dst + (long long)(4 * i) * p.ldc) = o;
           }
+          __syncwarp();
+        } else if (gr < p.R) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c0 + j < p.N) crow[c0 + j] = __uint_as_float(v[j]);
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       g_mbar_arrive(g_smem_u32(&s_acce[acc]));
+      if ((p.dbg & 128) && blockIdx.x == 0 && tid == 0) {
+        g_gemm_prof[8] += te1 - te0; g_gemm_prof[9] += clock64() - te1; g_gemm_prof[10] += 1;
+      }
     }
   }
 
@@ -312,6 +411,8 @@ struct WgradParams {
   float *P;          // [nchunks][N][K] partial sums
   int nchunks;       // row chunks of `chunk` slabs; one partial block each
   int chunk;         // slabs (of 32 rows) accumulated per TMEM accumulator
+  int dbg;           // NESIE_GEMM_DBG & 128: cycle counters of CTA 0
+  int mn;            // 1: MN-major operand tiles (straight float4 copies); 0: transposing loaders
 };
 
 // The tensor core's fp32 accumulation truncates: the error of a serial in-TMEM reduction grows
@@ -382,10 +483,68 @@ __global__ void __launch_bounds__(W_THREADS, 1) gemm_wgrad_3xtf32_kernel(WgradPa
       unsigned char *sb_hi = sa_lo + a_part;
       unsigned char *sb_lo = sb_hi + b_part;
       const long long r0 = (long long)slab * 32;
+      const long long t0 = clock64();
       g_mbar_wait(g_smem_u32(&s_empty[st]), ph ^ 1u);
+      const long long t1 = clock64();
+      const int lw = lt >> 5, ll = lt & 31;       // warp of the group, lane
+      if (p.mn) {
+        // MN-major tiles: the channels of a reduction row are contiguous in memory and in the
+        // operand tile, so a warp store covers one 512-byte atom (4 rows x 32 channels) with plain
+        // float4 copies: lane = 16-byte chunk (ll & 7) of row (ll >> 3).
+        const int c16 = ll & 7, j = ll >> 3;
+        const unsigned sw = (unsigned)(j * 128 + (((c16 >> 1) ^ j) << 5) + ((c16 & 1) << 4));
+        const unsigned sa = g_smem_u32(sa_hi), sbb = g_smem_u32(sb_hi);
+        {
+          float4 v[8];
+          const int ch = m0 + lw * 32 + c16 * 4;
+          const float *src = p.A + (r0 + j) * p.lda + ch;
+          const long long step = 4 * p.lda;
+#pragma unroll
+          for (int i = 0; i < 8; ++i, src += step)
+            v[i] = (r0 + i * 4 + j < p.R && ch < p.N) ? __ldg(reinterpret_cast<const float4 *>(src))
+                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4 hi, lo;
+            split_tf32_fast(v[i].x, hi.x, lo.x);
+            split_tf32_fast(v[i].y, hi.y, lo.y);
+            split_tf32_fast(v[i].z, hi.z, lo.z);
+            split_tf32_fast(v[i].w, hi.w, lo.w);
+            const unsigned off = (unsigned)(lw * 4096 + i * 512) + sw;
+            g_sts128(sa + off, hi);
+            g_sts128(sa + (unsigned)a_part + off, lo);
+          }
+        }
+        const int natoms = (p.kp >> 5) * 8;       // (32-channel block, 4-row group) pairs of the B tile
+        for (int t0 = lw; t0 < natoms; t0 += 16) {
+          float4 v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int idx = t0 + 4 * u;
+            const int ch = (idx >> 3) * 32 + c16 * 4;
+            long long gr = r0 + (idx & 7) * 4 + j;
+            gr = gr < p.R ? gr : (long long)p.R - 1;  // A is zero there; any finite value will do
+            v[u] = (idx < natoms && ch < p.K) ? __ldg(reinterpret_cast<const float4 *>(p.B + gr * p.ldb + ch))
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int idx = t0 + 4 * u;
+            if (idx < natoms) {
+              float4 hi, lo;
+              split_tf32_fast(v[u].x, hi.x, lo.x);
+              split_tf32_fast(v[u].y, hi.y, lo.y);
+              split_tf32_fast(v[u].z, hi.z, lo.z);
+              split_tf32_fast(v[u].w, hi.w, lo.w);
+              const unsigned off = (unsigned)((idx >> 3) * 4096 + (idx & 7) * 512) + sw;
+              g_sts128(sbb + off, hi);
+              g_sts128(sbb + (unsigned)b_part + off, lo);
+            }
+          }
+        }
+      } else {
       // Transposing loads: lane <-> reduction row (r0 + lane), so the four scalar stores of a
       // float4 go to four operand rows (channels) at 32 distinct words each: conflict-free.
-      const int lw = lt >> 5, ll = lt & 31;       // warp of the group, lane
       const long long gr = r0 + ll;
       const bool rok = gr < p.R;
       // ---- A tile: operand rows = 128 channels (m0..), 32 reduction elements per row
@@ -447,24 +606,36 @@ __global__ void __launch_bounds__(W_THREADS, 1) gemm_wgrad_3xtf32_kernel(WgradPa
           *reinterpret_cast<float *>(sb_lo + off) = lo;
         }
       }
+      }
+      const long long t2 = clock64();
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       g_mbar_arrive(g_smem_u32(&s_full[st]));
+      if ((p.dbg & 128) && blockIdx.x == 0 && blockIdx.y == 0 && lt == 0 && lg == 0) {
+        g_gemm_prof[0] += t1 - t0; g_gemm_prof[1] += t2 - t1; g_gemm_prof[2] += clock64() - t2;
+        g_gemm_prof[3] += 1;
+      }
     }
   } else if (warp == 4 + 4 * G_LGROUPS) {
     // ================================ MMA issuer =============================================
     if (lane == 0) {
       unsigned it = 0, ccount = 0;
+      long long w_acce = 0, w_full = 0, w_issue = 0, t_begin = clock64();
       for (int chunk = blockIdx.x; chunk < p.nchunks; chunk += gridDim.x, ++ccount) {
       const int acc = nacc == 2 ? (int)(ccount & 1) : 0;
       const unsigned dbase = tmem + (unsigned)(acc * 256);
       const unsigned use = nacc == 2 ? (ccount >> 1) : ccount;  // how often this accumulator was used
+      long long ta = clock64();
       g_mbar_wait(g_smem_u32(&s_acce[acc]), (use & 1u) ^ 1u);   // epilogue has drained it
+      w_acce += clock64() - ta;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       bool first = true;
       for (int slab = chunk * p.chunk; slab < min(nslab, (chunk + 1) * p.chunk); ++slab, ++it) {
         const int st = it % p.nstages;
         const unsigned ph = (it / p.nstages) & 1u;
+        ta = clock64();
         g_mbar_wait(g_smem_u32(&s_full[st]), ph);
+        const long long tb = clock64();
+        w_full += tb - ta;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const unsigned a_hi = g_smem_u32(smem + (size_t)st * stage_bytes);
         const unsigned a_lo = a_hi + (unsigned)a_part;
@@ -475,18 +646,31 @@ __global__ void __launch_bounds__(W_THREADS, 1) gemm_wgrad_3xtf32_kernel(WgradPa
           const unsigned o = (unsigned)ks * 32u;
           for (int n0 = 0; n0 < p.kp; n0 += 256) {
             const int nn = min(256, p.kp - n0);
-            const unsigned idesc = g_idesc(128, nn);
-            const unsigned bo = (unsigned)n0 * 128u + o;  // operand rows n0.. of the B tile
             const unsigned d = dbase + (unsigned)n0;
-            g_mma(d, g_desc(a_hi + o), g_desc(b_hi + bo), idesc, first ? 0u : 1u);
-            g_mma(d, g_desc(a_hi + o), g_desc(b_lo + bo), idesc, 1u);
-            g_mma(d, g_desc(a_lo + o), g_desc(b_hi + bo), idesc, 1u);
+            if (p.mn) {  // 8 reduction rows = two 512-byte K atoms; 32-channel blocks 4096 bytes apart
+              const unsigned idesc = g_idesc(128, nn) | (1u << 15) | (1u << 16);  // A and B MN-major
+              const unsigned ao = (unsigned)ks * 1024u, bo = (unsigned)n0 * 128u + ao;
+              g_mma(d, g_desc_mn(a_hi + ao, 4096, 512), g_desc_mn(b_hi + bo, 4096, 512), idesc, first ? 0u : 1u);
+              g_mma(d, g_desc_mn(a_hi + ao, 4096, 512), g_desc_mn(b_lo + bo, 4096, 512), idesc, 1u);
+              g_mma(d, g_desc_mn(a_lo + ao, 4096, 512), g_desc_mn(b_hi + bo, 4096, 512), idesc, 1u);
+            } else {
+              const unsigned idesc = g_idesc(128, nn);
+              const unsigned bo = (unsigned)n0 * 128u + o;  // operand rows n0.. of the B tile
+              g_mma(d, g_desc(a_hi + o), g_desc(b_hi + bo), idesc, first ? 0u : 1u);
+              g_mma(d, g_desc(a_hi + o), g_desc(b_lo + bo), idesc, 1u);
+              g_mma(d, g_desc(a_lo + o), g_desc(b_hi + bo), idesc, 1u);
+            }
           }
           first = false;
         }
         g_commit(g_smem_u32(&s_empty[st]));
+        w_issue += clock64() - tb;
       }
       g_commit(g_smem_u32(&s_accf[acc]));
+      }
+      if ((p.dbg & 128) && blockIdx.x == 0 && blockIdx.y == 0) {
+        g_gemm_prof[4] = w_acce; g_gemm_prof[5] = w_full; g_gemm_prof[6] = w_issue;
+        g_gemm_prof[7] = clock64() - t_begin;
       }
     }
   } else if (warp < 4) {
@@ -496,7 +680,9 @@ __global__ void __launch_bounds__(W_THREADS, 1) gemm_wgrad_3xtf32_kernel(WgradPa
     for (int chunk = blockIdx.x; chunk < p.nchunks; chunk += gridDim.x, ++ccount) {
       const int acc = nacc == 2 ? (int)(ccount & 1) : 0;
       const unsigned use = nacc == 2 ? (ccount >> 1) : ccount;
+      const long long te0 = clock64();
       g_mbar_wait(g_smem_u32(&s_accf[acc]), use & 1u);
+      const long long te1 = clock64();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       float *prow = p.P + ((size_t)chunk * p.N + n) * p.K;
       for (int c0 = 0; c0 < p.kp; c0 += 32) {
@@ -511,6 +697,9 @@ __global__ void __launch_bounds__(W_THREADS, 1) gemm_wgrad_3xtf32_kernel(WgradPa
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       g_mbar_arrive(g_smem_u32(&s_acce[acc]));
+      if ((p.dbg & 128) && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) {
+        g_gemm_prof[8] += te1 - te0; g_gemm_prof[9] += clock64() - te1; g_gemm_prof[10] += 1;
+      }
     }
   }
 
@@ -563,6 +752,18 @@ extern "C" int nesie_gemm_pack_b(int n, int k, long long stride_n, long long str
   return check_launch("nesie_gemm_pack_b");
 }
 
+// Diagnostic: cycle counters of CTA 0 accumulated by NT launches made with NESIE_GEMM_DBG & 128
+// (loader: wait-empty, fill, publish, slabs; MMA thread: wait-acc, wait-full, issue, total;
+// epilogue: wait-acc, drain, tiles).  Reading resets them.
+extern "C" int nesie_gemm_debug_profile(long long *out16) {
+  NESIE_REQUIRE(out16, "null pointer");
+  NESIE_CUDA(cudaDeviceSynchronize());
+  NESIE_CUDA(cudaMemcpyFromSymbol(out16, g_gemm_prof, sizeof(long long) * 16));
+  long long zero[16] = {0};
+  NESIE_CUDA(cudaMemcpyToSymbol(g_gemm_prof, zero, sizeof(zero)));
+  return NESIE_OK;
+}
+
 extern "C" int nesie_gemm_nt_3xtf32(long long r, int n, int k, const float *a, long long lda,
                                     const void *b_image, float *c, long long ldc, void *stream) {
   NESIE_REQUIRE(r >= 0 && n >= 1 && n <= 256 && k >= 1, "need r >= 0, 1 <= n <= 256, k >= 1");
@@ -576,10 +777,12 @@ extern "C" int nesie_gemm_nt_3xtf32(long long r, int n, int k, const float *a, l
   p.nslab = (k + 31) / 32;
   p.lda = lda; p.ldc = ldc;
   p.A = a; p.Bimg = reinterpret_cast<const unsigned char *>(b_image); p.C = c;
+  p.fast = ((lda & 3) == 0) && ((k & 3) == 0) && ((reinterpret_cast<uintptr_t>(a) & 15) == 0);
+  { const char *e = getenv("NESIE_GEMM_DBG"); p.dbg = e ? atoi(e) : 0; }
   const size_t stage = 2 * G_ASLAB + 2 * (size_t)p.npad * 128;
-  p.nstages = (int)((226 * 1024) / stage);
+  p.nstages = (int)((226 * 1024 - G_EPI_STAGE) / stage);
   if (p.nstages > G_MAXSTAGES) p.nstages = G_MAXSTAGES;
-  const size_t smem = (size_t)p.nstages * stage + 1024;
+  const size_t smem = (size_t)p.nstages * stage + G_EPI_STAGE + 1024;
   NESIE_CUDA(cudaFuncSetAttribute(gemm_nt_3xtf32_kernel,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int ntiles = (p.R + G_TILE - 1) / G_TILE;
@@ -617,6 +820,10 @@ extern "C" int nesie_gemm_wgrad_3xtf32(long long r, int n, int k, const float *a
   NESIE_CUDA(cudaFuncSetAttribute(gemm_wgrad_3xtf32_kernel,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   p.nchunks = nsplits;
+  p.mn = ((lda & 3) == 0) && ((ldb & 3) == 0) && ((n & 3) == 0) && ((k & 3) == 0) &&
+         (((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0);
+  { const char *e = getenv("NESIE_GEMM_DBG"); p.dbg = e ? atoi(e) : 0; }
+  { const char *e = getenv("NESIE_WGRAD_LAYOUT"); if (e && e[0] == 't') p.mn = 0; }
   p.chunk = wgrad_chunk((r + 31) / 32, (n + 127) / 128);
   const int mblocks = (n + 127) / 128;
   int gx = num_sms() / mblocks;

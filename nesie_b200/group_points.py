@@ -109,10 +109,12 @@ class _QueryGroupConcat(Function):
 class _QueryGroupRows(Function):
     """Row-major grouped tensor (B*npoint*nsample, 3 + C) for the GEMM formulation of the shared
     MLP: [ (xyz[idx] - centre) * (1/radius) | features[idx] ] per row.  Same values as
-    _QueryGroupConcat, different layout; gradients to features, points_xyz and center_xyz."""
+    _QueryGroupConcat, different layout; gradients to features, points_xyz and center_xyz.
+    pad_to > 1 rounds the row width up to a multiple of it with zero columns (16-byte aligned rows
+    for the GEMM's vector loads; the matching weight columns are zero-padded by the caller)."""
 
     @staticmethod
-    def forward(ctx, points_xyz, center_xyz, features, idx, radius):
+    def forward(ctx, points_xyz, center_xyz, features, idx, radius, pad_to=1):
         _lib.need_cuda(points_xyz, center_xyz, features, idx)
         points_xyz = points_xyz.contiguous()
         center_xyz = center_xyz.contiguous()
@@ -120,14 +122,16 @@ class _QueryGroupRows(Function):
         npoint, nsample = idx.shape[1], idx.shape[2]
         C = 0 if features is None else features.shape[1]
         table = None if features is None else features.transpose(1, 2).contiguous()  # (B, N, C)
-        rows = torch.empty((B * npoint * nsample, 3 + C), dtype=torch.float32,
+        ld = -(-(3 + C) // pad_to) * pad_to
+        rows = torch.empty((B * npoint * nsample, ld), dtype=torch.float32,
                            device=points_xyz.device)
         with torch.cuda.device(points_xyz.device):
             _lib.call("nesie_group_rows", B, C, N, npoint, nsample, _lib.ptr(points_xyz),
                       _lib.ptr(center_xyz), _lib.ptr(table), _lib.ptr(idx), float(radius),
-                      _lib.ptr(rows), _lib.stream())
+                      _lib.ptr(rows), ld, _lib.stream())
         ctx.save_for_backward(idx)
         ctx.shape = (B, C, N, npoint, nsample)
+        ctx.ld = ld
         ctx.radius = float(radius)
         return rows
 
@@ -147,9 +151,9 @@ class _QueryGroupRows(Function):
             with torch.cuda.device(dev):
                 _lib.call("nesie_group_rows_grad", B, C, N, npoint, nsample, _lib.ptr(grad_rows),
                           _lib.ptr(idx), ctx.radius, _lib.ptr(g_table), _lib.ptr(g_xyz),
-                          _lib.ptr(g_center), _lib.stream())
+                          _lib.ptr(g_center), ctx.ld, _lib.stream())
         g_feat = g_table.transpose(1, 2).contiguous() if g_table is not None else None
-        return g_xyz, g_center, g_feat, None, None
+        return g_xyz, g_center, g_feat, None, None, None
 
 
 class QueryAndGroup(nn.Module):
@@ -180,12 +184,13 @@ class QueryAndGroup(nn.Module):
         if self.uniform_sample:
             raise NotImplementedError('uniform_sample is outside the Nesie hot path')
 
-    def forward_rows(self, points_xyz, center_xyz, features):
-        """Row-major variant for the GEMM-form shared MLP: (B*npoint*sample_num, 3+C) rows."""
+    def forward_rows(self, points_xyz, center_xyz, features, pad_to=1):
+        """Row-major variant for the GEMM-form shared MLP: (B*npoint*sample_num, 3+C) rows
+        (row width rounded up to a multiple of pad_to with zero columns)."""
         idx = ball_query(self.min_radius, self.max_radius, self.sample_num,
                          points_xyz.contiguous(), center_xyz.contiguous())
         radius = self.max_radius if self.normalize_xyz else 0.0
-        return _QueryGroupRows.apply(points_xyz, center_xyz, features, idx, radius)
+        return _QueryGroupRows.apply(points_xyz, center_xyz, features, idx, radius, pad_to)
 
     def forward(self, points_xyz, center_xyz, features=None):
         """points_xyz (B,N,3), center_xyz (B,npoint,3), features (B,C,N) ->

@@ -187,7 +187,10 @@ class BasePointSAModule(nn.Module):
         for li, layer in enumerate(layers):
             bn = layer.bn
             # fp32-parity GEMM on tcgen05 (3xTF32); NESIE_ROWS_GEMM=cublas selects the library GEMM
-            x = _rows_linear(x, layer.conv.weight.flatten(1))
+            w = layer.conv.weight.flatten(1)
+            if x.shape[1] != w.shape[1]:  # grouped rows were zero-padded to a multiple of 4 columns
+                w = F.pad(w, (0, x.shape[1] - w.shape[1]))
+            x = _rows_linear(x, w)
             last = li == len(layers) - 1
             if _fused_bn() and bn_rows.supported(x, bn, K if last else 0):
                 # fused BatchNorm(batch stats) + ReLU (+ the max-pool over the K rows of a group)
@@ -214,7 +217,7 @@ class BasePointSAModule(nn.Module):
             if self.rows_mlp and points_xyz.is_cuda and features is not None and \
                     self._rows_ok(i, None):
                 g = self.groupers[i]
-                rows = g.forward_rows(points_xyz, new_xyz, features)
+                rows = g.forward_rows(points_xyz, new_xyz, features, pad_to=4)
                 new_features_list.append(self._mlp_rows(i, rows, points_xyz.shape[0],
                                                         new_xyz.shape[1], g.sample_num))
                 continue

@@ -177,6 +177,31 @@ def test_query_and_group_matches_unfused_reference_graph():
         assert torch.allclose(cg.grad.cpu(), cc.grad, rtol=1e-4, atol=1e-4)
 
 
+@pytest.mark.parametrize("pad_to", [1, 4])
+def test_query_and_group_rows_layout_matches_channel_major(pad_to):
+    """The row-major (GEMM) grouped tensor holds the same bits as the reference-layout one; padded
+    columns are zero and receive no gradient."""
+    xyz = scene_xyz(2, 3000, 11)
+    feats = torch.randn(2, 6, 3000)
+    centres = xyz[:, :128].contiguous()
+    grouper = nb.QueryAndGroup(0.3, 16, use_xyz=True, normalize_xyz=True)
+    xa, ca, fa = (dev(t).requires_grad_(True) for t in (xyz, centres, feats))
+    xb, cb, fb = (dev(t).requires_grad_(True) for t in (xyz, centres, feats))
+    want = grouper(xa, ca, fa)                                   # (B, 9, 128, 16)
+    rows = grouper.forward_rows(xb, cb, fb, pad_to=pad_to)       # (B*128*16, ld)
+    ld = -(-9 // pad_to) * pad_to
+    assert rows.shape == (2 * 128 * 16, ld)
+    assert torch.equal(rows[:, :9].view(2, 128, 16, 9).permute(0, 3, 1, 2), want)
+    assert (rows[:, 9:] == 0).all()
+    g = torch.randn_like(want)
+    want.backward(g)
+    grows = torch.full_like(rows, 7.0)                           # garbage in the padding columns
+    grows[:, :9] = g.permute(0, 2, 3, 1).reshape(-1, 9)
+    rows.backward(grows)
+    for a, b in ((xa, xb), (ca, cb), (fa, fb)):
+        assert torch.allclose(a.grad, b.grad, rtol=1e-5, atol=1e-5)
+
+
 # ---------------------------------------------------------------- three_nn / interpolate
 @pytest.mark.parametrize("B,n,m", [(2, 512, 256), (2, 1024, 512), (1, 7, 2), (1, 5, 1), (1, 3000, 2500)])
 def test_three_nn(B, n, m):
