@@ -29,9 +29,10 @@ constexpr int G_TILE = 128;
 constexpr int G_SLABK = 32;            // fp32 elements per 128-byte swizzle row
 constexpr int G_MAXSTAGES = 4;
 constexpr int G_LGROUPS = 4;                       // loader groups of 128 threads (stage it -> group it % 4)
-constexpr int G_THREADS = 128 + 128 * G_LGROUPS + 32;  // epilogue + loaders + MMA warp
+constexpr int G_EPIW = 8;                          // NT epilogue warps: 2 per TMEM lane quarter
+constexpr int G_THREADS = 32 * G_EPIW + 128 * G_LGROUPS + 32;  // epilogue + loaders + MMA warp
 constexpr int G_ASLAB = G_TILE * 128;  // bytes of one A part-slab
-constexpr int G_EPI_STAGE = 4 * 4096;  // epilogue transpose staging: 32 rows x 128 B per warp
+constexpr int G_EPI_STAGE = G_EPIW * 4096;  // epilogue transpose staging: 32 rows x 128 B per warp
 
 // cycle counters of CTA 0 (NESIE_GEMM_DBG bit 128), read back by nesie_gemm_debug_profile
 __device__ long long g_gemm_prof[16];
@@ -74,6 +75,12 @@ __device__ __forceinline__ void g_mma(unsigned d, unsigned long long a, unsigned
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc)
       : "memory");
+}
+// true in exactly one lane of a converged warp
+__device__ __forceinline__ bool g_elect_one() {
+  unsigned pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void g_commit(unsigned mbar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar)
@@ -187,7 +194,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_nt_3xtf32_kernel(GemmParams
     }
     for (int a = 0; a < 2; ++a) {
       g_mbar_init(g_smem_u32(&s_accf[a]), 1);
-      g_mbar_init(g_smem_u32(&s_acce[a]), 128);
+      g_mbar_init(g_smem_u32(&s_acce[a]), 32 * G_EPIW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -196,12 +203,12 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_nt_3xtf32_kernel(GemmParams
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const unsigned tmem = s_tmem;
 
-  if (warp >= 4 && warp < 4 + 4 * G_LGROUPS) {
+  if (warp >= G_EPIW && warp < G_EPIW + 4 * G_LGROUPS) {
     // ================================ loaders ================================================
     // Bandwidth = bytes in flight / latency: one group only keeps 16 KB of loads in flight per SM
     // (~2.4 TB/s chip-wide); four groups working on four consecutive stages keep 64 KB.
-    const int lg = (warp - 4) >> 2;
-    const int lt = (tid - 128) & 127;
+    const int lg = (warp - G_EPIW) >> 2;
+    const int lt = (tid - 32 * G_EPIW) & 127;
     const unsigned smem_base = g_smem_u32(smem);
     unsigned it = 0;  // global stage counter
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -285,9 +292,12 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_nt_3xtf32_kernel(GemmParams
         }
       }
     }
-  } else if (warp == 4 + 4 * G_LGROUPS) {
+  } else if (warp == G_EPIW + 4 * G_LGROUPS) {
     // ================================ MMA issuer =============================================
-    if (lane == 0) {
+    // The whole warp runs the loop (uniform control flow keeps descriptors in uniform registers:
+    // issued from inside an `if (lane == 0)` region every MMA cost an ELECT + 5 R2UR round trip);
+    // one elected lane issues the MMAs and commits.
+    {
       const unsigned idesc = g_idesc(128, p.npad);
       unsigned it = 0, tcount = 0;
       long long w_acce = 0, w_full = 0, w_issue = 0, t_begin = clock64();
@@ -306,36 +316,41 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_nt_3xtf32_kernel(GemmParams
           const long long tb = clock64();
           w_full += tb - ta;
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const unsigned a_hi = g_smem_u32(smem + (size_t)st * stage_bytes);
-          const unsigned a_lo = a_hi + G_ASLAB;
-          const unsigned b_hi = a_lo + G_ASLAB;
-          const unsigned b_lo = b_hi + (unsigned)bslab;
+          const unsigned a_hi = g_smem_u32(smem) + (unsigned)(st * stage_bytes);
+          const unsigned long long ah0 = g_desc(a_hi), al0 = ah0 + (G_ASLAB >> 4);
+          const unsigned long long bh0 = al0 + (G_ASLAB >> 4), bl0 = bh0 + (unsigned long long)(bslab >> 4);
+          if (g_elect_one()) {
+            if (!(p.dbg & 4)) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {  // UMMA_K = 8 tf32 = 32 bytes
-            if (p.dbg & 4) break;
-            const unsigned o = (unsigned)k * 32u;
-            g_mma(d, g_desc(a_hi + o), g_desc(b_hi + o), idesc, (ks | k) ? 1u : 0u);
-            g_mma(d, g_desc(a_hi + o), g_desc(b_lo + o), idesc, 1u);
-            g_mma(d, g_desc(a_lo + o), g_desc(b_hi + o), idesc, 1u);
+              for (int k = 0; k < 4; ++k) {  // UMMA_K = 8 tf32 = 32 bytes = 2 descriptor units
+                g_mma(d, ah0 + 2 * k, bh0 + 2 * k, idesc, (ks | k) ? 1u : 0u);
+                g_mma(d, ah0 + 2 * k, bl0 + 2 * k, idesc, 1u);
+                g_mma(d, al0 + 2 * k, bh0 + 2 * k, idesc, 1u);
+              }
+            }
+            if (p.dbg & 64) g_mbar_arrive(g_smem_u32(&s_empty[st]));
+            else g_commit(g_smem_u32(&s_empty[st]));  // stage reusable once these MMAs have read it
+            if (ks == p.nslab - 1) {
+              if (p.dbg & 64) g_mbar_arrive(g_smem_u32(&s_accf[acc]));
+              else g_commit(g_smem_u32(&s_accf[acc]));    // accumulator complete
+            }
           }
-          if (p.dbg & 64) g_mbar_arrive(g_smem_u32(&s_empty[st]));
-          else g_commit(g_smem_u32(&s_empty[st]));  // stage reusable once these MMAs have read it
+          __syncwarp();
           w_issue += clock64() - tb;
         }
-        if (p.dbg & 64) g_mbar_arrive(g_smem_u32(&s_accf[acc]));
-        else g_commit(g_smem_u32(&s_accf[acc]));    // accumulator complete
       }
-      if ((p.dbg & 128) && blockIdx.x == 0) {
+      if ((p.dbg & 128) && blockIdx.x == 0 && lane == 0) {
         g_gemm_prof[4] = w_acce; g_gemm_prof[5] = w_full; g_gemm_prof[6] = w_issue;
         g_gemm_prof[7] = clock64() - t_begin;
       }
     }
-  } else if (warp < 4) {
+  } else if (warp < G_EPIW) {
     // ================================ epilogue ===============================================
     unsigned tcount = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
       const int acc = tcount & 1;
-      const long long gr = (long long)tile * G_TILE + warp * 32 + lane;
+      const int q = warp & 3, half = warp >> 2;  // TMEM lane quarter (fixed by warp % 4), column interleave
+      const long long gr = (long long)tile * G_TILE + q * 32 + lane;
       const long long te0 = clock64();
       g_mbar_wait(g_smem_u32(&s_accf[acc]), (tcount >> 1) & 1u);
       const long long te1 = clock64();
@@ -348,10 +363,10 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_nt_3xtf32_kernel(GemmParams
       // shared memory and writes 128 contiguous bytes per quarter-warp.
       const unsigned stg = g_smem_u32(smem) + (unsigned)(p.nstages * stage_bytes) + (unsigned)(warp * 4096);
       const int qr = lane >> 3, qc = lane & 7;   // read-back: row qr + 4i, 16-byte chunk qc
-      for (int c0 = 0; c0 < p.npad; c0 += 32) {
+      for (int c0 = half * 32; c0 < p.npad; c0 += 32 * (G_EPIW / 4)) {
         unsigned v[32];
         if (p.dbg & 32) break;
-        g_tmem_ld32(tmem + (unsigned)(acc * 256 + c0) + ((unsigned)(warp * 32) << 16), v);
+        g_tmem_ld32(tmem + (unsigned)(acc * 256 + c0) + ((unsigned)(q * 32) << 16), v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (p.dbg & 2) continue;
         if (vec) {
@@ -362,7 +377,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_nt_3xtf32_kernel(GemmParams
                                  __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
           __syncwarp();
           const int cc = c0 + qc * 4;
-          const long long grow = (long long)tile * G_TILE + warp * 32 + qr;
+          const long long grow = (long long)tile * G_TILE + q * 32 + qr;
           float *dst = p.C + grow * p.ldc + cc;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -412,7 +427,9 @@ struct WgradParams {
   int nchunks;       // row chunks of `chunk` slabs; one partial block each
   int chunk;         // slabs (of 32 rows) accumulated per TMEM accumulator
   int dbg;           // NESIE_GEMM_DBG & 128: cycle counters of CTA 0
-  int mn;            // 1: MN-major operand tiles (straight float4 copies); 0: transposing loaders
+  int mn;            // bit 0: B tile MN-major, bit 1: A tile MN-major (straight float4 copies);
+                     // a clear bit selects the transposing loader and a K-major tile
+  int vec;           // rows 16-byte aligned, channel counts multiples of 4
 };
 
 // The tensor core's fp32 accumulation truncates: the error of a serial in-TMEM reduction grows
@@ -487,68 +504,55 @@ __global__ void __launch_bounds__(W_THREADS, 1) gemm_wgrad_3xtf32_kernel(WgradPa
       g_mbar_wait(g_smem_u32(&s_empty[st]), ph ^ 1u);
       const long long t1 = clock64();
       const int lw = lt >> 5, ll = lt & 31;       // warp of the group, lane
-      if (p.mn) {
-        // MN-major tiles: the channels of a reduction row are contiguous in memory and in the
-        // operand tile, so a warp store covers one 512-byte atom (4 rows x 32 channels) with plain
-        // float4 copies: lane = 16-byte chunk (ll & 7) of row (ll >> 3).
-        const int c16 = ll & 7, j = ll >> 3;
-        const unsigned sw = (unsigned)(j * 128 + (((c16 >> 1) ^ j) << 5) + ((c16 & 1) << 4));
-        const unsigned sa = g_smem_u32(sa_hi), sbb = g_smem_u32(sb_hi);
-        {
-          float4 v[8];
-          const int ch = m0 + lw * 32 + c16 * 4;
-          const float *src = p.A + (r0 + j) * p.lda + ch;
-          const long long step = 4 * p.lda;
-#pragma unroll
-          for (int i = 0; i < 8; ++i, src += step)
-            v[i] = (r0 + i * 4 + j < p.R && ch < p.N) ? __ldg(reinterpret_cast<const float4 *>(src))
-                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float4 hi, lo;
-            split_tf32_fast(v[i].x, hi.x, lo.x);
-            split_tf32_fast(v[i].y, hi.y, lo.y);
-            split_tf32_fast(v[i].z, hi.z, lo.z);
-            split_tf32_fast(v[i].w, hi.w, lo.w);
-            const unsigned off = (unsigned)(lw * 4096 + i * 512) + sw;
-            g_sts128(sa + off, hi);
-            g_sts128(sa + (unsigned)a_part + off, lo);
-          }
-        }
-        const int natoms = (p.kp >> 5) * 8;       // (32-channel block, 4-row group) pairs of the B tile
-        for (int t0 = lw; t0 < natoms; t0 += 16) {
-          float4 v[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int idx = t0 + 4 * u;
-            const int ch = (idx >> 3) * 32 + c16 * 4;
-            long long gr = r0 + (idx & 7) * 4 + j;
-            gr = gr < p.R ? gr : (long long)p.R - 1;  // A is zero there; any finite value will do
-            v[u] = (idx < natoms && ch < p.K) ? __ldg(reinterpret_cast<const float4 *>(p.B + gr * p.ldb + ch))
-                                              : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int idx = t0 + 4 * u;
-            if (idx < natoms) {
-              float4 hi, lo;
-              split_tf32_fast(v[u].x, hi.x, lo.x);
-              split_tf32_fast(v[u].y, hi.y, lo.y);
-              split_tf32_fast(v[u].z, hi.z, lo.z);
-              split_tf32_fast(v[u].w, hi.w, lo.w);
-              const unsigned off = (unsigned)((idx >> 3) * 4096 + (idx & 7) * 512) + sw;
-              g_sts128(sbb + off, hi);
-              g_sts128(sbb + (unsigned)b_part + off, lo);
-            }
-          }
-        }
-      } else {
-      // Transposing loads: lane <-> reduction row (r0 + lane), so the four scalar stores of a
-      // float4 go to four operand rows (channels) at 32 distinct words each: conflict-free.
+      const unsigned sa = g_smem_u32(sa_hi), sbb = g_smem_u32(sb_hi);
+      // MN-major tiles: the channels of a reduction row are contiguous in memory and in the
+      // operand tile, so a warp store covers one 512-byte atom (4 rows x 32 channels) with plain
+      // float4 copies: lane = 16-byte chunk (ll & 7) of row (ll >> 3).
+      const int c16 = ll & 7, j4 = ll >> 3;
+      const unsigned sw = (unsigned)(j4 * 128 + (((c16 >> 1) ^ j4) << 5) + ((c16 & 1) << 4));
+      // Transposing (K-major) tiles: lane <-> reduction row (r0 + lane), so the four scalar stores
+      // of a float4 go to four operand rows (channels) at 32 distinct words: conflict-free.
       const long long gr = r0 + ll;
       const bool rok = gr < p.R;
-      // ---- A tile: operand rows = 128 channels (m0..), 32 reduction elements per row
-      {
+      const unsigned tw = (unsigned)(((ll >> 2) << 4) + ((ll & 3) << 2));  // chunk ll>>2, word ll&3
+      // MN-major B tile: (32-channel block, 4-row group) pairs, four per warp and batch.  The first
+      // batch is requested together with the A tile so that a slab costs one memory round trip.
+      const int natoms = (p.kp >> 5) * 8;
+      auto load_b = [&](int t0, float4 (&v)[4]) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int idx = t0 + 4 * u;
+          const int ch = (idx >> 3) * 32 + c16 * 4;
+          long long g2 = r0 + (idx & 7) * 4 + j4;
+          g2 = g2 < p.R ? g2 : (long long)p.R - 1;  // A is zero there; any finite value will do
+          v[u] = (idx < natoms && ch < p.K) ? __ldg(reinterpret_cast<const float4 *>(p.B + g2 * p.ldb + ch))
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      float4 vb[4], vb_next[4];
+      if (p.mn & 1) load_b(lw, vb);
+      // ---- A tile: 128 channels (m0..) x 32 reduction rows
+      if (p.mn & 2) {
+        float4 v[8];
+        const int ch = m0 + lw * 32 + c16 * 4;
+        const float *src = p.A + (r0 + j4) * p.lda + ch;
+        const long long step = 4 * p.lda;
+#pragma unroll
+        for (int i = 0; i < 8; ++i, src += step)
+          v[i] = (r0 + i * 4 + j4 < p.R && ch < p.N) ? __ldg(reinterpret_cast<const float4 *>(src))
+                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 hi, lo;
+          split_tf32_fast(v[i].x, hi.x, lo.x);
+          split_tf32_fast(v[i].y, hi.y, lo.y);
+          split_tf32_fast(v[i].z, hi.z, lo.z);
+          split_tf32_fast(v[i].w, hi.w, lo.w);
+          const unsigned off = (unsigned)(lw * 4096 + i * 512) + sw;
+          g_sts128(sa + off, hi);
+          g_sts128(sa + (unsigned)a_part + off, lo);
+        }
+      } else {
         float4 v[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -556,7 +560,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) gemm_wgrad_3xtf32_kernel(WgradPa
           v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (rok && ch < p.N) {
             const float *src = p.A + gr * p.lda + ch;
-            if (ch + 3 < p.N && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+            if (p.vec) {
               v[i] = __ldg(reinterpret_cast<const float4 *>(src));
             } else {
               v[i].x = __ldg(src);
@@ -571,41 +575,62 @@ __global__ void __launch_bounds__(W_THREADS, 1) gemm_wgrad_3xtf32_kernel(WgradPa
           const float e[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const int n = lw * 32 + i * 4 + j;  // operand row
+            const int n = lw * 32 + i * 4 + j;  // operand row; n & 7 == (i * 4 + j) & 7
             float hi, lo;
-            split_tf32(e[j], hi, lo);
-            const unsigned off = (unsigned)(n * 128 + ((((ll >> 2) ^ (n & 7))) << 4) + ((ll & 3) << 2));
-            *reinterpret_cast<float *>(sa_hi + off) = hi;
-            *reinterpret_cast<float *>(sa_lo + off) = lo;
+            split_tf32_fast(e[j], hi, lo);
+            const unsigned off = (unsigned)(n * 128) + (tw ^ (unsigned)(((i * 4 + j) & 7) << 4));
+            g_sts32(sa + off, hi);
+            g_sts32(sa + (unsigned)a_part + off, lo);
           }
         }
       }
-      // ---- B tile: operand rows = kp channels of X, 32 reduction elements per row
-      for (int c4 = lw; c4 < kq; c4 += 4) {
-        const int k0 = c4 * 4;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (rok && k0 < p.K) {
-          const float *src = p.B + gr * p.ldb + k0;
-          if (k0 + 3 < p.K && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
-            v = __ldg(reinterpret_cast<const float4 *>(src));
-          } else {
-            v.x = __ldg(src);
-            if (k0 + 1 < p.K) v.y = __ldg(src + 1);
-            if (k0 + 2 < p.K) v.z = __ldg(src + 2);
-            if (k0 + 3 < p.K) v.w = __ldg(src + 3);
-          }
-        }
-        const float e[4] = {v.x, v.y, v.z, v.w};
+      // ---- B tile: kp channels x 32 reduction rows
+      if (p.mn & 1) {
+        for (int t0 = lw; t0 < natoms; t0 += 16) {
+          if (t0 + 16 < natoms) load_b(t0 + 16, vb_next);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int n = k0 + j;
-          float hi, lo;
-          split_tf32(e[j], hi, lo);
-          const unsigned off = (unsigned)(n * 128 + ((((ll >> 2) ^ (n & 7))) << 4) + ((ll & 3) << 2));
-          *reinterpret_cast<float *>(sb_hi + off) = hi;
-          *reinterpret_cast<float *>(sb_lo + off) = lo;
+          for (int u = 0; u < 4; ++u) {
+            const int idx = t0 + 4 * u;
+            if (idx < natoms) {
+              float4 hi, lo;
+              split_tf32_fast(vb[u].x, hi.x, lo.x);
+              split_tf32_fast(vb[u].y, hi.y, lo.y);
+              split_tf32_fast(vb[u].z, hi.z, lo.z);
+              split_tf32_fast(vb[u].w, hi.w, lo.w);
+              const unsigned off = (unsigned)((idx >> 3) * 4096 + (idx & 7) * 512) + sw;
+              g_sts128(sbb + off, hi);
+              g_sts128(sbb + (unsigned)b_part + off, lo);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) vb[u] = vb_next[u];
         }
-      }
+      } else {
+        for (int c4 = lw; c4 < kq; c4 += 4) {
+          const int k0 = c4 * 4;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (rok && k0 < p.K) {
+            const float *src = p.B + gr * p.ldb + k0;
+            if (p.vec) {
+              v = __ldg(reinterpret_cast<const float4 *>(src));
+            } else {
+              v.x = __ldg(src);
+              if (k0 + 1 < p.K) v.y = __ldg(src + 1);
+              if (k0 + 2 < p.K) v.z = __ldg(src + 2);
+              if (k0 + 3 < p.K) v.w = __ldg(src + 3);
+            }
+          }
+          const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int n = k0 + j;
+            float hi, lo;
+            split_tf32_fast(e[j], hi, lo);
+            const unsigned off = (unsigned)(n * 128) + (tw ^ (unsigned)((n & 7) << 4));
+            g_sts32(sbb + off, hi);
+            g_sts32(sbb + (unsigned)b_part + off, lo);
+          }
+        }
       }
       const long long t2 = clock64();
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -617,58 +642,70 @@ __global__ void __launch_bounds__(W_THREADS, 1) gemm_wgrad_3xtf32_kernel(WgradPa
     }
   } else if (warp == 4 + 4 * G_LGROUPS) {
     // ================================ MMA issuer =============================================
-    if (lane == 0) {
+    {  // whole warp, uniform control flow; one elected lane issues (see the NT kernel)
       unsigned it = 0, ccount = 0;
       long long w_acce = 0, w_full = 0, w_issue = 0, t_begin = clock64();
+      // per k-step (8 reduction rows) descriptor increments, in 16-byte units: two 512-byte K atoms
+      // of an MN-major tile, or 32 bytes inside the swizzle row of a K-major one
+      const int a_kstep = (p.mn & 2) ? 64 : 2, b_kstep = (p.mn & 1) ? 64 : 2;
+      const unsigned major_bits = ((p.mn & 2) ? (1u << 15) : 0u) | ((p.mn & 1) ? (1u << 16) : 0u);
+      const unsigned idesc0 = g_idesc(128, p.kp <= 256 ? p.kp : 256) | major_bits;
       for (int chunk = blockIdx.x; chunk < p.nchunks; chunk += gridDim.x, ++ccount) {
-      const int acc = nacc == 2 ? (int)(ccount & 1) : 0;
-      const unsigned dbase = tmem + (unsigned)(acc * 256);
-      const unsigned use = nacc == 2 ? (ccount >> 1) : ccount;  // how often this accumulator was used
-      long long ta = clock64();
-      g_mbar_wait(g_smem_u32(&s_acce[acc]), (use & 1u) ^ 1u);   // epilogue has drained it
-      w_acce += clock64() - ta;
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      bool first = true;
-      for (int slab = chunk * p.chunk; slab < min(nslab, (chunk + 1) * p.chunk); ++slab, ++it) {
-        const int st = it % p.nstages;
-        const unsigned ph = (it / p.nstages) & 1u;
-        ta = clock64();
-        g_mbar_wait(g_smem_u32(&s_full[st]), ph);
-        const long long tb = clock64();
-        w_full += tb - ta;
+        const int acc = nacc == 2 ? (int)(ccount & 1) : 0;
+        const unsigned dbase = tmem + (unsigned)(acc * 256);
+        const unsigned use = nacc == 2 ? (ccount >> 1) : ccount;  // how often this accumulator was used
+        long long ta = clock64();
+        g_mbar_wait(g_smem_u32(&s_acce[acc]), (use & 1u) ^ 1u);   // epilogue has drained it
+        w_acce += clock64() - ta;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const unsigned a_hi = g_smem_u32(smem + (size_t)st * stage_bytes);
-        const unsigned a_lo = a_hi + (unsigned)a_part;
-        const unsigned b_hi = a_lo + (unsigned)a_part;
-        const unsigned b_lo = b_hi + (unsigned)b_part;
+        const int slab_end = min(nslab, (chunk + 1) * p.chunk);
+        for (int slab = chunk * p.chunk; slab < slab_end; ++slab, ++it) {
+          const int st = it % p.nstages;
+          const unsigned ph = (it / p.nstages) & 1u;
+          ta = clock64();
+          g_mbar_wait(g_smem_u32(&s_full[st]), ph);
+          const long long tb = clock64();
+          w_full += tb - ta;
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          // The descriptors of a stage differ from a base only in the start-address field (bits
+          // 0-13, no carry out for < 256 KB of shared memory): one add per operand and MMA.
+          const unsigned a_hi = g_smem_u32(smem) + (unsigned)(st * stage_bytes);
+          const unsigned b_hi = a_hi + 2u * (unsigned)a_part;
+          const unsigned long long ah0 = (p.mn & 2) ? g_desc_mn(a_hi, 4096, 512) : g_desc(a_hi);
+          const unsigned long long bh0 = (p.mn & 1) ? g_desc_mn(b_hi, 4096, 512) : g_desc(b_hi);
+          const unsigned long long al0 = ah0 + (unsigned long long)(a_part >> 4);
+          const unsigned long long bl0 = bh0 + (unsigned long long)(b_part >> 4);
+          const bool first = slab == chunk * p.chunk;
+          if (g_elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {  // UMMA_K = 8 reduction rows = 32 bytes along the operand rows
-          const unsigned o = (unsigned)ks * 32u;
-          for (int n0 = 0; n0 < p.kp; n0 += 256) {
-            const int nn = min(256, p.kp - n0);
-            const unsigned d = dbase + (unsigned)n0;
-            if (p.mn) {  // 8 reduction rows = two 512-byte K atoms; 32-channel blocks 4096 bytes apart
-              const unsigned idesc = g_idesc(128, nn) | (1u << 15) | (1u << 16);  // A and B MN-major
-              const unsigned ao = (unsigned)ks * 1024u, bo = (unsigned)n0 * 128u + ao;
-              g_mma(d, g_desc_mn(a_hi + ao, 4096, 512), g_desc_mn(b_hi + bo, 4096, 512), idesc, first ? 0u : 1u);
-              g_mma(d, g_desc_mn(a_hi + ao, 4096, 512), g_desc_mn(b_lo + bo, 4096, 512), idesc, 1u);
-              g_mma(d, g_desc_mn(a_lo + ao, 4096, 512), g_desc_mn(b_hi + bo, 4096, 512), idesc, 1u);
-            } else {
-              const unsigned idesc = g_idesc(128, nn);
-              const unsigned bo = (unsigned)n0 * 128u + o;  // operand rows n0.. of the B tile
-              g_mma(d, g_desc(a_hi + o), g_desc(b_hi + bo), idesc, first ? 0u : 1u);
-              g_mma(d, g_desc(a_hi + o), g_desc(b_lo + bo), idesc, 1u);
-              g_mma(d, g_desc(a_lo + o), g_desc(b_hi + bo), idesc, 1u);
+            for (int ks = 0; ks < 4; ++ks) {  // UMMA_K = 8 reduction rows
+              const unsigned long long ao = (unsigned long long)(ks * a_kstep);
+              const unsigned long long bo = (unsigned long long)(ks * b_kstep);
+              const unsigned accum = (first && ks == 0) ? 0u : 1u;
+              if (p.kp <= 256) {
+                g_mma(dbase, ah0 + ao, bh0 + bo, idesc0, accum);
+                g_mma(dbase, ah0 + ao, bl0 + bo, idesc0, 1u);
+                g_mma(dbase, al0 + ao, bh0 + bo, idesc0, 1u);
+              } else {
+                for (int n0 = 0; n0 < p.kp; n0 += 256) {
+                  const int nn = min(256, p.kp - n0);
+                  const unsigned idesc = g_idesc(128, nn) | major_bits;
+                  const unsigned long long bn = bo + (unsigned long long)(n0 * 8);  // n0 * 128 bytes >> 4
+                  const unsigned d = dbase + (unsigned)n0;
+                  g_mma(d, ah0 + ao, bh0 + bn, idesc, accum);
+                  g_mma(d, ah0 + ao, bl0 + bn, idesc, 1u);
+                  g_mma(d, al0 + ao, bh0 + bn, idesc, 1u);
+                }
+              }
             }
+            g_commit(g_smem_u32(&s_empty[st]));
+            if (slab == slab_end - 1) g_commit(g_smem_u32(&s_accf[acc]));
           }
-          first = false;
+          __syncwarp();
+          w_issue += clock64() - tb;
         }
-        g_commit(g_smem_u32(&s_empty[st]));
-        w_issue += clock64() - tb;
       }
-      g_commit(g_smem_u32(&s_accf[acc]));
-      }
-      if ((p.dbg & 128) && blockIdx.x == 0 && blockIdx.y == 0) {
+      if ((p.dbg & 128) && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) {
         g_gemm_prof[4] = w_acce; g_gemm_prof[5] = w_full; g_gemm_prof[6] = w_issue;
         g_gemm_prof[7] = clock64() - t_begin;
       }
@@ -820,10 +857,11 @@ extern "C" int nesie_gemm_wgrad_3xtf32(long long r, int n, int k, const float *a
   NESIE_CUDA(cudaFuncSetAttribute(gemm_wgrad_3xtf32_kernel,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   p.nchunks = nsplits;
-  p.mn = ((lda & 3) == 0) && ((ldb & 3) == 0) && ((n & 3) == 0) && ((k & 3) == 0) &&
-         (((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0);
+  p.vec = ((lda & 3) == 0) && ((ldb & 3) == 0) && ((n & 3) == 0) && ((k & 3) == 0) &&
+          (((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0);
+  p.mn = p.vec ? 3 : 0;
   { const char *e = getenv("NESIE_GEMM_DBG"); p.dbg = e ? atoi(e) : 0; }
-  { const char *e = getenv("NESIE_WGRAD_LAYOUT"); if (e && e[0] == 't') p.mn = 0; }
+  { const char *e = getenv("NESIE_WGRAD_LAYOUT"); if (e && p.vec) p.mn = atoi(e) & 3; }
   p.chunk = wgrad_chunk((r + 31) / 32, (n + 127) / 128);
   const int mblocks = (n + 127) / 128;
   int gx = num_sms() / mblocks;

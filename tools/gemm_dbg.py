@@ -13,10 +13,10 @@ def timeit(fn, iters=10):
         a.record(); fn(); b.record(); torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
     return sorted(ts)[len(ts) // 2]
 
-for R, N, K in [(1048576, 64, 64)]:
+for R, N, K in [(1048576, 64, 64), (1048576, 128, 64), (262144, 256, 128), (262144, 128, 256)]:
     a = torch.randn(R, K, device="cuda"); w = torch.randn(N, K, device="cuda")
     out = []
-    for dbg in [0, 127]:
+    for dbg in [0]:
         os.environ["NESIE_GEMM_DBG"] = str(dbg)
         out.append(f"dbg{dbg}={timeit(lambda: gemm_nt(a, w)) * 1e3:.0f}us")
         os.environ["NESIE_GEMM_DBG"] = str(dbg | 128)
@@ -34,14 +34,18 @@ for R, N, K in [(1048576, 64, 64)]:
 from nesie_b200.linear_rows import wgrad  # noqa: E402
 import ctypes  # noqa: E402
 from nesie_b200 import _lib  # noqa: E402
-for R, N, K in [(1048576, 64, 64), (1048576, 128, 64), (262144, 256, 128), (262144, 128, 128)]:
+for R, N, K in [(1048576, 64, 64), (1048576, 128, 64), (1048576, 64, 128), (262144, 256, 128), (262144, 128, 256), (262144, 128, 128)]:
     gy = torch.randn(R, N, device="cuda"); x = torch.randn(R, K, device="cuda")
-    os.environ["NESIE_GEMM_DBG"] = "0"
-    t = timeit(lambda: wgrad(gy, x)) * 1e3
-    os.environ["NESIE_GEMM_DBG"] = "128"
-    buf = (ctypes.c_longlong * 16)()
-    _lib.lib().nesie_gemm_debug_profile(buf)
-    wgrad(gy, x)
-    _lib.lib().nesie_gemm_debug_profile(buf)
-    v = list(buf); ns = max(v[3], 1); nt = max(v[10], 1)
-    print("wgrad", R, N, K, f"{t:.0f}us [loader/slab: wait {v[0]//ns} fill {v[1]//ns} publish {v[2]//ns} (n={v[3]}) | mma/chunk: acce {v[4]//nt} full {v[5]//nt} issue {v[6]//nt} total {v[7]//nt} | epi/chunk: wait {v[8]//nt} drain {v[9]//nt} (n={v[10]})]", flush=True)
+    want = gy.double().t() @ x.double()
+    for layout in ["3", "2", "0"]:
+        os.environ["NESIE_WGRAD_LAYOUT"] = layout
+        os.environ["NESIE_GEMM_DBG"] = "0"
+        t = timeit(lambda: wgrad(gy, x)) * 1e3
+        err = ((wgrad(gy, x).double() - want).abs().max() / want.abs().max()).item()
+        os.environ["NESIE_GEMM_DBG"] = "128"
+        buf = (ctypes.c_longlong * 16)()
+        _lib.lib().nesie_gemm_debug_profile(buf)
+        wgrad(gy, x)
+        _lib.lib().nesie_gemm_debug_profile(buf)
+        v = list(buf); ns = max(v[3], 1); nt = max(v[10], 1)
+        print("wgrad", R, N, K, "layout", layout, f"{t:.0f}us err {err:.1e} [loader/slab: wait {v[0]//ns} fill {v[1]//ns} publish {v[2]//ns} | mma/chunk: full {v[5]//nt} issue {v[6]//nt} total {v[7]//nt} (chunks {v[10]}, slabs {v[3]})]", flush=True)
