@@ -1,0 +1,520 @@
+// TMA-fed variants of the 3xTF32 GEMM kernels (included by gemm_3xtf32.cu).
+//
+// The register-staged loaders of gemm_nt_3xtf32_kernel / gemm_wgrad_3xtf32_kernel pay one full
+// memory round trip per pipeline stage with nothing else in flight for that stage (measured: 2700-
+// 4800 cycles of "fill" per 16 KB slab, ~2.5 TB/s of reads chip-wide).  Here the fp32 operand tiles
+// are brought in by the TMA engine (cp.async.bulk.tensor.2d) straight into the swizzled UMMA layout,
+// so every free stage always has its load in flight and no thread holds data in registers:
+//
+//   producer (1 thread) : waits for a free stage, arms its mbarrier, issues the tensor copies
+//   transform (8 warps) : the RAW fp32 tile is used as the `hi` operand as it is -- the tensor core
+//                         reads the top 19 bits of each word, i.e. hi = x truncated to TF32 -- and
+//                         lo = RN_tf32(x - trunc(x)) is written to a second tile of the same layout
+//                         (LDS.128 + 16 ALU + STS.128 per four elements, half the old loader's work)
+//   MMA (1 elected lane): hi*hi + hi*lo + lo*hi as before
+//   epilogue            : unchanged
+//
+// Requirements (else the register-staged kernels run): 16-byte aligned base and row stride.
+#pragma once
+#include <cuda.h>
+
+#include "gemm_common.cuh"
+
+namespace nesie {
+namespace {
+
+constexpr int T_EPIW = 8;   // epilogue warps (NT); the weight-gradient kernel uses the first four
+constexpr int T_XFW = 8;    // transform warps
+constexpr int T_THREADS = 32 * (T_EPIW + T_XFW + 2);  // + producer warp + MMA warp
+constexpr int T_XF0 = T_EPIW, T_PROD = T_EPIW + T_XFW, T_MMA = T_PROD + 1;
+
+__device__ __forceinline__ void g_tma_2d(unsigned dst, const CUtensorMap *tm, int c0, int c1,
+                                         unsigned mbar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(mbar)
+      : "memory");
+}
+__device__ __forceinline__ void g_mbar_arm(unsigned mbar, unsigned bytes) { g_mbar_expect_tx(mbar, bytes); }
+
+// lo part of a raw fp32 word whose top 19 bits the tensor core uses as hi
+__device__ __forceinline__ float lo_of_raw(float x) {
+  const float hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+  return tf32_rn_fast(x - hi);
+}
+__device__ __forceinline__ float4 lo_of_raw4(float4 v) {
+  return make_float4(lo_of_raw(v.x), lo_of_raw(v.y), lo_of_raw(v.z), lo_of_raw(v.w));
+}
+
+// ----------------------------------------------------------------------------------------------
+// C[R x N] = A[R x K] * B[N x K]^T   (B pre-split / pre-swizzled image as in the register kernel)
+// ----------------------------------------------------------------------------------------------
+struct GemmTmaParams {
+  int R, N, K;
+  int npad, nslab, nstages;
+  long long ldc;
+  const unsigned char *Bimg;
+  float *C;
+  int dbg;
+};
+
+__global__ void __launch_bounds__(T_THREADS, 1)
+gemm_nt_tma_kernel(const __grid_constant__ CUtensorMap tmA, GemmTmaParams p) {
+  extern __shared__ unsigned char g_smem_dyn[];
+  unsigned char *smem = reinterpret_cast<unsigned char *>(
+      (reinterpret_cast<uintptr_t>(g_smem_dyn) + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) unsigned long long s_tma[G_MAXSTAGES], s_full[G_MAXSTAGES], s_empty[G_MAXSTAGES],
+      s_accf[2], s_acce[2];
+  __shared__ unsigned s_tmem;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int bslab = p.npad * 128;                       // bytes of one B part-slab
+  const int stage_bytes = 2 * G_ASLAB + 2 * bslab;      // A raw (= hi), A lo, B hi, B lo
+  const int ntiles = (p.R + G_TILE - 1) / G_TILE;
+  const unsigned smem_base = g_smem_u32(smem);
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     g_smem_u32(&s_tmem)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    for (int s = 0; s < p.nstages; ++s) {
+      g_mbar_init(g_smem_u32(&s_tma[s]), 1);
+      g_mbar_init(g_smem_u32(&s_full[s]), 32 * T_XFW);
+      g_mbar_init(g_smem_u32(&s_empty[s]), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      g_mbar_init(g_smem_u32(&s_accf[a]), 1);
+      g_mbar_init(g_smem_u32(&s_acce[a]), 32 * T_EPIW);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const unsigned tmem = s_tmem;
+
+  if (warp == T_PROD) {
+    // ================================ producer ===============================================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+      unsigned it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int ks = 0; ks < p.nslab; ++ks, ++it) {
+          const int st = it % p.nstages;
+          const unsigned ph = (it / p.nstages) & 1u;
+          const unsigned sa = smem_base + (unsigned)(st * stage_bytes);
+          const unsigned sb = sa + 2 * G_ASLAB;
+          const unsigned bar = g_smem_u32(&s_tma[st]);
+          g_mbar_wait(g_smem_u32(&s_empty[st]), ph ^ 1u);
+          g_mbar_arm(bar, (unsigned)G_ASLAB + 2u * (unsigned)bslab);
+          // box = 32 floats x 128 rows; columns >= K and rows >= R arrive as zeros
+          g_tma_2d(sa, &tmA, ks * G_SLABK, tile * G_TILE, bar);
+          g_bulk_g2s(sb, p.Bimg + (size_t)ks * bslab, (unsigned)bslab, bar);
+          g_bulk_g2s(sb + bslab, p.Bimg + (size_t)(p.nslab + ks) * bslab, (unsigned)bslab, bar);
+        }
+      }
+    }
+  } else if (warp >= T_XF0 && warp < T_PROD) {
+    // ================================ transform ==============================================
+    const int xt = tid - 32 * T_XF0;  // 0..255
+    unsigned it = 0;
+    long long w_wait = 0, w_work = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int ks = 0; ks < p.nslab; ++ks, ++it) {
+        const int st = it % p.nstages;
+        const unsigned ph = (it / p.nstages) & 1u;
+        const unsigned sa = smem_base + (unsigned)(st * stage_bytes) + (unsigned)(xt * 16);
+        const long long t0 = clock64();
+        g_mbar_wait(g_smem_u32(&s_tma[st]), ph);
+        const long long t1 = clock64();
+        float4 v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = g_lds128(sa + i * 4096);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) g_sts128(sa + G_ASLAB + i * 4096, lo_of_raw4(v[i]));
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        g_mbar_arrive(g_smem_u32(&s_full[st]));
+        w_wait += t1 - t0;
+        w_work += clock64() - t1;
+      }
+    }
+    if ((p.dbg & 128) && blockIdx.x == 0 && xt == 0) {
+      g_gemm_prof[0] = w_wait; g_gemm_prof[1] = w_work; g_gemm_prof[2] = 0; g_gemm_prof[3] = it;
+    }
+  } else if (warp == T_MMA) {
+    // ================================ MMA issuer =============================================
+    const unsigned idesc = g_idesc(128, p.npad);
+    unsigned it = 0, tcount = 0;
+    long long w_acce = 0, w_full = 0, w_issue = 0, t_begin = clock64();
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+      const int acc = tcount & 1;
+      const unsigned d = tmem + (unsigned)(acc * 256);
+      long long ta = clock64();
+      g_mbar_wait(g_smem_u32(&s_acce[acc]), ((tcount >> 1) & 1u) ^ 1u);  // epilogue drained it
+      w_acce += clock64() - ta;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int ks = 0; ks < p.nslab; ++ks, ++it) {
+        const int st = it % p.nstages;
+        const unsigned ph = (it / p.nstages) & 1u;
+        ta = clock64();
+        g_mbar_wait(g_smem_u32(&s_full[st]), ph);
+        const long long tb = clock64();
+        w_full += tb - ta;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const unsigned a_hi = smem_base + (unsigned)(st * stage_bytes);
+        const unsigned long long ah0 = g_desc(a_hi), al0 = ah0 + (G_ASLAB >> 4);
+        const unsigned long long bh0 = al0 + (G_ASLAB >> 4), bl0 = bh0 + (unsigned long long)(bslab >> 4);
+        if (g_elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {  // UMMA_K = 8 tf32 = 32 bytes = 2 descriptor units
+            g_mma(d, ah0 + 2 * k, bh0 + 2 * k, idesc, (ks | k) ? 1u : 0u);
+            g_mma(d, ah0 + 2 * k, bl0 + 2 * k, idesc, 1u);
+            g_mma(d, al0 + 2 * k, bh0 + 2 * k, idesc, 1u);
+          }
+          g_commit(g_smem_u32(&s_empty[st]));  // stage reusable once these MMAs have read it
+          if (ks == p.nslab - 1) g_commit(g_smem_u32(&s_accf[acc]));
+        }
+        __syncwarp();
+        w_issue += clock64() - tb;
+      }
+    }
+    if ((p.dbg & 128) && blockIdx.x == 0 && lane == 0) {
+      g_gemm_prof[4] = w_acce; g_gemm_prof[5] = w_full; g_gemm_prof[6] = w_issue;
+      g_gemm_prof[7] = clock64() - t_begin;
+    }
+  } else if (warp < T_EPIW) {
+    // ================================ epilogue ===============================================
+    // thread = accumulator row; each warp transposes its 32 x 32 block through 4 KB of shared
+    // memory so that a quarter-warp writes 128 contiguous bytes (see gemm_nt_3xtf32_kernel)
+    unsigned tcount = 0;
+    const int q = warp & 3, half = warp >> 2;  // TMEM lane quarter (warp % 4), column interleave
+    const bool vec = ((p.ldc & 3) == 0) && ((p.N & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+    const unsigned stg = smem_base + (unsigned)(p.nstages * stage_bytes) + (unsigned)(warp * 4096);
+    const int qr = lane >> 3, qc = lane & 7;   // read-back: row qr + 4i, 16-byte chunk qc
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+      const int acc = tcount & 1;
+      const long long gr = (long long)tile * G_TILE + q * 32 + lane;
+      const long long te0 = clock64();
+      g_mbar_wait(g_smem_u32(&s_accf[acc]), (tcount >> 1) & 1u);
+      const long long te1 = clock64();
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int c0 = half * 32; c0 < p.npad; c0 += 32 * (T_EPIW / 4)) {
+        unsigned v[32];
+        g_tmem_ld32(tmem + (unsigned)(acc * 256 + c0) + ((unsigned)(q * 32) << 16), v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (vec) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            g_sts128(stg + (unsigned)(lane * 128 + ((j ^ (lane & 7)) << 4)),
+                     make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                 __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
+          __syncwarp();
+          const int cc = c0 + qc * 4;
+          const long long grow = (long long)tile * G_TILE + q * 32 + qr;
+          float *dst = p.C + grow * p.ldc + cc;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = qr + 4 * i;
+            const float4 o = g_lds128(stg + (unsigned)(rr * 128 + ((qc ^ (rr & 7)) << 4)));
+            if (grow + 4 * i < p.R && cc < p.N) *reinterpret_cast<float4 *>(dst + (long long)(4 * i) * p.ldc) = o;
+          }
+          __syncwarp();
+        } else if (gr < p.R) {
+          float *crow = p.C + gr * p.ldc;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c0 + j < p.N) crow[c0 + j] = __uint_as_float(v[j]);
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      g_mbar_arrive(g_smem_u32(&s_acce[acc]));
+      if ((p.dbg & 128) && blockIdx.x == 0 && tid == 0) {
+        g_gemm_prof[8] += te1 - te0; g_gemm_prof[9] += clock64() - te1; g_gemm_prof[10] += 1;
+      }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u)
+                 : "memory");
+}
+
+// ----------------------------------------------------------------------------------------------
+// Weight gradient  W'[n x k] = sum_r A[r, n] * B[r, k]  with MN-major (SW128_32B) operand tiles
+// ----------------------------------------------------------------------------------------------
+struct WgradTmaParams {
+  int R, N, K;
+  int kp;            // K rounded up to 32
+  int nstages;
+  float *P;          // [nchunks][N][K] partial sums
+  int nchunks, chunk;
+  int dbg;
+};
+
+__global__ void __launch_bounds__(T_THREADS, 1)
+gemm_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      WgradTmaParams p) {
+  extern __shared__ unsigned char g_smem_dyn[];
+  unsigned char *smem = reinterpret_cast<unsigned char *>(
+      (reinterpret_cast<uintptr_t>(g_smem_dyn) + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) unsigned long long s_tma[G_MAXSTAGES], s_full[G_MAXSTAGES], s_empty[G_MAXSTAGES],
+      s_accf[2], s_acce[2];
+  __shared__ unsigned s_tmem;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nacc = p.kp <= 256 ? 2 : 1;     // TMEM accumulators (double-buffered when they fit)
+  const int m0 = blockIdx.y * 128;          // first channel of A handled by this CTA
+  const int ma = min(4, (p.N - m0 + 31) >> 5);  // 32-channel blocks of A that exist
+  const int nb = p.kp >> 5;                 // 32-channel blocks of B
+  const int a_part = 128 * 128;             // A tile: 4 blocks x (32 rows x 128 B)
+  const int b_part = p.kp * 128;
+  const int stage_bytes = 2 * a_part + 2 * b_part;   // A raw, A lo, B raw, B lo
+  const int nslab = (p.R + 31) >> 5;        // reduction slabs of 32 rows
+  const unsigned smem_base = g_smem_u32(smem);
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     g_smem_u32(&s_tmem)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    for (int s = 0; s < p.nstages; ++s) {
+      g_mbar_init(g_smem_u32(&s_tma[s]), 1);
+      g_mbar_init(g_smem_u32(&s_full[s]), 32 * T_XFW);
+      g_mbar_init(g_smem_u32(&s_empty[s]), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      g_mbar_init(g_smem_u32(&s_accf[a]), 1);
+      g_mbar_init(g_smem_u32(&s_acce[a]), 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const unsigned tmem = s_tmem;
+
+  if (warp == T_PROD) {
+    // ================================ producer ===============================================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+      unsigned it = 0;
+      for (int chunk = blockIdx.x; chunk < p.nchunks; chunk += gridDim.x) {
+        const int slab_end = min(nslab, (chunk + 1) * p.chunk);
+        for (int slab = chunk * p.chunk; slab < slab_end; ++slab, ++it) {
+          const int st = it % p.nstages;
+          const unsigned ph = (it / p.nstages) & 1u;
+          const unsigned sa = smem_base + (unsigned)(st * stage_bytes);
+          const unsigned sb = sa + 2u * (unsigned)a_part;
+          const unsigned bar = g_smem_u32(&s_tma[st]);
+          g_mbar_wait(g_smem_u32(&s_empty[st]), ph ^ 1u);
+          g_mbar_arm(bar, (unsigned)(ma + nb) * 4096u);
+          // box = 32 channels x 32 rows = one 4 KB column of SW128_32B atoms; rows >= R and
+          // channels beyond the tensor arrive as zeros
+          for (int m = 0; m < ma; ++m) g_tma_2d(sa + (unsigned)m * 4096u, &tmA, m0 + 32 * m, slab * 32, bar);
+          for (int c = 0; c < nb; ++c) g_tma_2d(sb + (unsigned)c * 4096u, &tmB, 32 * c, slab * 32, bar);
+        }
+      }
+    }
+  } else if (warp >= T_XF0 && warp < T_PROD) {
+    // ================================ transform ==============================================
+    const int xt = tid - 32 * T_XF0;  // 0..255: one float4 of a 4 KB block
+    unsigned it = 0;
+    long long w_wait = 0, w_work = 0;
+    for (int chunk = blockIdx.x; chunk < p.nchunks; chunk += gridDim.x) {
+      const int slab_end = min(nslab, (chunk + 1) * p.chunk);
+      for (int slab = chunk * p.chunk; slab < slab_end; ++slab, ++it) {
+        const int st = it % p.nstages;
+        const unsigned ph = (it / p.nstages) & 1u;
+        const unsigned sa = smem_base + (unsigned)(st * stage_bytes) + (unsigned)(xt * 16);
+        const unsigned sb = sa + 2u * (unsigned)a_part;
+        const long long t0 = clock64();
+        g_mbar_wait(g_smem_u32(&s_tma[st]), ph);
+        const long long t1 = clock64();
+        {
+          float4 v[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (i < ma) v[i] = g_lds128(sa + i * 4096);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (i < ma) g_sts128(sa + (unsigned)a_part + i * 4096, lo_of_raw4(v[i]));
+        }
+        for (int c = 0; c < nb; c += 4) {
+          float4 v[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (c + i < nb) v[i] = g_lds128(sb + (c + i) * 4096);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (c + i < nb) g_sts128(sb + (unsigned)b_part + (c + i) * 4096, lo_of_raw4(v[i]));
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        g_mbar_arrive(g_smem_u32(&s_full[st]));
+        w_wait += t1 - t0;
+        w_work += clock64() - t1;
+      }
+    }
+    if ((p.dbg & 128) && blockIdx.x == 0 && blockIdx.y == 0 && xt == 0) {
+      g_gemm_prof[0] = w_wait; g_gemm_prof[1] = w_work; g_gemm_prof[2] = 0; g_gemm_prof[3] = it;
+    }
+  } else if (warp == T_MMA) {
+    // ================================ MMA issuer =============================================
+    unsigned it = 0, ccount = 0;
+    long long w_acce = 0, w_full = 0, w_issue = 0, t_begin = clock64();
+    const unsigned major_bits = (1u << 15) | (1u << 16);  // A and B MN-major
+    const unsigned idesc0 = g_idesc(128, p.kp <= 256 ? p.kp : 256) | major_bits;
+    for (int chunk = blockIdx.x; chunk < p.nchunks; chunk += gridDim.x, ++ccount) {
+      const int acc = nacc == 2 ? (int)(ccount & 1) : 0;
+      const unsigned dbase = tmem + (unsigned)(acc * 256);
+      const unsigned use = nacc == 2 ? (ccount >> 1) : ccount;
+      long long ta = clock64();
+      g_mbar_wait(g_smem_u32(&s_acce[acc]), (use & 1u) ^ 1u);   // epilogue has drained it
+      w_acce += clock64() - ta;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int slab_end = min(nslab, (chunk + 1) * p.chunk);
+      for (int slab = chunk * p.chunk; slab < slab_end; ++slab, ++it) {
+        const int st = it % p.nstages;
+        const unsigned ph = (it / p.nstages) & 1u;
+        ta = clock64();
+        g_mbar_wait(g_smem_u32(&s_full[st]), ph);
+        const long long tb = clock64();
+        w_full += tb - ta;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const unsigned a_hi = smem_base + (unsigned)(st * stage_bytes);
+        const unsigned b_hi = a_hi + 2u * (unsigned)a_part;
+        const unsigned long long ah0 = g_desc_mn(a_hi, 4096, 512), bh0 = g_desc_mn(b_hi, 4096, 512);
+        const unsigned long long al0 = ah0 + (unsigned long long)(a_part >> 4);
+        const unsigned long long bl0 = bh0 + (unsigned long long)(b_part >> 4);
+        const bool first = slab == chunk * p.chunk;
+        if (g_elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {  // 8 reduction rows = two 512-byte K atoms = 64 units
+            const unsigned long long o = (unsigned long long)(ks * 64);
+            const unsigned accum = (first && ks == 0) ? 0u : 1u;
+            if (p.kp <= 256) {
+              g_mma(dbase, ah0 + o, bh0 + o, idesc0, accum);
+              g_mma(dbase, ah0 + o, bl0 + o, idesc0, 1u);
+              g_mma(dbase, al0 + o, bh0 + o, idesc0, 1u);
+            } else {
+              for (int n0 = 0; n0 < p.kp; n0 += 256) {
+                const int nn = min(256, p.kp - n0);
+                const unsigned idesc = g_idesc(128, nn) | major_bits;
+                const unsigned long long bn = o + (unsigned long long)(n0 * 8);  // n0 * 128 bytes >> 4
+                const unsigned d = dbase + (unsigned)n0;
+                g_mma(d, ah0 + o, bh0 + bn, idesc, accum);
+                g_mma(d, ah0 + o, bl0 + bn, idesc, 1u);
+                g_mma(d, al0 + o, bh0 + bn, idesc, 1u);
+              }
+            }
+          }
+          g_commit(g_smem_u32(&s_empty[st]));
+          if (slab == slab_end - 1) g_commit(g_smem_u32(&s_accf[acc]));
+        }
+        __syncwarp();
+        w_issue += clock64() - tb;
+      }
+    }
+    if ((p.dbg & 128) && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) {
+      g_gemm_prof[4] = w_acce; g_gemm_prof[5] = w_full; g_gemm_prof[6] = w_issue;
+      g_gemm_prof[7] = clock64() - t_begin;
+    }
+  } else if (warp < 4) {
+    // ================================ epilogue ===============================================
+    const int n = m0 + warp * 32 + lane;
+    unsigned ccount = 0;
+    for (int chunk = blockIdx.x; chunk < p.nchunks; chunk += gridDim.x, ++ccount) {
+      const int acc = nacc == 2 ? (int)(ccount & 1) : 0;
+      const unsigned use = nacc == 2 ? (ccount >> 1) : ccount;
+      const long long te0 = clock64();
+      g_mbar_wait(g_smem_u32(&s_accf[acc]), use & 1u);
+      const long long te1 = clock64();
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      float *prow = p.P + ((size_t)chunk * p.N + n) * p.K;
+      for (int c0 = 0; c0 < p.kp; c0 += 32) {
+        unsigned v[32];
+        g_tmem_ld32(tmem + (unsigned)(acc * 256 + c0) + ((unsigned)(warp * 32) << 16), v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (n < p.N) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (c0 + j + 3 < p.K && (p.K & 3) == 0) {
+              *reinterpret_cast<float4 *>(prow + c0 + j) =
+                  make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                              __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            } else {
+#pragma unroll
+              for (int t = 0; t < 4; ++t)
+                if (c0 + j + t < p.K) prow[c0 + j + t] = __uint_as_float(v[j + t]);
+            }
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      g_mbar_arrive(g_smem_u32(&s_acce[acc]));
+      if ((p.dbg & 128) && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) {
+        g_gemm_prof[8] += te1 - te0; g_gemm_prof[9] += clock64() - te1; g_gemm_prof[10] += 1;
+      }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u)
+                 : "memory");
+}
+
+// ---- host side: tensor maps through the driver entry point (libcuda is not linked) -----------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                  const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    else
+      (void)cudaGetLastError();
+  }
+  return fn;
+}
+
+// fp32 matrix (rows x cols, row stride ld floats) as a 2-D tensor; box = box_cols x box_rows
+inline bool make_tmap(CUtensorMap *tm, const float *base, long long rows, long long cols, long long ld,
+                      int box_cols, int box_rows, CUtensorMapSwizzle swz) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld & 3)) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+inline bool gemm_tma_enabled() {
+  const char *e = getenv("NESIE_GEMM_PATH");
+  return !(e && e[0] == 'r');  // NESIE_GEMM_PATH=reg selects the register-staged loaders
+}
+
+}  // namespace
+}  // namespace nesie
