@@ -81,14 +81,16 @@ __global__ void __launch_bounds__(BN_THREADS) bn_colsum_kernel(
   }
 }
 
-// Sum the per-CTA partials of 32 channels: blockDim = (32 channels, FIN_SLICES slices); every slice
-// walks its share of the partial blocks in double, then the slices are combined through shared memory.
-constexpr int FIN_SLICES = 32;
+// Sum the per-CTA partials of FIN_CH channels: blockDim = (FIN_CH channels, FIN_SLICES slices); every
+// slice walks its share of the partial blocks in double, then the slices are combined through shared
+// memory.  Few channels per CTA spread the ~0.6 MB of partials over C / 8 SMs (one SM pulls only
+// ~150 GB/s: with 32 channels per CTA the finalize of a 64-channel layer took 9 us on two SMs).
+constexpr int FIN_CH = 8, FIN_SLICES = 128;
 
 __device__ __forceinline__ bool reduce_partials(int C, int nparts, const float *__restrict__ partial,
                                                 double &s1, double &s2) {
-  __shared__ double s_red[2][FIN_SLICES][33];
-  const int c = blockIdx.x * 32 + threadIdx.x;
+  __shared__ double s_red[2][FIN_SLICES][FIN_CH + 1];
+  const int c = blockIdx.x * FIN_CH + threadIdx.x;
   double a1 = 0.0, a2 = 0.0;
   if (c < C) {
     for (int p = threadIdx.y; p < nparts; p += FIN_SLICES) {
@@ -99,24 +101,29 @@ __device__ __forceinline__ bool reduce_partials(int C, int nparts, const float *
   s_red[0][threadIdx.y][threadIdx.x] = a1;
   s_red[1][threadIdx.y][threadIdx.x] = a2;
   __syncthreads();
-  if (threadIdx.y != 0 || c >= C) return false;
-  s1 = 0.0; s2 = 0.0;
-  for (int y = 0; y < FIN_SLICES; ++y) {  // fixed order: deterministic
-    s1 += s_red[0][y][threadIdx.x];
-    s2 += s_red[1][y][threadIdx.x];
+  // tree over the slices, fixed order: deterministic
+  for (int h = FIN_SLICES / 2; h >= 1; h >>= 1) {
+    if (threadIdx.y < h) {
+      s_red[0][threadIdx.y][threadIdx.x] += s_red[0][threadIdx.y + h][threadIdx.x];
+      s_red[1][threadIdx.y][threadIdx.x] += s_red[1][threadIdx.y + h][threadIdx.x];
+    }
+    __syncthreads();
   }
+  if (threadIdx.y != 0 || c >= C) return false;
+  s1 = s_red[0][0][threadIdx.x];
+  s2 = s_red[1][0][threadIdx.x];
   return true;
 }
 
 // forward finalize: partial sums -> mean / invstd / scale / shift, running stats
-__global__ void __launch_bounds__(32 * FIN_SLICES) bn_fwd_finalize_kernel(
+__global__ void __launch_bounds__(FIN_CH * FIN_SLICES) bn_fwd_finalize_kernel(
     long long R, int C, int nparts, const float *__restrict__ Y, const float *__restrict__ partial,
     const float *__restrict__ gamma, const float *__restrict__ beta, float eps, float momentum,
     float *__restrict__ running_mean, float *__restrict__ running_var,
     float *__restrict__ stats /* [4][C]: mean, invstd, scale, shift */) {
   double s1, s2;
   if (!reduce_partials(C, nparts, partial, s1, s2)) return;
-  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int c = blockIdx.x * FIN_CH + threadIdx.x;
   const double n = (double)R, m1 = s1 / n;
   double var = s2 / n - m1 * m1;  // variance of (y - pivot) == variance of y
   if (var < 0.0) var = 0.0;
@@ -135,12 +142,12 @@ __global__ void __launch_bounds__(32 * FIN_SLICES) bn_fwd_finalize_kernel(
 }
 
 // backward finalize: sum g -> d beta, sum g*xhat -> d gamma, and the two means used by the apply pass
-__global__ void __launch_bounds__(32 * FIN_SLICES) bn_bwd_finalize_kernel(
+__global__ void __launch_bounds__(FIN_CH * FIN_SLICES) bn_bwd_finalize_kernel(
     long long R, int C, int nparts, const float *__restrict__ partial, float *__restrict__ dgamma,
     float *__restrict__ dbeta, float *__restrict__ coef /* [2][C]: mean g, mean g*xhat */) {
   double s1, s2;
   if (!reduce_partials(C, nparts, partial, s1, s2)) return;
-  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int c = blockIdx.x * FIN_CH + threadIdx.x;
   dbeta[c] = (float)s1;
   dgamma[c] = (float)s2;
   coef[c] = (float)(s1 / (double)R);
@@ -319,7 +326,7 @@ extern "C" int nesie_bn_relu_rows_forward(long long r, int c, int k, const float
   const int nparts = parts_for(r, c);
   bn_colsum_kernel<0><<<nparts, BN_THREADS, 0, st>>>(r, c, y, nullptr, nullptr, nullptr, nullptr,
                                                     nullptr, partial);
-  bn_fwd_finalize_kernel<<<ceil_div(c, 32), dim3(32, FIN_SLICES), 0, st>>>(r, c, nparts, y, partial, gamma, beta,
+  bn_fwd_finalize_kernel<<<ceil_div(c, FIN_CH), dim3(FIN_CH, FIN_SLICES), 0, st>>>(r, c, nparts, y, partial, gamma, beta,
                                                           eps, momentum, running_mean, running_var,
                                                           stats);
   if (k == 0) {
@@ -359,7 +366,7 @@ extern "C" int nesie_bn_relu_rows_backward(long long r, int c, int k, const floa
     nparts = (int)g;
     bn_pool_bwd_colsum_kernel<<<nparts, BN_THREADS, 0, st>>>(G, k, c, y, d_a, arg, stats, partial);
   }
-  bn_bwd_finalize_kernel<<<ceil_div(c, 32), dim3(32, FIN_SLICES), 0, st>>>(r, c, nparts, partial, d_gamma, d_beta, coef);
+  bn_bwd_finalize_kernel<<<ceil_div(c, FIN_CH), dim3(FIN_CH, FIN_SLICES), 0, st>>>(r, c, nparts, partial, d_gamma, d_beta, coef);
   const long long n4 = r * (c >> 2);
   if (k == 0)
     bn_relu_bwd_apply_kernel<false><<<grid_for(n4), BN_THREADS, 0, st>>>(r, 1, c, y, d_a, nullptr,

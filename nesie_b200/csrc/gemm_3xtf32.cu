@@ -693,11 +693,11 @@ extern "C" int nesie_gemm_nt_3xtf32(long long r, int n, int k, const float *a, l
       q.nstages = (int)((226 * 1024 - epi) / stage);
       if (q.nstages > G_MAXSTAGES) q.nstages = G_MAXSTAGES;
       const size_t smem = (size_t)q.nstages * stage + epi + 1024;
-      NESIE_CUDA(cudaFuncSetAttribute(gemm_nt_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem));
+      auto kern = gemm_tma_capped() ? gemm_nt_tma_kernel<T_MAXREG> : gemm_nt_tma_kernel<96>;
+      NESIE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       int grid = num_sms();
       if (ntiles_all < grid) grid = ntiles_all;
-      gemm_nt_tma_kernel<<<grid, T_THREADS, smem, (cudaStream_t)stream>>>(tm, q);
+      kern<<<grid, T_THREADS, smem, (cudaStream_t)stream>>>(tm, q);
       return check_launch("nesie_gemm_nt_3xtf32");
     }
   }
@@ -743,15 +743,15 @@ extern "C" int nesie_gemm_wgrad_3xtf32(long long r, int n, int k, const float *a
       if (q.nstages > G_MAXSTAGES) q.nstages = G_MAXSTAGES;
       NESIE_REQUIRE(q.nstages >= 1, "k too large for shared memory");
       const size_t smem = (size_t)q.nstages * stage + 1024;
-      NESIE_CUDA(cudaFuncSetAttribute(gemm_wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem));
+      auto kern = gemm_tma_capped() ? gemm_wgrad_tma_kernel<T_MAXREG> : gemm_wgrad_tma_kernel<96>;
+      NESIE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       q.nchunks = nsplits;
       q.chunk = wgrad_chunk((r + 31) / 32, (n + 127) / 128);
       const int mblocks = (n + 127) / 128;
       int gx = num_sms() / mblocks;
       if (gx < 1) gx = 1;
       if (gx > nsplits) gx = nsplits;
-      gemm_wgrad_tma_kernel<<<dim3(gx, mblocks), T_THREADS, smem, (cudaStream_t)stream>>>(ta, tb, q);
+      kern<<<dim3(gx, mblocks), T_THREADS, smem, (cudaStream_t)stream>>>(ta, tb, q);
       return check_launch("nesie_gemm_wgrad_3xtf32");
     }
   }

@@ -26,6 +26,12 @@ namespace {
 constexpr int T_EPIW = 8;   // epilogue warps (NT); the weight-gradient kernel uses the first four
 constexpr int T_XFW = 8;    // transform warps
 constexpr int T_THREADS = 32 * (T_EPIW + T_XFW + 2);  // + producer warp + MMA warp
+// A second build capped at 64 registers can share an SM with a CTA of the FPS kernel (256 threads x
+// 112 registers) that the input pipeline runs on another stream.  Measured in bench.py (same box,
+// alternating): capped 9.62 / 9.48 ms per step, uncapped 9.51 / 9.35 -- the cap costs the kernels
+// more than co-residency returns, so the uncapped build is the default (NESIE_GEMM_REGS=64 selects
+// the capped one).
+constexpr int T_MAXREG = 64;
 constexpr int T_XF0 = T_EPIW, T_PROD = T_EPIW + T_XFW, T_MMA = T_PROD + 1;
 
 __device__ __forceinline__ void g_tma_2d(unsigned dst, const CUtensorMap *tm, int c0, int c1,
@@ -58,7 +64,8 @@ struct GemmTmaParams {
   int dbg;
 };
 
-__global__ void __launch_bounds__(T_THREADS, 1)
+template <int MAXREG>
+__global__ void __maxnreg__(MAXREG)
 gemm_nt_tma_kernel(const __grid_constant__ CUtensorMap tmA, GemmTmaParams p) {
   extern __shared__ unsigned char g_smem_dyn[];
   unsigned char *smem = reinterpret_cast<unsigned char *>(
@@ -257,7 +264,8 @@ struct WgradTmaParams {
   int dbg;
 };
 
-__global__ void __launch_bounds__(T_THREADS, 1)
+template <int MAXREG>
+__global__ void __maxnreg__(MAXREG)
 gemm_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       WgradTmaParams p) {
   extern __shared__ unsigned char g_smem_dyn[];
@@ -509,6 +517,11 @@ inline bool make_tmap(CUtensorMap *tm, const float *base, long long rows, long l
   return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+inline bool gemm_tma_capped() {
+  const char *e = getenv("NESIE_GEMM_REGS");
+  return e && atoi(e) <= T_MAXREG;
 }
 
 inline bool gemm_tma_enabled() {

@@ -33,9 +33,13 @@ def gemm_nt(a, w, transpose_w=False):
         sn, sk = K, 1
     out = torch.empty((R, N), dtype=torch.float32, device=a.device)
     with torch.cuda.device(a.device):
-        img = _pack(w, N, K, sn, sk)
-        _lib.call("nesie_gemm_nt_3xtf32", R, N, K, _lib.ptr(a), K, _lib.ptr(img), _lib.ptr(out), N,
-                  _lib.stream())
+        # the kernel produces at most 256 output columns (one TMEM accumulator): wider products
+        # (the data gradient of a layer with more than 256 input channels) run as column blocks
+        for n0 in range(0, N, 256):
+            nb = min(256, N - n0)
+            img = _pack(w.reshape(-1)[n0 * sn:], nb, K, sn, sk)
+            _lib.call("nesie_gemm_nt_3xtf32", R, nb, K, _lib.ptr(a), K, _lib.ptr(img),
+                      _lib.ptr(out) + 4 * n0, N, _lib.stream())
     return out
 
 
@@ -53,7 +57,7 @@ def wgrad(gy, x):
 
 
 def supported(n, k):
-    return 1 <= n <= 256 and k >= 1
+    return 1 <= n <= 1024 and k >= 1
 
 
 class _LinearRows(Function):
@@ -82,7 +86,7 @@ class _LinearRows(Function):
 
 
 def linear_rows(x, w):
-    """x (R, K) @ w (N, K)^T with fp32 parity on the tensor cores; falls back to torch for N > 256."""
+    """x (R, K) @ w (N, K)^T with fp32 parity on the tensor cores (library GEMM beyond N = 1024)."""
     if not supported(w.shape[0], w.shape[1]) or not x.is_cuda:
         return torch.nn.functional.linear(x, w)
     return _LinearRows.apply(x, w)

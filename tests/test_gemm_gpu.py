@@ -9,7 +9,7 @@ pytestmark = pytest.mark.gpu
 
 @pytest.mark.parametrize("R,N,K", [(128, 64, 4), (1000, 64, 64), (4096, 128, 131), (300, 256, 128),
                                    (65536, 128, 259), (257, 16, 32), (5000, 4, 64), (2048, 259 - 3, 128),
-                                   (1, 128, 128), (70000, 256, 128)])
+                                   (1, 128, 128), (70000, 256, 128), (4096, 515, 256), (8192, 512, 256)])
 def test_gemm_matches_float64(R, N, K):
     torch.manual_seed(R + N + K)
     a = torch.randn(R, K, device="cuda")
