@@ -12,7 +12,8 @@ all-reduce per step) -> weak scaling.  Prints ONE JSON line (rank 0).
   value  : scenes/s with the batch already resident in HBM (CUDA events, max over ranks)
   e2e    : scenes/s through the same public API with the batch in pinned host memory: every step
            copies its inputs host->device and reads the loss back
-  roofline: the dominant hand-written kernel (FPS 40000->2048), timed live with CUDA events
+  roofline: the dominant hand-written kernel on the critical path (tcgen05 row GEMM at its largest
+           shape), timed live with CUDA events; FPS (off the critical path) is reported beside it
   cpu_baseline: the same step on the host cores with the oracle port of the reference kernels
            (the reference has no CPU path of its own), bounded to 1 scene per step
 `--impl reference` times that CPU port alone (all host threads).
@@ -33,6 +34,10 @@ sys.path.insert(0, ROOT)
 SCENES_PER_GPU = 8
 N_POINTS = 40000
 WORKLOAD = "votenet_pretrain_fwd_bwd_adamw_b8_per_gpu_40kpts_18cls"
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the roofline kernel at the shape timed
+# below, from the ncu --set full capture summarised in profiles/r01_ncu_notes.md (268.5 MB read +
+# 480.0 MB written; 57 MB of the 537 MB output were still in L2 when the kernel ended)
+GEMM_DRAM_TRAFFIC = 748.6e6
 
 
 def peaks():
@@ -313,42 +318,92 @@ def main():
     launches = (_lib.LAUNCHES - l0) * K
 
     # ---- end to end: pinned host -> device every step, loss read back every step ---------------
-    sink = torch.zeros(1).pin_memory()
+    # The loss of every step is copied to pinned host memory right behind the step; the host waits
+    # for it one step later (the way a training loop logs), so the copy does not drain the pipeline.
+    sinks = [torch.zeros(1).pin_memory() for _ in range(2)]
+    sink_ev = [torch.cuda.Event(), torch.cuda.Event()]
+    seen = {"n": 0, "last": 0.0}
 
     def read_loss():
-        sink.copy_(s_loss.reshape(1), non_blocking=False)  # device -> host, synchronises
+        i = seen["n"]
+        sinks[i & 1].copy_(s_loss.reshape(1), non_blocking=True)   # device -> host
+        sink_ev[i & 1].record()
+        if i > 0:
+            sink_ev[(i - 1) & 1].synchronize()
+            seen["last"] = float(sinks[(i - 1) & 1][0])
+        seen["n"] = i + 1
 
-    run_pipeline(2, host_pts, host_gt, read_loss)
-    ms_e2e = timed(lambda: run_pipeline(K, host_pts, host_gt, read_loss))
+    def drain_loss():
+        i = seen["n"]
+        if i > 0:
+            sink_ev[(i - 1) & 1].synchronize()
+            seen["last"] = float(sinks[(i - 1) & 1][0])
+
+    def e2e_run(n):
+        run_pipeline(n, host_pts, host_gt, read_loss)
+        drain_loss()
+
+    e2e_run(2)
+    ms_e2e = timed(lambda: e2e_run(K))
     e2e_value = world * SCENES_PER_GPU * K / (ms_e2e / 1e3)
     h2d = host_pts[0].numel() * 4 + sum(t.numel() * t.element_size() for t in host_gt[0])
-    final_loss = float(sink[0])
+    final_loss = seen["last"]
 
     # ---- dominant hand-written kernel, timed live ---------------------------------------------
+    # By time on the step's critical path that is the tcgen05 row GEMM of the SA shared MLPs
+    # (gemm_nt_tma_kernel: ~1.8 ms per step over 56 launches; FPS is longer as a single launch but
+    # runs off the critical path in the input pipeline).  Its largest launch is SA1 layer 3
+    # (forward 64 -> 128 channels; the data gradient has the mirrored shape and the same bytes):
+    # R = 8 scenes x 2048 groups x 64 samples rows.  HBM-bound: algorithmic bytes = 4 R (K + N).
+    from nesie_b200 import linear_rows as lr
+    R_, K_, N_ = SCENES_PER_GPU * 2048 * 64, 64, 128
+    ga = torch.randn(R_, K_, device=dev)
+    gw = torch.randn(N_, K_, device=dev)
+    gout = torch.empty(R_, N_, device=dev)
+    gimg = lr._pack(gw, N_, K_, K_, 1)
+
+    def one_gemm():
+        _lib.call("nesie_gemm_nt_3xtf32", R_, N_, K_, _lib.ptr(ga), K_, _lib.ptr(gimg),
+                  _lib.ptr(gout), N_, _lib.stream())
+
+    for _ in range(5):
+        one_gemm()
+    torch.cuda.synchronize()
+    reps, ts = 10, []
+    for _ in range(max(K // 2, 5)):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):      # back to back: 805 MB per launch, nothing survives in the 126 MB L2
+            one_gemm()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b) / reps)
+    gemm_ms = sum(ts) / len(ts)
+    del ga, gout
     xyz = dev_pts[0][..., :3].contiguous()
     for _ in range(3):
         nb.furthest_point_sample(xyz, 2048)
     torch.cuda.synchronize()
-    ts = []
-    for _ in range(max(K, 10)):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(5):
         nb.furthest_point_sample(xyz, 2048)
-        b.record()
-        torch.cuda.synchronize()
-        ts.append(a.elapsed_time(b))
-    fps_ms = sum(ts) / len(ts)
+    b.record()
+    torch.cuda.synchronize()
+    fps_ms = a.elapsed_time(b) / 5
     pk, pk_kind = peaks()
-    alg_bytes = SCENES_PER_GPU * (12 * N_POINTS + 4 * 2048)  # B*(12N + 4M)
-    achieved = alg_bytes / (fps_ms * 1e-3) / 1e9
-    roofline = {"kernel": "fps_reg_kernel (FPS 40000->2048, batch 8)", "bound": "hbm",
-                "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk_kind,
-                "kernel_ms": fps_ms,
-                "point_updates_per_s": SCENES_PER_GPU * 2047 * N_POINTS / (fps_ms * 1e-3),
-                "note": "FPS is a chain of 2047 dependent argmax steps: latency/issue-bound, not "
-                        "HBM-bound (3.9 MB of algorithmic bytes); the HBM fraction is reported "
-                        "because the contract asks for it, the per-op table is in profiles/"}
+    alg_bytes = 4.0 * R_ * (K_ + N_)
+    achieved = alg_bytes / (gemm_ms * 1e-3) / 1e9
+    roofline = {"kernel": f"gemm_nt_tma_kernel (3xTF32 tcgen05 row GEMM, SA1 layer 3: {R_} x {K_} -> {N_})",
+                "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / pk["hbm_gbs"], "traffic": GEMM_DRAM_TRAFFIC, "peak_source": pk_kind,
+                "kernel_ms": gemm_ms, "algorithmic_bytes": alg_bytes,
+                "tensor_tflops_fp32_equiv": 2.0 * R_ * K_ * N_ / (gemm_ms * 1e-3) / 1e12,
+                "off_critical_path": {"kernel": "fps_reg_kernel (FPS 40000->2048, batch 8)",
+                                      "kernel_ms": fps_ms,
+                                      "point_updates_per_s": SCENES_PER_GPU * 2047 * N_POINTS / (fps_ms * 1e-3),
+                                      "note": "2047 dependent argmax steps: latency-bound (3.9 MB of "
+                                              "algorithmic bytes), overlapped with the previous step"}}
 
     line = {"metric": "train_scenes_per_s", "value": value, "unit": "scenes/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,

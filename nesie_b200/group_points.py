@@ -152,7 +152,7 @@ class _QueryGroupRows(Function):
                 _lib.call("nesie_group_rows_grad", B, C, N, npoint, nsample, _lib.ptr(grad_rows),
                           _lib.ptr(idx), ctx.radius, _lib.ptr(g_table), _lib.ptr(g_xyz),
                           _lib.ptr(g_center), ctx.ld, _lib.stream())
-        g_feat = g_table.transpose(1, 2).contiguous() if g_table is not None else None
+        g_feat = g_table.transpose(1, 2) if g_table is not None else None  # view: no copy
         return g_xyz, g_center, g_feat, None, None, None
 
 

@@ -196,7 +196,9 @@ class BasePointSAModule(nn.Module):
                 # fused BatchNorm(batch stats) + ReLU (+ the max-pool over the K rows of a group)
                 x = bn_rows.bn_relu_rows(x, bn, K if last else 0)
                 if last:
-                    return x.view(B, M, -1).transpose(1, 2).contiguous()
+                    # (B, C, M) as the reference returns it, as a VIEW of the point-major rows: the
+                    # next SA level's row gather wants exactly that storage order
+                    return x.view(B, M, -1).transpose(1, 2)
                 continue
             if bn.training and bn.track_running_stats:
                 bn.num_batches_tracked.add_(1)
@@ -230,7 +232,9 @@ class BasePointSAModule(nn.Module):
                 new_features = self.mlps[i](grouped_results)
                 new_features = self._pool_features(new_features)
             new_features_list.append(new_features)
-        return new_xyz, torch.cat(new_features_list, dim=1), indices
+        new_features = new_features_list[0] if len(new_features_list) == 1 \
+            else torch.cat(new_features_list, dim=1)
+        return new_xyz, new_features, indices
 
 
 class PointSAModuleMSG(BasePointSAModule):
@@ -322,7 +326,7 @@ class PointFPModule(nn.Module):
             x = F.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias,
                              bn.training or not bn.track_running_stats, bn.momentum, bn.eps)
             x = F.relu(x, inplace=True)
-        return x.view(B, n, -1).transpose(1, 2).contiguous()
+        return x.view(B, n, -1).transpose(1, 2)  # (B, C, n) view of point-major rows
 
 
 SA_MODULES = {'PointSAModule': PointSAModule, 'PointSAModuleMSG': PointSAModuleMSG}
