@@ -690,11 +690,11 @@ extern "C" int nesie_gemm_nt_3xtf32(long long r, int n, int k, const float *a, l
       { const char *e = getenv("NESIE_GEMM_DBG"); q.dbg = e ? atoi(e) : 0; }
       const size_t stage = 2 * G_ASLAB + 2 * (size_t)p.npad * 128;
       const size_t epi = (size_t)T_EPIW * 4096;
-      q.nstages = (int)((226 * 1024 - epi) / stage);
+      q.nstages = (int)((G_SMEM_BUDGET - epi) / stage);
       if (q.nstages > G_MAXSTAGES) q.nstages = G_MAXSTAGES;
       const size_t smem = (size_t)q.nstages * stage + epi + 1024;
       auto kern = gemm_tma_capped() ? gemm_nt_tma_kernel<T_MAXREG> : gemm_nt_tma_kernel<96>;
-      NESIE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      NESIE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G_MAX_DYN_SMEM));
       int grid = num_sms();
       if (ntiles_all < grid) grid = ntiles_all;
       kern<<<grid, T_THREADS, smem, (cudaStream_t)stream>>>(tm, q);
@@ -704,11 +704,11 @@ extern "C" int nesie_gemm_nt_3xtf32(long long r, int n, int k, const float *a, l
   p.fast = ((lda & 3) == 0) && ((k & 3) == 0) && ((reinterpret_cast<uintptr_t>(a) & 15) == 0);
   { const char *e = getenv("NESIE_GEMM_DBG"); p.dbg = e ? atoi(e) : 0; }
   const size_t stage = 2 * G_ASLAB + 2 * (size_t)p.npad * 128;
-  p.nstages = (int)((226 * 1024 - G_EPI_STAGE) / stage);
+  p.nstages = (int)((G_SMEM_BUDGET - G_EPI_STAGE) / stage);
   if (p.nstages > G_MAXSTAGES) p.nstages = G_MAXSTAGES;
   const size_t smem = (size_t)p.nstages * stage + G_EPI_STAGE + 1024;
   NESIE_CUDA(cudaFuncSetAttribute(gemm_nt_3xtf32_kernel,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, G_MAX_DYN_SMEM));
   const int ntiles = (p.R + G_TILE - 1) / G_TILE;
   int grid = num_sms();
   if (ntiles < grid) grid = ntiles;
@@ -739,12 +739,12 @@ extern "C" int nesie_gemm_wgrad_3xtf32(long long r, int n, int k, const float *a
       q.R = (int)r; q.N = n; q.K = k; q.kp = (k + 31) & ~31; q.P = partials;
       { const char *e = getenv("NESIE_GEMM_DBG"); q.dbg = e ? atoi(e) : 0; }
       const size_t stage = 2 * (size_t)(4 * 4096) + 2 * (size_t)(q.kp >> 5) * 4096;
-      q.nstages = (int)((226 * 1024) / stage);
+      q.nstages = (int)((G_SMEM_BUDGET) / stage);
       if (q.nstages > G_MAXSTAGES) q.nstages = G_MAXSTAGES;
       NESIE_REQUIRE(q.nstages >= 1, "k too large for shared memory");
       const size_t smem = (size_t)q.nstages * stage + 1024;
       auto kern = gemm_tma_capped() ? gemm_wgrad_tma_kernel<T_MAXREG> : gemm_wgrad_tma_kernel<96>;
-      NESIE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      NESIE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G_MAX_DYN_SMEM));
       q.nchunks = nsplits;
       q.chunk = wgrad_chunk((r + 31) / 32, (n + 127) / 128);
       const int mblocks = (n + 127) / 128;
@@ -761,12 +761,12 @@ extern "C" int nesie_gemm_wgrad_3xtf32(long long r, int n, int k, const float *a
   p.lda = lda; p.ldb = ldb;
   p.A = a; p.B = b; p.P = partials;
   const size_t stage = 2 * (size_t)(4 * 4096) + 2 * (size_t)(p.kp >> 5) * 4096;
-  p.nstages = (int)((226 * 1024) / stage);
+  p.nstages = (int)((G_SMEM_BUDGET) / stage);
   if (p.nstages > G_MAXSTAGES) p.nstages = G_MAXSTAGES;
   NESIE_REQUIRE(p.nstages >= 1, "k too large for shared memory");
   const size_t smem = (size_t)p.nstages * stage + 1024;
   NESIE_CUDA(cudaFuncSetAttribute(gemm_wgrad_3xtf32_kernel,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, G_MAX_DYN_SMEM));
   p.nchunks = nsplits;
   p.vec = ((lda & 3) == 0) && ((ldb & 3) == 0) && ((n & 3) == 0) && ((k & 3) == 0) &&
           (((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0);

@@ -7,6 +7,13 @@
 namespace nesie {
 namespace {
 
+// Dynamic shared memory limit the GEMM kernels opt in to (227 KB per CTA minus 1 KB for their static
+// barriers).  Always this constant rather than the launch's own size: the attribute is per FUNCTION,
+// and a CUDA graph replayed (or profiled node by node by ncu) after a later, smaller launch lowered
+// it fails with a launch error.
+constexpr int G_MAX_DYN_SMEM = 232448 - 1024;
+constexpr int G_SMEM_BUDGET = 224 * 1024;          // stages (+ epilogue staging); + 1 KB alignment slack
+
 constexpr int G_TILE = 128;
 constexpr int G_SLABK = 32;            // fp32 elements per 128-byte swizzle row
 constexpr int G_MAXSTAGES = 4;
