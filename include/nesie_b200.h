@@ -253,6 +253,19 @@ int nesie_gemm_pack_b(int n, int k, long long stride_n, long long stride_k, cons
                       void *image, void *stream);
 int nesie_gemm_nt_3xtf32(long long r, int n, int k, const float *a, long long lda,
                          const void *b_image, float *c, long long ldc, void *stream);
+/* The same GEMM with the neighbouring BatchNorm work fused in (TMA path only: 16-byte aligned rows,
+ * n and k multiples of 4; nesie_gemm_fused_supported() tells):
+ *   pro_scale / pro_shift (k floats each, both or neither): the A operand is
+ *       relu(a * scale + shift), i.e. the training BatchNorm + ReLU of the previous layer applied on
+ *       the fly from its statistics, so that the activation itself never goes to memory;
+ *   col_stats (nullable): receives nesie_gemm_stats_parts(r) blocks of [2][n] floats, the partial
+ *       column sums of C and of C^2 -- the batch statistics of this layer's BatchNorm -- for
+ *       nesie_bn_rows_forward_fused. */
+int nesie_gemm_fused_supported(long long r, int n, int k, const float *a, long long lda, long long ldc);
+int nesie_gemm_stats_parts(long long r);
+int nesie_gemm_nt_3xtf32_fused(long long r, int n, int k, const float *a, long long lda,
+                               const void *b_image, float *c, long long ldc, const float *pro_scale,
+                               const float *pro_shift, float *col_stats, void *stream);
 /* Diagnostic only: per-role cycle counters of CTA 0 collected by launches made with the environment
  * variable NESIE_GEMM_DBG & 128 (16 values; reading resets them). */
 int nesie_gemm_debug_profile(long long *out16);
@@ -264,6 +277,10 @@ int nesie_gemm_wgrad_splits(long long r, int n, int k);
 int nesie_gemm_wgrad_3xtf32(long long r, int n, int k, const float *a, long long lda,
                             const float *b, long long ldb, float *partials, int nsplits,
                             void *stream);
+/* ... with B = relu(b * scale + shift) applied on the fly (k floats each; TMA path only). */
+int nesie_gemm_wgrad_3xtf32_fused(long long r, int n, int k, const float *a, long long lda,
+                                  const float *b, long long ldb, const float *pro_scale,
+                                  const float *pro_shift, float *partials, int nsplits, void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * Training-mode BatchNorm (batch statistics) + ReLU [+ max-pool over k consecutive rows] on
@@ -282,6 +299,15 @@ int nesie_bn_relu_rows_forward(long long r, int c, int k, const float *y, const 
                                const float *beta, float eps, float momentum, float *running_mean,
                                float *running_var, float *stats, float *a_or_pooled,
                                unsigned char *arg, void *workspace, void *stream);
+/* forward with the options of the fused pipeline: col_partials (nullable) = nparts blocks of [2][c]
+ * column sums of y and y^2 from nesie_gemm_nt_3xtf32_fused, replacing the statistics sweep over y;
+ * a_or_pooled == NULL: statistics (and running stats) only -- the consumer GEMM applies
+ * scale / shift + ReLU in its prologue.  workspace may be NULL when col_partials is given. */
+int nesie_bn_rows_forward_fused(long long r, int c, int k, const float *y, const float *gamma,
+                                const float *beta, float eps, float momentum, float *running_mean,
+                                float *running_var, const float *col_partials, int nparts,
+                                float *stats, float *a_or_pooled, unsigned char *arg,
+                                void *workspace, void *stream);
 int nesie_bn_relu_rows_backward(long long r, int c, int k, const float *y, const float *d_a,
                                 const unsigned char *arg, const float *stats, float *d_y,
                                 float *d_gamma, float *d_beta, void *workspace, void *stream);

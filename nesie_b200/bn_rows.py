@@ -19,7 +19,7 @@ def supported(y, bn, k=0):
 class _BNReLURows(Function):
 
     @staticmethod
-    def forward(ctx, y, gamma, beta, running_mean, running_var, eps, momentum, k):
+    def forward(ctx, y, gamma, beta, running_mean, running_var, eps, momentum, k, col_partials=None):
         y = y.contiguous()
         R, C = y.shape
         dev = y.device
@@ -32,11 +32,18 @@ class _BNReLURows(Function):
             out = torch.empty((R // k, C), dtype=torch.float32, device=dev)
             arg = torch.empty((R // k, C), dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
-            _lib.call("nesie_bn_relu_rows_forward", R, C, k, _lib.ptr(y), _lib.ptr(gamma),
-                      _lib.ptr(beta), float(eps), float(momentum), _lib.ptr(running_mean),
-                      _lib.ptr(running_var), _lib.ptr(stats), _lib.ptr(out), _lib.ptr(arg),
-                      _lib.ptr(ws), _lib.stream())
-            _lib.LAUNCHES += 2
+            if col_partials is None:
+                _lib.call("nesie_bn_relu_rows_forward", R, C, k, _lib.ptr(y), _lib.ptr(gamma),
+                          _lib.ptr(beta), float(eps), float(momentum), _lib.ptr(running_mean),
+                          _lib.ptr(running_var), _lib.ptr(stats), _lib.ptr(out), _lib.ptr(arg),
+                          _lib.ptr(ws), _lib.stream())
+                _lib.LAUNCHES += 2
+            else:  # statistics from the producing GEMM's column sums: no sweep over y for them
+                _lib.call("nesie_bn_rows_forward_fused", R, C, k, _lib.ptr(y), _lib.ptr(gamma),
+                          _lib.ptr(beta), float(eps), float(momentum), _lib.ptr(running_mean),
+                          _lib.ptr(running_var), _lib.ptr(col_partials), col_partials.shape[0],
+                          _lib.ptr(stats), _lib.ptr(out), _lib.ptr(arg), _lib.ptr(ws), _lib.stream())
+                _lib.LAUNCHES += 1
         ctx.save_for_backward(y, stats, arg)
         ctx.k = k
         ctx.mark_non_differentiable(running_mean, running_var) if False else None
@@ -57,15 +64,16 @@ class _BNReLURows(Function):
                       _lib.ptr(arg), _lib.ptr(stats), _lib.ptr(d_y), _lib.ptr(d_gamma),
                       _lib.ptr(d_beta), _lib.ptr(ws), _lib.stream())
             _lib.LAUNCHES += 2
-        return d_y, d_gamma, d_beta, None, None, None, None, None
+        return d_y, d_gamma, d_beta, None, None, None, None, None, None
 
 
-def bn_relu_rows(y, bn, k=0):
+def bn_relu_rows(y, bn, k=0, col_partials=None):
     """relu(batch_norm(y)) for y (R, C) with `bn`'s parameters in training mode; k > 0 additionally
-    max-pools every k consecutive rows -> (R/k, C).  Updates bn's running statistics."""
+    max-pools every k consecutive rows -> (R/k, C).  Updates bn's running statistics.
+    col_partials: optional (nparts, 2, C) column sums of y and y^2 from the producing GEMM."""
     if bn.track_running_stats:
         bn.num_batches_tracked.add_(1)
         rm, rv = bn.running_mean, bn.running_var
     else:
         rm = rv = None
-    return _BNReLURows.apply(y, bn.weight, bn.bias, rm, rv, bn.eps, bn.momentum, k)
+    return _BNReLURows.apply(y, bn.weight, bn.bias, rm, rv, bn.eps, bn.momentum, k, col_partials)

@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(FIN_CH * FIN_SLICES) bn_fwd_finalize_kernel(
   const double n = (double)R, m1 = s1 / n;
   double var = s2 / n - m1 * m1;  // variance of (y - pivot) == variance of y
   if (var < 0.0) var = 0.0;
-  const double mean = (double)Y[c] + m1;
+  const double mean = (Y ? (double)Y[c] : 0.0) + m1;  // Y == nullptr: pivot-free sums
   const float invstd = (float)(1.0 / sqrt(var + (double)eps));
   const float sc = gamma[c] * invstd;
   stats[c] = (float)mean;
@@ -313,22 +313,33 @@ extern "C" long long nesie_bn_rows_workspace_bytes(int c) {
 
 // Forward statistics + apply.  stats (4*C) receives mean, invstd, scale, shift (saved for backward).
 // K == 0: A (R, C) = relu(bn(Y)).   K > 0: pooled (R/K, C) + arg (R/K, C) uint8, A is not written.
-extern "C" int nesie_bn_relu_rows_forward(long long r, int c, int k, const float *y,
-                                          const float *gamma, const float *beta, float eps,
-                                          float momentum, float *running_mean, float *running_var,
-                                          float *stats, float *a_or_pooled, unsigned char *arg,
-                                          void *workspace, void *stream) {
+// col_partials != nullptr: [nparts][2][c] pivot-free column sums (sum y, sum y^2) produced by the
+// GEMM epilogue (nesie_gemm_nt_3xtf32_fused) replace the statistics sweep over y.
+// a_or_pooled == nullptr: statistics only (the consumer applies scale / shift + ReLU itself).
+static int bn_forward_impl(long long r, int c, int k, const float *y, const float *gamma,
+                           const float *beta, float eps, float momentum, float *running_mean,
+                           float *running_var, const float *col_partials, int nparts_in,
+                           float *stats, float *a_or_pooled, unsigned char *arg, void *workspace,
+                           void *stream) {
   NESIE_REQUIRE(shape_ok(r, c), "need R >= 1 and C a multiple of 4 in [4, 1024]");
   NESIE_REQUIRE(k >= 0 && k <= 254 && (k == 0 || r % k == 0), "bad pooling window");
-  NESIE_REQUIRE(y && gamma && beta && stats && a_or_pooled && workspace && (k == 0 || arg), "null pointer");
+  NESIE_REQUIRE(y && gamma && beta && stats && (!a_or_pooled || k == 0 || arg), "null pointer");
+  NESIE_REQUIRE(col_partials || workspace, "null pointer");
+  NESIE_REQUIRE(!col_partials || nparts_in >= 1, "need nparts >= 1 with col_partials");
   cudaStream_t st = (cudaStream_t)stream;
-  float *partial = reinterpret_cast<float *>(workspace);
-  const int nparts = parts_for(r, c);
-  bn_colsum_kernel<0><<<nparts, BN_THREADS, 0, st>>>(r, c, y, nullptr, nullptr, nullptr, nullptr,
-                                                    nullptr, partial);
-  bn_fwd_finalize_kernel<<<ceil_div(c, FIN_CH), dim3(FIN_CH, FIN_SLICES), 0, st>>>(r, c, nparts, y, partial, gamma, beta,
-                                                          eps, momentum, running_mean, running_var,
-                                                          stats);
+  if (col_partials) {
+    bn_fwd_finalize_kernel<<<ceil_div(c, FIN_CH), dim3(FIN_CH, FIN_SLICES), 0, st>>>(
+        r, c, nparts_in, nullptr, col_partials, gamma, beta, eps, momentum, running_mean, running_var,
+        stats);
+  } else {
+    float *partial = reinterpret_cast<float *>(workspace);
+    const int nparts = parts_for(r, c);
+    bn_colsum_kernel<0><<<nparts, BN_THREADS, 0, st>>>(r, c, y, nullptr, nullptr, nullptr, nullptr,
+                                                      nullptr, partial);
+    bn_fwd_finalize_kernel<<<ceil_div(c, FIN_CH), dim3(FIN_CH, FIN_SLICES), 0, st>>>(
+        r, c, nparts, y, partial, gamma, beta, eps, momentum, running_mean, running_var, stats);
+  }
+  if (!a_or_pooled) return check_launch("nesie_bn_rows_forward");
   if (k == 0) {
     const long long n4 = r * (c >> 2);
     bn_relu_apply_kernel<<<grid_for(n4), BN_THREADS, 0, st>>>(n4, c, y, stats, a_or_pooled);
@@ -338,6 +349,26 @@ extern "C" int nesie_bn_relu_rows_forward(long long r, int c, int k, const float
                                                                       a_or_pooled, arg);
   }
   return check_launch("nesie_bn_relu_rows_forward");
+}
+
+extern "C" int nesie_bn_relu_rows_forward(long long r, int c, int k, const float *y,
+                                          const float *gamma, const float *beta, float eps,
+                                          float momentum, float *running_mean, float *running_var,
+                                          float *stats, float *a_or_pooled, unsigned char *arg,
+                                          void *workspace, void *stream) {
+  NESIE_REQUIRE(a_or_pooled && workspace, "null pointer");
+  return bn_forward_impl(r, c, k, y, gamma, beta, eps, momentum, running_mean, running_var, nullptr, 0,
+                         stats, a_or_pooled, arg, workspace, stream);
+}
+
+extern "C" int nesie_bn_rows_forward_fused(long long r, int c, int k, const float *y,
+                                           const float *gamma, const float *beta, float eps,
+                                           float momentum, float *running_mean, float *running_var,
+                                           const float *col_partials, int nparts, float *stats,
+                                           float *a_or_pooled, unsigned char *arg, void *workspace,
+                                           void *stream) {
+  return bn_forward_impl(r, c, k, y, gamma, beta, eps, momentum, running_mean, running_var,
+                         col_partials, nparts, stats, a_or_pooled, arg, workspace, stream);
 }
 
 // Backward.  K == 0: d_a is (R, C).  K > 0: d_a is the pooled gradient (R/K, C) and arg the forward's.

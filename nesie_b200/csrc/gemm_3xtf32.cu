@@ -667,8 +667,9 @@ extern "C" int nesie_gemm_debug_profile(long long *out16) {
   return NESIE_OK;
 }
 
-extern "C" int nesie_gemm_nt_3xtf32(long long r, int n, int k, const float *a, long long lda,
-                                    const void *b_image, float *c, long long ldc, void *stream) {
+static int gemm_nt_impl(long long r, int n, int k, const float *a, long long lda,
+                        const void *b_image, float *c, long long ldc, const float *pro_scale,
+                        const float *pro_shift, float *col_stats, void *stream) {
   NESIE_REQUIRE(r >= 0 && n >= 1 && n <= 256 && k >= 1, "need r >= 0, 1 <= n <= 256, k >= 1");
   NESIE_REQUIRE(r < (1LL << 31) - 256, "too many rows");
   if (r == 0) return NESIE_OK;
@@ -687,6 +688,7 @@ extern "C" int nesie_gemm_nt_3xtf32(long long r, int n, int k, const float *a, l
       GemmTmaParams q;
       q.R = p.R; q.N = n; q.K = k; q.npad = p.npad; q.nslab = p.nslab; q.ldc = ldc;
       q.Bimg = p.Bimg; q.C = c;
+      q.pro_scale = pro_scale; q.pro_shift = pro_shift; q.col_stats = col_stats;
       { const char *e = getenv("NESIE_GEMM_DBG"); q.dbg = e ? atoi(e) : 0; }
       const size_t stage = 2 * G_ASLAB + 2 * (size_t)p.npad * 128;
       const size_t epi = (size_t)T_EPIW * 4096;
@@ -701,6 +703,8 @@ extern "C" int nesie_gemm_nt_3xtf32(long long r, int n, int k, const float *a, l
       return check_launch("nesie_gemm_nt_3xtf32");
     }
   }
+  NESIE_REQUIRE(!pro_scale && !col_stats,
+                "the fused prologue / statistics need the TMA path (16-byte aligned rows)");
   p.fast = ((lda & 3) == 0) && ((k & 3) == 0) && ((reinterpret_cast<uintptr_t>(a) & 15) == 0);
   { const char *e = getenv("NESIE_GEMM_DBG"); p.dbg = e ? atoi(e) : 0; }
   const size_t stage = 2 * G_ASLAB + 2 * (size_t)p.npad * 128;
@@ -716,6 +720,35 @@ extern "C" int nesie_gemm_nt_3xtf32(long long r, int n, int k, const float *a, l
   return check_launch("nesie_gemm_nt_3xtf32");
 }
 
+extern "C" int nesie_gemm_nt_3xtf32(long long r, int n, int k, const float *a, long long lda,
+                                    const void *b_image, float *c, long long ldc, void *stream) {
+  return gemm_nt_impl(r, n, k, a, lda, b_image, c, ldc, nullptr, nullptr, nullptr, stream);
+}
+
+extern "C" int nesie_gemm_fused_supported(long long r, int n, int k, const float *a, long long lda,
+                                          long long ldc) {
+  return r >= 1 && n >= 4 && n <= 256 && (n & 3) == 0 && (k & 3) == 0 && (lda & 3) == 0 &&
+         (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(a) & 15) == 0 && gemm_tma_enabled() &&
+         encode_tiled_fn() != nullptr;
+}
+
+extern "C" int nesie_gemm_stats_parts(long long r) {
+  if (r <= 0) return 0;
+  const long long ntiles = (r + G_TILE - 1) / G_TILE;
+  return 4 * (int)(ntiles < num_sms() ? ntiles : num_sms());
+}
+
+extern "C" int nesie_gemm_nt_3xtf32_fused(long long r, int n, int k, const float *a, long long lda,
+                                          const void *b_image, float *c, long long ldc,
+                                          const float *pro_scale, const float *pro_shift,
+                                          float *col_stats, void *stream) {
+  NESIE_REQUIRE((pro_scale == nullptr) == (pro_shift == nullptr), "scale and shift go together");
+  NESIE_REQUIRE(r >= 1, "need r >= 1");
+  NESIE_REQUIRE(nesie_gemm_fused_supported(r, n, k, a, lda, ldc), "shape / alignment not supported");
+  NESIE_REQUIRE((reinterpret_cast<uintptr_t>(c) & 15) == 0, "c must be 16-byte aligned");
+  return gemm_nt_impl(r, n, k, a, lda, b_image, c, ldc, pro_scale, pro_shift, col_stats, stream);
+}
+
 extern "C" int nesie_gemm_wgrad_splits(long long r, int n, int k) {
   (void)k;
   if (r <= 0 || n <= 0) return 0;
@@ -724,9 +757,9 @@ extern "C" int nesie_gemm_wgrad_splits(long long r, int n, int k) {
   return (int)((nslab + c - 1) / c);  // one partial block per chunk
 }
 
-extern "C" int nesie_gemm_wgrad_3xtf32(long long r, int n, int k, const float *a, long long lda,
-                                       const float *b, long long ldb, float *partials,
-                                       int nsplits, void *stream) {
+static int gemm_wgrad_impl(long long r, int n, int k, const float *a, long long lda,
+                           const float *b, long long ldb, const float *pro_scale,
+                           const float *pro_shift, float *partials, int nsplits, void *stream) {
   NESIE_REQUIRE(r >= 1 && n >= 1 && n <= 256 && k >= 1 && k <= 512, "need r>=1, n<=256, k<=512");
   NESIE_REQUIRE(r < (1LL << 31) - 256, "too many rows");
   NESIE_REQUIRE(a && b && partials, "null pointer");
@@ -737,6 +770,7 @@ extern "C" int nesie_gemm_wgrad_3xtf32(long long r, int n, int k, const float *a
         make_tmap(&tb, b, r, k, ldb, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) {
       WgradTmaParams q;
       q.R = (int)r; q.N = n; q.K = k; q.kp = (k + 31) & ~31; q.P = partials;
+      q.pro_scale = pro_scale; q.pro_shift = pro_shift;
       { const char *e = getenv("NESIE_GEMM_DBG"); q.dbg = e ? atoi(e) : 0; }
       const size_t stage = 2 * (size_t)(4 * 4096) + 2 * (size_t)(q.kp >> 5) * 4096;
       q.nstages = (int)((G_SMEM_BUDGET) / stage);
@@ -755,6 +789,7 @@ extern "C" int nesie_gemm_wgrad_3xtf32(long long r, int n, int k, const float *a
       return check_launch("nesie_gemm_wgrad_3xtf32");
     }
   }
+  NESIE_REQUIRE(!pro_scale, "the fused prologue needs the TMA path (16-byte aligned rows)");
   WgradParams p;
   p.R = (int)r; p.N = n; p.K = k;
   p.kp = (k + 31) & ~31;
@@ -781,4 +816,19 @@ extern "C" int nesie_gemm_wgrad_3xtf32(long long r, int n, int k, const float *a
   dim3 grid(gx, mblocks);
   gemm_wgrad_3xtf32_kernel<<<grid, W_THREADS, smem, (cudaStream_t)stream>>>(p);
   return check_launch("nesie_gemm_wgrad_3xtf32");
+}
+
+extern "C" int nesie_gemm_wgrad_3xtf32(long long r, int n, int k, const float *a, long long lda,
+                                       const float *b, long long ldb, float *partials,
+                                       int nsplits, void *stream) {
+  return gemm_wgrad_impl(r, n, k, a, lda, b, ldb, nullptr, nullptr, partials, nsplits, stream);
+}
+
+extern "C" int nesie_gemm_wgrad_3xtf32_fused(long long r, int n, int k, const float *a, long long lda,
+                                             const float *b, long long ldb, const float *pro_scale,
+                                             const float *pro_shift, float *partials, int nsplits,
+                                             void *stream) {
+  NESIE_REQUIRE(pro_scale && pro_shift, "null pointer");
+  NESIE_REQUIRE((k & 3) == 0, "k must be a multiple of 4");
+  return gemm_wgrad_impl(r, n, k, a, lda, b, ldb, pro_scale, pro_shift, partials, nsplits, stream);
 }

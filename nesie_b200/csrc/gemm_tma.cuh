@@ -52,6 +52,22 @@ __device__ __forceinline__ float4 lo_of_raw4(float4 v) {
   return make_float4(lo_of_raw(v.x), lo_of_raw(v.y), lo_of_raw(v.z), lo_of_raw(v.w));
 }
 
+// Operand prologue: the operand is relu(y * scale + shift) of the stored tensor y (training BatchNorm
+// + ReLU of the previous layer, applied on the fly so that the activation never goes to HBM).  The
+// value differs from the raw word, so both hi and lo are written.
+__device__ __forceinline__ void bn_relu_split4(float4 y, float4 sc, float4 sh, float4 &hi, float4 &lo) {
+  const float a0 = fmaxf(fmaf(y.x, sc.x, sh.x), 0.f), a1 = fmaxf(fmaf(y.y, sc.y, sh.y), 0.f);
+  const float a2 = fmaxf(fmaf(y.z, sc.z, sh.z), 0.f), a3 = fmaxf(fmaf(y.w, sc.w, sh.w), 0.f);
+  split_tf32_fast(a0, hi.x, lo.x);
+  split_tf32_fast(a1, hi.y, lo.y);
+  split_tf32_fast(a2, hi.z, lo.z);
+  split_tf32_fast(a3, hi.w, lo.w);
+}
+__device__ __forceinline__ float4 ldg4_guard(const float *p, int c, int n) {
+  // four consecutive per-channel constants; channels >= n read as 0 (n is a multiple of 4 here)
+  return c < n ? __ldg(reinterpret_cast<const float4 *>(p + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
 // ----------------------------------------------------------------------------------------------
 // C[R x N] = A[R x K] * B[N x K]^T   (B pre-split / pre-swizzled image as in the register kernel)
 // ----------------------------------------------------------------------------------------------
@@ -61,6 +77,8 @@ struct GemmTmaParams {
   long long ldc;
   const unsigned char *Bimg;
   float *C;
+  const float *pro_scale, *pro_shift;  // optional [K]: A operand = relu(a * scale + shift)
+  float *col_stats;                    // optional [gridDim.x * 4][2][N]: column sums of C and C^2
   int dbg;
 };
 
@@ -141,8 +159,22 @@ gemm_nt_tma_kernel(const __grid_constant__ CUtensorMap tmA, GemmTmaParams p) {
         float4 v[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) v[i] = g_lds128(sa + i * 4096);
+        if (p.pro_scale) {
+          // this thread's 16-byte position holds logical chunk (xt & 7) ^ (row & 7), and row & 7
+          // = (xt >> 3) & 7 for all four of its rows: four fixed columns per slab
+          const int col = ks * G_SLABK + 4 * ((xt & 7) ^ ((xt >> 3) & 7));
+          const float4 sc = ldg4_guard(p.pro_scale, col, p.K), sh = ldg4_guard(p.pro_shift, col, p.K);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) g_sts128(sa + G_ASLAB + i * 4096, lo_of_raw4(v[i]));
+          for (int i = 0; i < 4; ++i) {
+            float4 hi, lo;
+            bn_relu_split4(v[i], sc, sh, hi, lo);
+            g_sts128(sa + i * 4096, hi);
+            g_sts128(sa + G_ASLAB + i * 4096, lo);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) g_sts128(sa + G_ASLAB + i * 4096, lo_of_raw4(v[i]));
+        }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         g_mbar_arrive(g_smem_u32(&s_full[st]));
         w_wait += t1 - t0;
@@ -202,6 +234,9 @@ gemm_nt_tma_kernel(const __grid_constant__ CUtensorMap tmA, GemmTmaParams p) {
     const bool vec = ((p.ldc & 3) == 0) && ((p.N & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
     const unsigned stg = smem_base + (unsigned)(p.nstages * stage_bytes) + (unsigned)(warp * 4096);
     const int qr = lane >> 3, qc = lane & 7;   // read-back: row qr + 4i, 16-byte chunk qc
+    // optional BatchNorm statistics of the OUTPUT: lane l sums column c0 + l of every 32 x 32 block
+    // this warp drains (rows >= R are zero: TMA zero fill) -- up to four blocks (N = 256) per warp
+    float cs1[4] = {0.f, 0.f, 0.f, 0.f}, cs2[4] = {0.f, 0.f, 0.f, 0.f};
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
       const int acc = tcount & 1;
       const long long gr = (long long)tile * G_TILE + q * 32 + lane;
@@ -209,7 +244,10 @@ gemm_nt_tma_kernel(const __grid_constant__ CUtensorMap tmA, GemmTmaParams p) {
       g_mbar_wait(g_smem_u32(&s_accf[acc]), (tcount >> 1) & 1u);
       const long long te1 = clock64();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      for (int c0 = half * 32; c0 < p.npad; c0 += 32 * (T_EPIW / 4)) {
+#pragma unroll
+      for (int blk = 0; blk < 4; ++blk) {
+        const int c0 = half * 32 + blk * 32 * (T_EPIW / 4);
+        if (c0 >= p.npad) break;
         unsigned v[32];
         g_tmem_ld32(tmem + (unsigned)(acc * 256 + c0) + ((unsigned)(q * 32) << 16), v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -220,6 +258,24 @@ gemm_nt_tma_kernel(const __grid_constant__ CUtensorMap tmA, GemmTmaParams p) {
                      make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
                                  __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
           __syncwarp();
+          if (p.col_stats) {
+            float a1 = 0.f, a2 = 0.f;
+            const unsigned wo = (unsigned)((lane & 3) << 2);
+            const int ch = lane >> 2;
+            // rows >= R exist only in the last tile; with an operand prologue they are not zero
+            const long long left = (long long)p.R - ((long long)tile * G_TILE + q * 32);
+            const int nvalid = left >= 32 ? 32 : (left > 0 ? (int)left : 0);
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr) {
+              float y;
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(y) : "r"(stg + (unsigned)(rr * 128 + ((ch ^ (rr & 7)) << 4)) + wo) : "memory");
+              y = rr < nvalid ? y : 0.f;
+              a1 += y;
+              a2 = fmaf(y, y, a2);
+            }
+            cs1[blk] += a1;
+            cs2[blk] += a2;
+          }
           const int cc = c0 + qc * 4;
           const long long grow = (long long)tile * G_TILE + q * 32 + qr;
           float *dst = p.C + grow * p.ldc + cc;
@@ -243,6 +299,17 @@ gemm_nt_tma_kernel(const __grid_constant__ CUtensorMap tmA, GemmTmaParams p) {
         g_gemm_prof[8] += te1 - te0; g_gemm_prof[9] += clock64() - te1; g_gemm_prof[10] += 1;
       }
     }
+    if (p.col_stats) {
+      float *dst = p.col_stats + (size_t)(blockIdx.x * 4 + q) * 2 * p.N;
+#pragma unroll
+      for (int blk = 0; blk < 4; ++blk) {
+        const int c = half * 32 + blk * 32 * (T_EPIW / 4) + lane;
+        if (c < p.N) {
+          dst[c] = cs1[blk];
+          dst[p.N + c] = cs2[blk];
+        }
+      }
+    }
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -261,6 +328,7 @@ struct WgradTmaParams {
   int nstages;
   float *P;          // [nchunks][N][K] partial sums
   int nchunks, chunk;
+  const float *pro_scale, *pro_shift;  // optional [K]: B operand = relu(b * scale + shift)
   int dbg;
 };
 
@@ -357,14 +425,29 @@ gemm_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           for (int i = 0; i < 4; ++i)
             if (i < ma) g_sts128(sa + (unsigned)a_part + i * 4096, lo_of_raw4(v[i]));
         }
+        // position xt * 16 of a 4 KB block: row xt >> 3, 32-byte chunk ((xt >> 1) & 3) ^ (row & 3),
+        // half xt & 1 -> the same four channels (relative to the block) for every block
+        const int bch = (((xt >> 1) & 3) ^ ((xt >> 3) & 3)) * 8 + (xt & 1) * 4;
         for (int c = 0; c < nb; c += 4) {
           float4 v[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i)
             if (c + i < nb) v[i] = g_lds128(sb + (c + i) * 4096);
+          if (p.pro_scale) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (c + i < nb) g_sts128(sb + (unsigned)b_part + (c + i) * 4096, lo_of_raw4(v[i]));
+            for (int i = 0; i < 4; ++i)
+              if (c + i < nb) {
+                const int ch = (c + i) * 32 + bch;
+                float4 hi, lo;
+                bn_relu_split4(v[i], ldg4_guard(p.pro_scale, ch, p.K), ldg4_guard(p.pro_shift, ch, p.K), hi, lo);
+                g_sts128(sb + (c + i) * 4096, hi);
+                g_sts128(sb + (unsigned)b_part + (c + i) * 4096, lo);
+              }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (c + i < nb) g_sts128(sb + (unsigned)b_part + (c + i) * 4096, lo_of_raw4(v[i]));
+          }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         g_mbar_arrive(g_smem_u32(&s_full[st]));

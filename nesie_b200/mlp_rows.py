@@ -1,0 +1,158 @@
+"""Shared MLP (1x1 conv -> BatchNorm(batch statistics) -> ReLU, repeated) on row-major activations
+with the BatchNorm work fused into the tcgen05 GEMMs (training mode).
+
+Same parameters and arithmetic as the ConvModule stacks of the reference's SA / FP modules
+(ops/pointnet_modules/point_sa_module.py:136-158,279-288, point_fp_module.py:39-46).  Per layer the
+unfused path sweeps HBM five times forward (GEMM read + write, statistics read, apply read + write);
+here a layer is ONE kernel plus a tiny finalize:
+
+  y_l = gemm( relu(bn_{l-1}(y_{l-1})) , W_l )   prologue: scale / shift + ReLU of the previous layer on
+                                                the operand tile in shared memory (the activation is
+                                                never written); epilogue: column sums of y_l and y_l^2
+  stats_l = finalize(column sums)               mean / invstd / scale / shift + running statistics
+
+The last layer's BatchNorm + ReLU (+ max-pool over the k rows of a group) runs as the fused
+bn_relu_rows kernel fed with the GEMM's column sums.  Backward: weight gradient with the same
+prologue on its X operand, data gradient, then the BatchNorm backward kernels (which only need y and
+the saved statistics)."""
+import os
+
+import torch
+from torch.autograd import Function
+
+from . import _lib
+from . import bn_rows
+from .linear_rows import _pack, gemm_nt, wgrad
+
+
+def enabled():
+    return os.environ.get("NESIE_ROWS_FUSE", "1") != "0"
+
+
+def _gemm_supported(x, n, k):
+    return bool(_lib.lib().nesie_gemm_fused_supported(x.shape[0], n, k, _lib.ptr(x), k, n))
+
+
+def supported(x, layers):
+    """layers: [(weight (N, K), bn)]: every layer bias-free with a training-mode affine BatchNorm."""
+    if not (enabled() and x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and
+            x.is_contiguous() and x.shape[0] >= 2):
+        return False
+    k = x.shape[1]
+    for w, bn in layers:
+        n = w.shape[0]
+        if w.shape[1] != k or not (bn.training and bn.affine and bn.momentum is not None):
+            return False
+        if not (n % 4 == 0 and 4 <= n <= 256 and k % 4 == 0):
+            return False
+        k = n
+    return _gemm_supported(x, layers[0][0].shape[0], x.shape[1])
+
+
+def _gemm_fused(x, w, scale, shift, want_stats):
+    """y = [relu(x * scale + shift)] @ w.T, optionally with the column-sum partials of y."""
+    R, K = x.shape
+    N = w.shape[0]
+    y = torch.empty((R, N), dtype=torch.float32, device=x.device)
+    parts = None
+    if want_stats:
+        nparts = _lib.lib().nesie_gemm_stats_parts(R)
+        parts = torch.empty((nparts, 2, N), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        img = _pack(w, N, K, K, 1)
+        _lib.call("nesie_gemm_nt_3xtf32_fused", R, N, K, _lib.ptr(x), K, _lib.ptr(img), _lib.ptr(y), N,
+                  _lib.ptr(scale), _lib.ptr(shift), _lib.ptr(parts), _lib.stream())
+    return y, parts
+
+
+def _wgrad_fused(gy, x, scale, shift):
+    """gy^T @ relu(x * scale + shift) -> (N, K)."""
+    R, N = gy.shape
+    K = x.shape[1]
+    ns = _lib.lib().nesie_gemm_wgrad_splits(R, N, K)
+    parts = torch.empty((ns, N, K), dtype=torch.float32, device=gy.device)
+    with torch.cuda.device(gy.device):
+        _lib.call("nesie_gemm_wgrad_3xtf32_fused", R, N, K, _lib.ptr(gy), N, _lib.ptr(x), K,
+                  _lib.ptr(scale), _lib.ptr(shift), _lib.ptr(parts), ns, _lib.stream())
+    return parts.sum(dim=0)
+
+
+def _bn_stats(y, parts, gamma, beta, rm, rv, eps, momentum):
+    """[4, C] mean | invstd | scale | shift of y from the GEMM's column sums; updates rm / rv."""
+    R, C = y.shape
+    stats = torch.empty((4, C), dtype=torch.float32, device=y.device)
+    with torch.cuda.device(y.device):
+        _lib.call("nesie_bn_rows_forward_fused", R, C, 0, _lib.ptr(y), _lib.ptr(gamma), _lib.ptr(beta),
+                  float(eps), float(momentum), _lib.ptr(rm), _lib.ptr(rv), _lib.ptr(parts),
+                  parts.shape[0], _lib.ptr(stats), None, None, None, _lib.stream())
+    return stats
+
+
+class _LinearStats(Function):
+    """First layer: y = x @ w.T plus the column sums of y."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        y, parts = _gemm_fused(x, w, None, None, True)
+        ctx.save_for_backward(x, w)
+        ctx.mark_non_differentiable(parts)
+        return y, parts
+
+    @staticmethod
+    def backward(ctx, gy, _gparts):
+        x, w = ctx.saved_tensors
+        gy = gy.contiguous()
+        gx = gemm_nt(gy, w, transpose_w=True) if ctx.needs_input_grad[0] else None
+        gw = wgrad(gy, x) if ctx.needs_input_grad[1] else None
+        return gx, gw
+
+
+class _BNReLULinear(Function):
+    """y = relu(bn(y_prev)) @ w.T with bn's batch statistics taken from y_prev's column sums."""
+
+    @staticmethod
+    def forward(ctx, y_prev, parts_prev, gamma, beta, rm, rv, eps, momentum, w):
+        stats = _bn_stats(y_prev, parts_prev, gamma, beta, rm, rv, eps, momentum)
+        y, parts = _gemm_fused(y_prev, w, stats[2], stats[3], True)
+        ctx.save_for_backward(y_prev, stats, w)
+        ctx.mark_non_differentiable(parts)
+        return y, parts
+
+    @staticmethod
+    def backward(ctx, gy, _gparts):
+        y_prev, stats, w = ctx.saved_tensors
+        gy = gy.contiguous()
+        R, C = y_prev.shape
+        dev = y_prev.device
+        gw = _wgrad_fused(gy, y_prev, stats[2], stats[3]) if ctx.needs_input_grad[8] else None
+        g_act = gemm_nt(gy, w, transpose_w=True)          # gradient w.r.t. relu(bn(y_prev))
+        d_y = torch.empty_like(y_prev)
+        d_gamma = torch.empty((C,), dtype=torch.float32, device=dev)
+        d_beta = torch.empty((C,), dtype=torch.float32, device=dev)
+        ws = torch.empty((_lib.lib().nesie_bn_rows_workspace_bytes(C),), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.call("nesie_bn_relu_rows_backward", R, C, 0, _lib.ptr(y_prev), _lib.ptr(g_act), None,
+                      _lib.ptr(stats), _lib.ptr(d_y), _lib.ptr(d_gamma), _lib.ptr(d_beta),
+                      _lib.ptr(ws), _lib.stream())
+            _lib.LAUNCHES += 2
+        return d_y, None, d_gamma, d_beta, None, None, None, None, gw
+
+
+def _bn_buffers(bn):
+    if bn.track_running_stats:
+        bn.num_batches_tracked.add_(1)
+        return bn.running_mean, bn.running_var
+    return None, None
+
+
+def mlp_rows(x, layers, pool_k=0):
+    """x (R, K) -> relu(bn(... relu(bn(x @ W1^T)) ...)) as (R, C), or max-pooled over every pool_k
+    consecutive rows -> (R / pool_k, C).  `supported(x, layers)` must hold."""
+    w0, _ = layers[0]
+    y, parts = _LinearStats.apply(x, w0)
+    for li in range(1, len(layers)):
+        bn = layers[li - 1][1]
+        rm, rv = _bn_buffers(bn)
+        y, parts = _BNReLULinear.apply(y, parts, bn.weight, bn.bias, rm, rv, bn.eps, bn.momentum,
+                                       layers[li][0])
+    return bn_rows.bn_relu_rows(y, layers[-1][1], pool_k, col_partials=parts)

@@ -20,6 +20,7 @@ from .interpolate import three_interpolate, three_nn
 from . import sa_fused
 from .linear_rows import linear_rows
 from . import bn_rows
+from . import mlp_rows
 from .ball_query import ball_query
 
 def _rows_linear(x, w):
@@ -184,6 +185,14 @@ class BasePointSAModule(nn.Module):
 
     def _mlp_rows(self, i, x, B, M, K):
         layers = list(self.mlps[i])
+        if _fused_bn():
+            pairs = [(l.conv.weight.flatten(1), l.bn) for l in layers]
+            if x.shape[1] != pairs[0][0].shape[1]:  # rows zero-padded to a multiple of 4 columns
+                pairs[0] = (F.pad(pairs[0][0], (0, x.shape[1] - pairs[0][0].shape[1])), pairs[0][1])
+            if mlp_rows.supported(x, pairs):
+                # BatchNorm fused into the GEMMs: statistics in the epilogue, apply in the prologue
+                x = mlp_rows.mlp_rows(x, pairs, K)
+                return x.view(B, M, -1).transpose(1, 2)
         for li, layer in enumerate(layers):
             bn = layer.bn
             # fp32-parity GEMM on tcgen05 (3xTF32); NESIE_ROWS_GEMM=cublas selects the library GEMM
@@ -313,6 +322,10 @@ class PointFPModule(nn.Module):
     def _mlp_rows(self, feats):
         B, C, n = feats.shape
         x = feats.transpose(1, 2).reshape(B * n, C)
+        if _fused_bn() and all(l.conv.bias is None for l in self.mlps):
+            pairs = [(l.conv.weight.flatten(1), l.bn) for l in self.mlps]
+            if mlp_rows.supported(x, pairs):
+                return mlp_rows.mlp_rows(x, pairs).view(B, n, -1).transpose(1, 2)
         for layer in self.mlps:
             bn = layer.bn
             x = _rows_linear(x, layer.conv.weight.flatten(1))

@@ -26,6 +26,7 @@ from torch.nn import functional as F
 
 from .pointnet2_sa_ssg import PointNet2SASSG
 from . import bn_rows
+from . import mlp_rows
 from .pointnet_modules import ConvModule, PointSAModule, _fused_bn, _rows_linear
 from .side_loss import side_uncertainty_loss
 
@@ -44,6 +45,10 @@ def conv1d_rows(seq, x):
         return x
     B, C, n = x.shape
     r = x.transpose(1, 2).reshape(B * n, C)
+    if _fused_bn() and all(isinstance(m, ConvModule) and m.conv.bias is None for m in mods):
+        pairs = [(m.conv.weight.flatten(1), m.bn) for m in mods]
+        if mlp_rows.supported(r, pairs):  # BatchNorm fused into the GEMMs (mlp_rows.py)
+            return mlp_rows.mlp_rows(r, pairs).view(B, n, -1).transpose(1, 2)
     for m in mods:
         conv = m.conv if isinstance(m, ConvModule) else m
         r = _rows_linear(r, conv.weight.flatten(1))

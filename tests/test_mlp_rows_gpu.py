@@ -1,0 +1,84 @@
+"""Shared MLP with BatchNorm fused into the tcgen05 GEMMs (nesie_b200/mlp_rows.py) against a float64
+torch restatement of conv -> BN(batch stats) -> ReLU (ops/pointnet_modules/point_sa_module.py:279-288)."""
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from nesie_b200 import mlp_rows
+
+pytestmark = pytest.mark.gpu
+
+
+def _layers(chs, dtype, seed):
+    torch.manual_seed(seed)
+    out = []
+    for k, n in zip(chs[:-1], chs[1:]):
+        w = (torch.randn(n, k) * (2.0 / k) ** 0.5).to("cuda", dtype).requires_grad_(True)
+        bn = nn.BatchNorm1d(n).to("cuda", dtype)
+        with torch.no_grad():
+            bn.weight.copy_(torch.rand(n) + 0.5)
+            bn.bias.copy_(torch.randn(n) * 0.3)
+        out.append((w, bn))
+    return out
+
+
+def _reference(x, layers, pool_k):
+    for w, bn in layers:
+        x = F.relu(F.batch_norm(F.linear(x, w), bn.running_mean, bn.running_var, bn.weight, bn.bias,
+                                True, bn.momentum, bn.eps))
+    if pool_k:
+        x = x.view(-1, pool_k, x.shape[1]).amax(dim=1)
+    return x
+
+
+@pytest.mark.parametrize("R,chs,pool_k", [(4096, (8, 64, 64, 128), 16), (3000, (132, 128, 128, 256), 0),
+                                          (129 * 32, (4, 64, 64, 128), 32), (640, (256, 128, 128), 0),
+                                          (70000, (64, 64), 0)])
+def test_fused_mlp_matches_float64(R, chs, pool_k):
+    layers = _layers(chs, torch.float32, 1)
+    ref = _layers(chs, torch.float64, 1)
+    torch.manual_seed(5)
+    x = (torch.randn(R, chs[0], device="cuda") + 0.5).requires_grad_(True)
+    xd = x.detach().double().requires_grad_(True)
+    assert mlp_rows.supported(x, layers)
+    got = mlp_rows.mlp_rows(x, layers, pool_k)
+    want = _reference(xd, ref, pool_k)
+    scale = want.abs().max().item()
+    assert (got.double() - want).abs().max().item() < 2e-5 * scale
+    g = torch.randn_like(got)
+    got.backward(g)
+    want.backward(g.double())
+    rel = lambda a, b: ((a.double() - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()  # noqa: E731
+    # A pre-activation within fp32 rounding of zero takes the other branch of the ReLU derivative
+    # than in float64: with millions of elements that happens to a row now and then, and it is
+    # not an error of the kernels.  Such rows are counted, not compared.
+    row_err = (x.grad.double() - xd.grad).abs().max(dim=1).values / xd.grad.abs().max()
+    flipped = int((row_err > 1e-4).sum())
+    assert flipped <= R // 20000, (flipped, row_err.max().item())
+    ptol = 1e-4 if flipped == 0 else 1e-2
+    for (w, bn), (wd, bnd) in zip(layers, ref):
+        assert rel(w.grad, wd.grad) < ptol
+        assert rel(bn.weight.grad, bnd.weight.grad) < ptol
+        assert rel(bn.bias.grad, bnd.bias.grad) < ptol
+        assert rel(bn.running_mean, bnd.running_mean) < 1e-5
+        assert rel(bn.running_var, bnd.running_var) < 1e-5
+        assert int(bn.num_batches_tracked) == 1
+
+
+def test_fused_mlp_with_large_mean_keeps_variance():
+    """The GEMM epilogue sums y and y^2 without a pivot: a mean ten times the spread must still give
+    the variance to 1e-4."""
+    layers = _layers((64, 64), torch.float32, 2)
+    ref = _layers((64, 64), torch.float64, 2)
+    x = torch.randn(20000, 64, device="cuda") * 0.1 + 3.0
+    got = mlp_rows.mlp_rows(x, layers)
+    want = _reference(x.double(), ref, 0)
+    assert (got.double() - want).abs().max().item() < 5e-4 * want.abs().max().item()
+    assert ((layers[0][1].running_var.double() - ref[0][1].running_var).abs().max() /
+            ref[0][1].running_var.abs().max()).item() < 1e-4
+
+
+def test_unsupported_shapes_are_reported():
+    layers = _layers((7, 64), torch.float32, 3)
+    assert not mlp_rows.supported(torch.randn(100, 7, device="cuda"), layers)
