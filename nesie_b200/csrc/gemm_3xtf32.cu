@@ -289,8 +289,8 @@ struct WgradParams {
   int nstages;
   long long lda, ldb;
   const float *A, *B;
-  float *P;          // [nchunks][N][K] partial sums
-  int nchunks;       // row chunks of `chunk` slabs; one partial block each
+  float *P;          // [gridDim.x][N][K] partial sums, one block per CTA
+  int nchunks;       // row chunks of `chunk` slabs (one TMEM accumulation each)
   int chunk;         // slabs (of 32 rows) accumulated per TMEM accumulator
   int dbg;           // NESIE_GEMM_DBG & 128: cycle counters of CTA 0
   int mn;            // bit 0: B tile MN-major, bit 1: A tile MN-major (straight float4 copies);
@@ -587,7 +587,8 @@ __global__ void __launch_bounds__(W_THREADS, 1) gemm_wgrad_3xtf32_kernel(WgradPa
       g_mbar_wait(g_smem_u32(&s_accf[acc]), use & 1u);
       const long long te1 = clock64();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      float *prow = p.P + ((size_t)chunk * p.N + n) * p.K;
+      float *prow = p.P + ((size_t)blockIdx.x * p.N + n) * p.K;  // one partial block per CTA
+      const bool addto = ccount > 0;
       for (int c0 = 0; c0 < p.kp; c0 += 32) {
         unsigned v[32];
         g_tmem_ld32(tmem + (unsigned)(acc * 256 + c0) + ((unsigned)(warp * 32) << 16), v);
@@ -595,7 +596,7 @@ __global__ void __launch_bounds__(W_THREADS, 1) gemm_wgrad_3xtf32_kernel(WgradPa
         if (n < p.N) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (c0 + j < p.K) prow[c0 + j] = __uint_as_float(v[j]);
+            if (c0 + j < p.K) prow[c0 + j] = (addto ? prow[c0 + j] : 0.f) + __uint_as_float(v[j]);
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -749,12 +750,24 @@ extern "C" int nesie_gemm_nt_3xtf32_fused(long long r, int n, int k, const float
   return gemm_nt_impl(r, n, k, a, lda, b_image, c, ldc, pro_scale, pro_shift, col_stats, stream);
 }
 
+// row chunks (one TMEM accumulation each) and CTAs along x (one partial block each)
+static void wgrad_plan(long long r, int n, int *chunk, int *nchunks, int *gx) {
+  const long long nslab = (r + 31) / 32;
+  const int mblocks = (n + 127) / 128;
+  *chunk = wgrad_chunk(nslab, mblocks);
+  *nchunks = (int)((nslab + *chunk - 1) / *chunk);
+  int g = num_sms() / mblocks;
+  if (g < 1) g = 1;
+  if (g > *nchunks) g = *nchunks;
+  *gx = g;
+}
+
 extern "C" int nesie_gemm_wgrad_splits(long long r, int n, int k) {
   (void)k;
   if (r <= 0 || n <= 0) return 0;
-  const long long nslab = (r + 31) / 32;
-  const int c = wgrad_chunk(nslab, (n + 127) / 128);
-  return (int)((nslab + c - 1) / c);  // one partial block per chunk
+  int chunk, nchunks, gx;
+  wgrad_plan(r, n, &chunk, &nchunks, &gx);
+  return gx;  // one partial block per CTA
 }
 
 static int gemm_wgrad_impl(long long r, int n, int k, const float *a, long long lda,
@@ -779,12 +792,9 @@ static int gemm_wgrad_impl(long long r, int n, int k, const float *a, long long 
       const size_t smem = (size_t)q.nstages * stage + 1024;
       auto kern = gemm_tma_capped() ? gemm_wgrad_tma_kernel<T_MAXREG> : gemm_wgrad_tma_kernel<96>;
       NESIE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G_MAX_DYN_SMEM));
-      q.nchunks = nsplits;
-      q.chunk = wgrad_chunk((r + 31) / 32, (n + 127) / 128);
+      int gx;
+      wgrad_plan(r, n, &q.chunk, &q.nchunks, &gx);
       const int mblocks = (n + 127) / 128;
-      int gx = num_sms() / mblocks;
-      if (gx < 1) gx = 1;
-      if (gx > nsplits) gx = nsplits;
       kern<<<dim3(gx, mblocks), T_THREADS, smem, (cudaStream_t)stream>>>(ta, tb, q);
       return check_launch("nesie_gemm_wgrad_3xtf32");
     }
@@ -802,17 +812,14 @@ static int gemm_wgrad_impl(long long r, int n, int k, const float *a, long long 
   const size_t smem = (size_t)p.nstages * stage + 1024;
   NESIE_CUDA(cudaFuncSetAttribute(gemm_wgrad_3xtf32_kernel,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, G_MAX_DYN_SMEM));
-  p.nchunks = nsplits;
+  int gx;
+  wgrad_plan(r, n, &p.chunk, &p.nchunks, &gx);
   p.vec = ((lda & 3) == 0) && ((ldb & 3) == 0) && ((n & 3) == 0) && ((k & 3) == 0) &&
           (((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0);
   p.mn = p.vec ? 3 : 0;
   { const char *e = getenv("NESIE_GEMM_DBG"); p.dbg = e ? atoi(e) : 0; }
   { const char *e = getenv("NESIE_WGRAD_LAYOUT"); if (e && p.vec) p.mn = atoi(e) & 3; }
-  p.chunk = wgrad_chunk((r + 31) / 32, (n + 127) / 128);
   const int mblocks = (n + 127) / 128;
-  int gx = num_sms() / mblocks;
-  if (gx < 1) gx = 1;
-  if (gx > nsplits) gx = nsplits;
   dim3 grid(gx, mblocks);
   gemm_wgrad_3xtf32_kernel<<<grid, W_THREADS, smem, (cudaStream_t)stream>>>(p);
   return check_launch("nesie_gemm_wgrad_3xtf32");

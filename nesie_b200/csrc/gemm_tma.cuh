@@ -326,7 +326,7 @@ struct WgradTmaParams {
   int R, N, K;
   int kp;            // K rounded up to 32
   int nstages;
-  float *P;          // [nchunks][N][K] partial sums
+  float *P;          // [gridDim.x][N][K] partial sums, one block per CTA
   int nchunks, chunk;
   const float *pro_scale, *pro_shift;  // optional [K]: B operand = relu(b * scale + shift)
   int dbg;
@@ -530,23 +530,32 @@ gemm_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       g_mbar_wait(g_smem_u32(&s_accf[acc]), use & 1u);
       const long long te1 = clock64();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      float *prow = p.P + ((size_t)chunk * p.N + n) * p.K;
+      // One partial block per CTA: the chunks a CTA processes are added (round-to-nearest fp32,
+      // fixed order) into its own block, which stays in L2 between chunks; the thread that owns
+      // an element is the only one that ever touches it.
+      float *prow = p.P + ((size_t)blockIdx.x * p.N + n) * p.K;
+      const bool addto = ccount > 0;
       for (int c0 = 0; c0 < p.kp; c0 += 32) {
         unsigned v[32];
         g_tmem_ld32(tmem + (unsigned)(acc * 256 + c0) + ((unsigned)(warp * 32) << 16), v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (n < p.N) {
+          if ((p.K & 3) == 0) {
+            float4 old[8];
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (c0 + j + 3 < p.K && (p.K & 3) == 0) {
-              *reinterpret_cast<float4 *>(prow + c0 + j) =
-                  make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                              __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-            } else {
+            for (int j = 0; j < 8; ++j)
+              old[j] = (addto && c0 + 4 * j < p.K) ? *reinterpret_cast<const float4 *>(prow + c0 + 4 * j)
+                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-              for (int t = 0; t < 4; ++t)
-                if (c0 + j + t < p.K) prow[c0 + j + t] = __uint_as_float(v[j + t]);
-            }
+            for (int j = 0; j < 8; ++j)
+              if (c0 + 4 * j < p.K)
+                *reinterpret_cast<float4 *>(prow + c0 + 4 * j) =
+                    make_float4(old[j].x + __uint_as_float(v[4 * j]), old[j].y + __uint_as_float(v[4 * j + 1]),
+                                old[j].z + __uint_as_float(v[4 * j + 2]), old[j].w + __uint_as_float(v[4 * j + 3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c0 + j < p.K) prow[c0 + j] = (addto ? prow[c0 + j] : 0.f) + __uint_as_float(v[j]);
           }
         }
       }
