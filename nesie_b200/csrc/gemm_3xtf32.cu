@@ -693,10 +693,12 @@ static int gemm_nt_impl(long long r, int n, int k, const float *a, long long lda
       { const char *e = getenv("NESIE_GEMM_DBG"); q.dbg = e ? atoi(e) : 0; }
       const size_t stage = 2 * G_ASLAB + 2 * (size_t)p.npad * 128;
       const size_t epi = (size_t)T_EPIW * 4096;
-      q.nstages = (int)((G_SMEM_BUDGET - epi) / stage);
+      q.nstages = (int)((gemm_smem_budget() - epi) / stage);
+      if (q.nstages < 1) q.nstages = 1;
       if (q.nstages > G_MAXSTAGES) q.nstages = G_MAXSTAGES;
       const size_t smem = (size_t)q.nstages * stage + epi + 1024;
-      auto kern = gemm_tma_capped() ? gemm_nt_tma_kernel<T_MAXREG> : gemm_nt_tma_kernel<96>;
+      const int regs = gemm_tma_regs();
+      auto kern = regs == 64 ? gemm_nt_tma_kernel<64> : (regs == 88 ? gemm_nt_tma_kernel<88> : gemm_nt_tma_kernel<96>);
       NESIE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G_MAX_DYN_SMEM));
       int grid = num_sms();
       if (ntiles_all < grid) grid = ntiles_all;
@@ -786,11 +788,12 @@ static int gemm_wgrad_impl(long long r, int n, int k, const float *a, long long 
       q.pro_scale = pro_scale; q.pro_shift = pro_shift;
       { const char *e = getenv("NESIE_GEMM_DBG"); q.dbg = e ? atoi(e) : 0; }
       const size_t stage = 2 * (size_t)(4 * 4096) + 2 * (size_t)(q.kp >> 5) * 4096;
-      q.nstages = (int)((G_SMEM_BUDGET) / stage);
+      q.nstages = (int)((gemm_smem_budget()) / stage);
       if (q.nstages > G_MAXSTAGES) q.nstages = G_MAXSTAGES;
       NESIE_REQUIRE(q.nstages >= 1, "k too large for shared memory");
       const size_t smem = (size_t)q.nstages * stage + 1024;
-      auto kern = gemm_tma_capped() ? gemm_wgrad_tma_kernel<T_MAXREG> : gemm_wgrad_tma_kernel<96>;
+      const int regs = gemm_tma_regs();
+      auto kern = regs == 64 ? gemm_wgrad_tma_kernel<64> : (regs == 88 ? gemm_wgrad_tma_kernel<88> : gemm_wgrad_tma_kernel<96>);
       NESIE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G_MAX_DYN_SMEM));
       int gx;
       wgrad_plan(r, n, &q.chunk, &q.nchunks, &gx);

@@ -14,6 +14,7 @@ namespace {
 constexpr int G_MAX_DYN_SMEM = 232448 - 1024;
 constexpr int G_SMEM_BUDGET = 224 * 1024;          // stages (+ epilogue staging); + 1 KB alignment slack
 
+constexpr unsigned G_WAIT_BACKOFF_NS = 64;
 constexpr int G_TILE = 128;
 constexpr int G_SLABK = 32;            // fp32 elements per 128-byte swizzle row
 constexpr int G_MAXSTAGES = 4;
@@ -87,7 +88,7 @@ __device__ __forceinline__ void g_mbar_expect_tx(unsigned mbar, unsigned bytes) 
 }
 __device__ __forceinline__ void g_mbar_wait(unsigned mbar, unsigned parity) {
   unsigned ok = 0;
-  while (!ok) {
+  while (true) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -95,6 +96,11 @@ __device__ __forceinline__ void g_mbar_wait(unsigned mbar, unsigned parity) {
         : "=r"(ok)
         : "r"(mbar), "r"(parity)
         : "memory");
+    if (ok) break;
+    // back off: ~20 warps of a CTA poll barriers most of the time, and a warp scheduler that keeps
+    // re-issuing a failing poll starves a co-resident CTA of another kernel (measured: an FPS CTA
+    // sharing the SM ran 2-40x slower without the sleep)
+    __nanosleep(G_WAIT_BACKOFF_NS);
   }
 }
 __device__ __forceinline__ void g_bulk_g2s(unsigned dst, const void *src, unsigned bytes,

@@ -611,9 +611,17 @@ inline bool make_tmap(CUtensorMap *tm, const float *base, long long rows, long l
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-inline bool gemm_tma_capped() {
+// shared memory the TMA kernels may use for stages (+ epilogue staging); NESIE_GEMM_SMEM_KB overrides
+inline size_t gemm_smem_budget() {
+  const char *e = getenv("NESIE_GEMM_SMEM_KB");
+  return e ? (size_t)atoi(e) * 1024 : (size_t)G_SMEM_BUDGET;
+}
+
+// register cap of the build to launch: 64, 88 or 96 (NESIE_GEMM_REGS; default 96)
+inline int gemm_tma_regs() {
   const char *e = getenv("NESIE_GEMM_REGS");
-  return e && atoi(e) <= T_MAXREG;
+  const int r = e ? atoi(e) : 96;
+  return r <= 64 ? 64 : (r <= 88 ? 88 : 96);
 }
 
 inline bool gemm_tma_enabled() {
