@@ -191,24 +191,47 @@ def main():
     host_gt = [tuple(t.pin_memory() for t in pg) for pg in padded]
     dev_pts = [p.to(dev) for p in host_pts]
     dev_gt = [tuple(t.to(dev) for t in pg) for pg in host_gt]
-    # Two input slots, pipelined: while the step of batch t runs on the main stream, a side stream
-    # loads batch t+1 into the other slot and runs its furthest-point-sampling chain (FPS depends
-    # on coordinates only -- the classic input-pipeline overlap; FPS is a serial latency-bound
-    # kernel that leaves most SMs free).  Every buffer is static so both pieces replay as CUDA graphs.
-    num_sa = model.backbone.num_sa
+    # Input pipeline.  The FPS chain depends on coordinates only, so the chain of batch t+1 is computed
+    # while batch t trains (three input slots: one training, one being sampled, one being loaded).
+    # FPS is a serial, latency-bound kernel whose CTAs cannot share an SM with the persistent GEMM
+    # CTAs (registers), so WHERE it runs matters: forked at the start of the step it collides with
+    # the large SA1 / SA2 GEMMs; NESIE_BENCH_FPS_AT=<level> forks it inside the captured step right
+    # after SA level <level> has been issued (default 3 = after the last SA level: it then overlaps
+    # the small-grid middle of the step; measured 8.52 ms per step vs 8.84 at level 1 and 8.8-9.3
+    # beside the step), NESIE_BENCH_FPS_AT=start keeps it on a separate graph launched beside the step.
+    fps_at = os.environ.get("NESIE_BENCH_FPS_AT", "3")
+    fork_level = None if fps_at == "start" else int(fps_at)
+    NSLOT = 3
     slots = []
-    for _ in range(2):
+    for _ in range(NSLOT):
         slots.append(dict(pts=torch.empty_like(dev_pts[0]),
                           gt=tuple(torch.empty_like(t) for t in dev_gt[0]),
                           fps=[torch.zeros((SCENES_PER_GPU, n), dtype=torch.int32, device=dev)
                                for n in model.backbone.num_points],
-                          ev_fps=torch.cuda.Event(), ev_step=torch.cuda.Event()))
+                          ev_fps=torch.cuda.Event(), ev_step=torch.cuda.Event(),
+                          ev_load=torch.cuda.Event()))
     s_loss = torch.zeros((), device=dev)
     side = torch.cuda.Stream()
+    copy_stream = torch.cuda.Stream()
 
-    def step_body(slot):
+    def fps_body(slot):
+        for dst, src in zip(slot["fps"], model.backbone.fps_chain(slot["pts"])):
+            dst.copy_(src)
+
+    def step_body(slot, nxt=None):
+        """One training step on `slot`; with `nxt`, the FPS chain of the next batch is forked onto
+        the side stream after SA level `fork_level` and joined at the end of the step."""
+        cur = torch.cuda.current_stream()
+        hook = None
+        if nxt is not None:
+            def hook(i):
+                if i == fork_level and os.environ.get("NESIE_BENCH_SKIP_FPS") != "1":
+                    side.wait_stream(cur)
+                    with torch.cuda.stream(side):
+                        fps_body(nxt)
         flat_grad.zero_()
-        loss, _ = model.train_step_loss_padded(slot["pts"], *slot["gt"], fps_indices=slot["fps"])
+        loss, _ = model.train_step_loss_padded(slot["pts"], *slot["gt"], fps_indices=slot["fps"],
+                                               after_level=hook)
         loss.backward()
         if world > 1:
             dist.all_reduce(flat_grad)
@@ -216,15 +239,16 @@ def main():
         torch.nn.utils.clip_grad_norm_(params, 10.0)
         opt.step()
         s_loss.copy_(loss.detach())
-
-    def fps_body(slot):
-        for dst, src in zip(slot["fps"], model.backbone.fps_chain(slot["pts"])):
-            dst.copy_(src)
+        if nxt is not None:
+            cur.wait_stream(side)
 
     def load_inputs(slot, pts, gt):
         slot["pts"].copy_(pts, non_blocking=True)
         for d, t in zip(slot["gt"], gt):
             d.copy_(t, non_blocking=True)
+
+    def nxt_of(j):
+        return slots[(j + 1) % NSLOT] if fork_level is not None else None
 
     # warm up eagerly on the side stream (also initialises NCCL), then capture each piece once
     side.wait_stream(torch.cuda.current_stream())
@@ -237,20 +261,26 @@ def main():
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
     mode = "eager"
-    step_fn = [lambda sl=sl: step_body(sl) for sl in slots]
+    step_fn = [lambda j=j: step_body(slots[j], nxt_of(j)) for j in range(NSLOT)]
     fps_fn = [lambda sl=sl: fps_body(sl) for sl in slots]
     graphs = []
     if os.environ.get("NESIE_BENCH_GRAPH", "1") != "0":
         try:
-            for sl in slots:
-                g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            step_g, fps_g = [], []
+            for j, sl in enumerate(slots):
+                g1 = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g1):
-                    step_body(sl)
-                with torch.cuda.graph(g2):
-                    fps_body(sl)
-                graphs += [g1, g2]
-            step_fn = [graphs[0].replay, graphs[2].replay]
-            fps_fn = [graphs[1].replay, graphs[3].replay]
+                    step_body(sl, nxt_of(j))
+                step_g.append(g1)
+                if fork_level is None:
+                    g2 = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g2):
+                        fps_body(sl)
+                    fps_g.append(g2)
+            graphs = step_g + fps_g
+            step_fn = [g.replay for g in step_g]
+            if fps_g:
+                fps_fn = [g.replay for g in fps_g]
             mode = "cuda_graph"
         except Exception as e:  # noqa: BLE001 -- fall back to eager launches
             graphs = []
@@ -262,30 +292,45 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def prefetch(i, src_pts, src_gt):
-        """side stream: batch i -> slot i&1 (inputs + FPS chain), after the slot's last step."""
-        sl = slots[i & 1]
-        with torch.cuda.stream(side):
-            side.wait_event(sl["ev_step"])
+    def load_async(i, src_pts, src_gt):
+        """copy stream: batch i -> slot i % 3, once the slot's previous step has finished."""
+        sl = slots[i % NSLOT]
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(sl["ev_step"])
             load_inputs(sl, src_pts[i % NB], src_gt[i % NB])
-            if os.environ.get("NESIE_BENCH_SKIP_FPS") != "1":  # diagnostic: cost of the co-running FPS
-                fps_fn[i & 1]()
-            sl["ev_fps"].record(side)
+            sl["ev_load"].record(copy_stream)
 
     def run_pipeline(nsteps, src_pts, src_gt, after_step=None):
         main = torch.cuda.current_stream()
         for sl in slots:
             sl["ev_step"].record(main)
-        prefetch(0, src_pts, src_gt)
+        # prologue: batch 0 loaded and sampled, batch 1 loaded
+        load_async(0, src_pts, src_gt)
+        with torch.cuda.stream(side):
+            side.wait_event(slots[0]["ev_load"])
+            fps_fn[0]()
+            slots[0]["ev_fps"].record(side)
+        load_async(1, src_pts, src_gt)
+        main.wait_event(slots[0]["ev_fps"])
         for i in range(nsteps):
-            sl = slots[i & 1]
-            prefetch(i + 1, src_pts, src_gt)       # overlaps this step
-            main.wait_event(sl["ev_fps"])
-            step_fn[i & 1]()
+            sl, nx = slots[i % NSLOT], slots[(i + 1) % NSLOT]
+            load_async(i + 2, src_pts, src_gt)          # overlaps this step
+            main.wait_event(nx["ev_load"])
+            if fork_level is None:
+                # FPS of batch i+1 on its own graph beside the step
+                with torch.cuda.stream(side):
+                    side.wait_event(nx["ev_load"])
+                    side.wait_event(nx["ev_step"])
+                    if os.environ.get("NESIE_BENCH_SKIP_FPS") != "1":
+                        fps_fn[(i + 1) % NSLOT]()
+                    nx["ev_fps"].record(side)
+                main.wait_event(sl["ev_fps"])
+            step_fn[i % NSLOT]()                         # fork mode: samples batch i+1 inside
             sl["ev_step"].record(main)
             if after_step is not None:
                 after_step()
         main.wait_stream(side)
+        main.wait_stream(copy_stream)
 
     def timed(fn):
         barrier()
@@ -413,7 +458,8 @@ def main():
                        "classes": 18, "parallelism": f"dp{world}",
                        "l2": "4 distinct resident batches cycled; per-step activations exceed L2",
                        "launch": mode,
-                       "input_pipeline": "batch t+1 (copy + FPS chain) on a side stream during step t"},
+                       "input_pipeline": ("batch t+2 copied and batch t+1 sampled (FPS chain) during step t; FPS forked "
+                                          + ("beside the step" if fork_level is None else f"inside the captured step after SA level {fork_level}"))},
             "e2e": {"value": e2e_value, "unit": "scenes/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / K},
             "gpu_launches": launches, "roofline": roofline, "clocks": clocks,

@@ -700,7 +700,7 @@ static int gemm_nt_impl(long long r, int n, int k, const float *a, long long lda
       const int regs = gemm_tma_regs();
       auto kern = regs == 64 ? gemm_nt_tma_kernel<64> : (regs == 88 ? gemm_nt_tma_kernel<88> : gemm_nt_tma_kernel<96>);
       NESIE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G_MAX_DYN_SMEM));
-      int grid = num_sms();
+      int grid = gemm_grid_sms();
       if (ntiles_all < grid) grid = ntiles_all;
       kern<<<grid, T_THREADS, smem, (cudaStream_t)stream>>>(tm, q);
       return check_launch("nesie_gemm_nt_3xtf32");
@@ -738,7 +738,7 @@ extern "C" int nesie_gemm_fused_supported(long long r, int n, int k, const float
 extern "C" int nesie_gemm_stats_parts(long long r) {
   if (r <= 0) return 0;
   const long long ntiles = (r + G_TILE - 1) / G_TILE;
-  return 4 * (int)(ntiles < num_sms() ? ntiles : num_sms());
+  return 4 * (int)(ntiles < gemm_grid_sms() ? ntiles : gemm_grid_sms());
 }
 
 extern "C" int nesie_gemm_nt_3xtf32_fused(long long r, int n, int k, const float *a, long long lda,
@@ -758,7 +758,7 @@ static void wgrad_plan(long long r, int n, int *chunk, int *nchunks, int *gx) {
   const int mblocks = (n + 127) / 128;
   *chunk = wgrad_chunk(nslab, mblocks);
   *nchunks = (int)((nslab + *chunk - 1) / *chunk);
-  int g = num_sms() / mblocks;
+  int g = gemm_grid_sms() / mblocks;
   if (g < 1) g = 1;
   if (g > *nchunks) g = *nchunks;
   *gx = g;

@@ -617,6 +617,18 @@ inline size_t gemm_smem_budget() {
   return e ? (size_t)atoi(e) * 1024 : (size_t)G_SMEM_BUDGET;
 }
 
+// CTAs of a persistent GEMM launch: all SMs, or NESIE_GEMM_GRID (e.g. 140 leaves eight SMs to the
+// single-CTA-per-scene FPS kernels of the input pipeline so that they do not force a second wave)
+inline int gemm_grid_sms() {
+  static int g = -1;
+  if (g < 0) {
+    const char *e = getenv("NESIE_GEMM_GRID");
+    g = e ? atoi(e) : num_sms();
+    if (g < 1 || g > num_sms()) g = num_sms();
+  }
+  return g;
+}
+
 // register cap of the build to launch: 64, 88 or 96 (NESIE_GEMM_REGS; default 96)
 inline int gemm_tma_regs() {
   const char *e = getenv("NESIE_GEMM_REGS");

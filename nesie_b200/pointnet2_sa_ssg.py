@@ -106,9 +106,11 @@ class PointNet2SASSG(nn.Module):
                         .transpose(1, 2).contiguous()
         return out
 
-    def forward(self, points, fps_indices=None):
+    def forward(self, points, fps_indices=None, after_level=None):
         """points (B, N, 3 + input_feature_dim) -> dict of lists, as the reference returns.
-        fps_indices: optional precomputed result of fps_chain(points)."""
+        fps_indices: optional precomputed result of fps_chain(points).
+        after_level: optional callable(i) invoked once SA level i has been issued (scheduling hook:
+        bench.py forks the next batch's FPS chain there, away from the large SA1 / SA2 GEMMs)."""
         xyz, features = self._split_point_feats(points)
         batch, num_points = xyz.shape[:2]
         indices = torch.arange(num_points, device=xyz.device, dtype=torch.long) \
@@ -129,6 +131,8 @@ class PointNet2SASSG(nn.Module):
             sa_xyz.append(cur_xyz)
             sa_features.append(cur_features)
             sa_indices.append(torch.gather(sa_indices[-1], 1, cur_indices.long()))
+            if after_level is not None:
+                after_level(i)
 
         fp_xyz, fp_features, fp_indices = [sa_xyz[-1]], [sa_features[-1]], [sa_indices[-1]]
         for i in range(self.num_fp):

@@ -114,9 +114,9 @@ class VoteNetHarness(nn.Module):
         self.max_side = 3.0  # a side lies within 3 m of its proposal point
 
     # ---- hot-path hooks (overridden by the CPU oracle harness) --------------------------------
-    def _backbone(self, points, fps_indices=None):
-        if fps_indices is not None:
-            return self.backbone(points, fps_indices=fps_indices)
+    def _backbone(self, points, fps_indices=None, after_level=None):
+        if fps_indices is not None or after_level is not None:
+            return self.backbone(points, fps_indices=fps_indices, after_level=after_level)
         return self.backbone(points)
 
     def _aggregate(self, xyz, feats):
@@ -127,8 +127,9 @@ class VoteNetHarness(nn.Module):
                                      10.0, self.alpha)
 
     # ---- forward ------------------------------------------------------------------------------
-    def forward(self, points, fps_indices=None):
-        feat = self._backbone(points, fps_indices) if fps_indices is not None else self._backbone(points)
+    def forward(self, points, fps_indices=None, after_level=None):
+        feat = self._backbone(points, fps_indices, after_level) \
+            if (fps_indices is not None or after_level is not None) else self._backbone(points)
         seed_points, seed_feats = feat['fp_xyz'][-1], feat['fp_features'][-1]
         vote_points, vote_feats, _ = self.vote_module(seed_points, seed_feats)
         agg_points, agg_feats, _ = self._aggregate(vote_points, vote_feats)
@@ -229,8 +230,8 @@ class VoteNetHarness(nn.Module):
         losses = self.loss(self.forward(points), gt_boxes, gt_labels)
         return sum(losses.values()), losses
 
-    def train_step_loss_padded(self, points, boxes, labels, valid, fps_indices=None):
-        losses = self.loss_padded(self.forward(points, fps_indices), boxes, labels, valid)
+    def train_step_loss_padded(self, points, boxes, labels, valid, fps_indices=None, after_level=None):
+        losses = self.loss_padded(self.forward(points, fps_indices, after_level), boxes, labels, valid)
         return sum(losses.values()), losses
 
 

@@ -9,7 +9,7 @@ from . import restate
 
 class VoteNetOracle(VoteNetHarness):
 
-    def _backbone(self, points, fps_indices=None):
+    def _backbone(self, points, fps_indices=None, after_level=None):
         return om.backbone_forward(self.backbone, points)
 
     def _aggregate(self, xyz, feats):
