@@ -214,9 +214,21 @@ def main():
     side = torch.cuda.Stream()
     copy_stream = torch.cuda.Stream()
 
+    fps_levels = os.environ.get("NESIE_BENCH_FPS_LEVELS", "all")  # diagnostic: "first" / "rest"
+
     def fps_body(slot):
-        for dst, src in zip(slot["fps"], model.backbone.fps_chain(slot["pts"])):
-            dst.copy_(src)
+        if fps_levels == "all":
+            for dst, src in zip(slot["fps"], model.backbone.fps_chain(slot["pts"])):
+                dst.copy_(src)
+            return
+        # timing diagnostics only (the indices of the skipped levels stay stale)
+        cur = slot["pts"][..., 0:3].contiguous()
+        for i in range(model.backbone.num_sa):
+            if (fps_levels == "first") == (i == 0):
+                slot["fps"][i].copy_(nb.furthest_point_sample(cur, model.backbone.num_points[i]))
+            if i + 1 < model.backbone.num_sa:
+                cur = nb.gather_points(cur.transpose(1, 2).contiguous(), slot["fps"][i]) \
+                    .transpose(1, 2).contiguous()
 
     def step_body(slot, nxt=None):
         """One training step on `slot`; with `nxt`, the FPS chain of the next batch is forked onto

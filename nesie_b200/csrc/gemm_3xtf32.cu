@@ -696,7 +696,7 @@ static int gemm_nt_impl(long long r, int n, int k, const float *a, long long lda
       q.nstages = (int)((gemm_smem_budget() - epi) / stage);
       if (q.nstages < 1) q.nstages = 1;
       if (q.nstages > G_MAXSTAGES) q.nstages = G_MAXSTAGES;
-      const size_t smem = (size_t)q.nstages * stage + epi + 1024;
+      const size_t smem = (size_t)q.nstages * stage + epi + T_CTRL_BYTES;
       const int regs = gemm_tma_regs();
       auto kern = regs == 64 ? gemm_nt_tma_kernel<64> : (regs == 88 ? gemm_nt_tma_kernel<88> : gemm_nt_tma_kernel<96>);
       NESIE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G_MAX_DYN_SMEM));

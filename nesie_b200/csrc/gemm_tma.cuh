@@ -32,6 +32,7 @@ constexpr int T_THREADS = 32 * (T_EPIW + T_XFW + 2);  // + producer warp + MMA w
 // more than co-residency returns, so the uncapped build is the default (NESIE_GEMM_REGS=64 selects
 // the capped one).
 constexpr int T_MAXREG = 64;
+constexpr int T_CTRL_BYTES = 256;  // barriers + TMEM base of the NT kernel, behind its tiles
 constexpr int T_XF0 = T_EPIW, T_PROD = T_EPIW + T_XFW, T_MMA = T_PROD + 1;
 
 __device__ __forceinline__ void g_tma_2d(unsigned dst, const CUtensorMap *tm, int c0, int c1,
@@ -85,18 +86,23 @@ struct GemmTmaParams {
 template <int MAXREG>
 __global__ void __maxnreg__(MAXREG)
 gemm_nt_tma_kernel(const __grid_constant__ CUtensorMap tmA, GemmTmaParams p) {
-  extern __shared__ unsigned char g_smem_dyn[];
-  unsigned char *smem = reinterpret_cast<unsigned char *>(
-      (reinterpret_cast<uintptr_t>(g_smem_dyn) + 1023) & ~(uintptr_t)1023);
-  __shared__ __align__(8) unsigned long long s_tma[G_MAXSTAGES], s_full[G_MAXSTAGES], s_empty[G_MAXSTAGES],
-      s_accf[2], s_acce[2];
-  __shared__ unsigned s_tmem;
-
+  // No static shared memory and no alignment slack: the kernel's 224 KB + 256 B then leave room on
+  // the SM for a small CTA of another kernel (the single-CTA-per-scene FPS launches of the input
+  // pipeline), which otherwise pushes eight GEMM CTAs into a second wave.  The dynamic window of a
+  // kernel without static shared memory starts 1 KB-aligned (checked below).
+  extern __shared__ __align__(1024) unsigned char g_smem_al[];
+  unsigned char *smem = g_smem_al;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int bslab = p.npad * 128;                       // bytes of one B part-slab
   const int stage_bytes = 2 * G_ASLAB + 2 * bslab;      // A raw (= hi), A lo, B hi, B lo
   const int ntiles = (p.R + G_TILE - 1) / G_TILE;
   const unsigned smem_base = g_smem_u32(smem);
+  if (smem_base & 1023u) __trap();
+  unsigned long long *ctrl = reinterpret_cast<unsigned long long *>(
+      smem + (size_t)p.nstages * stage_bytes + (size_t)T_EPIW * 4096);
+  unsigned long long *s_tma = ctrl, *s_full = ctrl + G_MAXSTAGES, *s_empty = ctrl + 2 * G_MAXSTAGES;
+  unsigned long long *s_accf = ctrl + 3 * G_MAXSTAGES, *s_acce = s_accf + 2;
+  unsigned &s_tmem = *reinterpret_cast<unsigned *>(s_acce + 2);
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
