@@ -103,6 +103,27 @@ def test_backbone_votenet_shape(overlap):
     assert got["fp_indices"][-1].dtype == torch.int64
 
 
+def test_backbone_with_precomputed_fps_chain_is_identical():
+    """forward(points, fps_indices=fps_chain(points)) -- the input-pipeline entry bench.py uses --
+    returns exactly what forward(points) returns; the after_level hook fires once per SA level."""
+    torch.manual_seed(3)
+    pts = make_batch(2, 8192, seed0=13)[0].cuda()
+    bb = nb.PointNet2SASSG(in_channels=4, num_points=(512, 256, 128, 64), radius=(0.2, 0.4, 0.8, 1.2),
+                           num_samples=(32, 16, 16, 16)).cuda()
+    bb2 = copy.deepcopy(bb)
+    want = bb(pts)
+    chain = bb2.fps_chain(pts)
+    assert [tuple(c.shape) for c in chain] == [(2, 512), (2, 256), (2, 128), (2, 64)]
+    seen = []
+    got = bb2(pts, fps_indices=chain, after_level=seen.append)
+    assert seen == [0, 1, 2, 3]
+    for k in ("sa_indices", "fp_indices", "sa_xyz"):
+        for a, b in zip(got[k], want[k]):
+            assert torch.equal(a, b), k
+    for a, b in zip(got["fp_features"], want["fp_features"]):
+        assert torch.equal(a, b)
+
+
 def test_state_dict_names_follow_reference_layout():
     bb = nb.PointNet2SASSG(in_channels=4)
     keys = set(bb.state_dict().keys())
