@@ -201,7 +201,11 @@ def main():
     # beside the step), NESIE_BENCH_FPS_AT=start keeps it on a separate graph launched beside the step.
     fps_at = os.environ.get("NESIE_BENCH_FPS_AT", "3")
     fork_level = None if fps_at == "start" else int(fps_at)
-    NSLOT = 3
+    # NESIE_BENCH_FPS_SPLIT=1 (fork mode only): the long first FPS level (128 SMs, 2.1 ms) of batch
+    # t+2 and the short remaining levels (8 SMs, 1.1 ms) of batch t+1 run side by side on two forked
+    # branches, so the FPS window of a step shrinks from 3.3 to 2.1 ms (four input slots).
+    split = fork_level is not None and os.environ.get("NESIE_BENCH_FPS_SPLIT", "1") == "1"
+    NSLOT = 4 if split else 3
     slots = []
     for _ in range(NSLOT):
         slots.append(dict(pts=torch.empty_like(dev_pts[0]),
@@ -212,6 +216,7 @@ def main():
                           ev_load=torch.cuda.Event()))
     s_loss = torch.zeros((), device=dev)
     side = torch.cuda.Stream()
+    side2 = torch.cuda.Stream()
     copy_stream = torch.cuda.Stream()
 
     fps_levels = os.environ.get("NESIE_BENCH_FPS_LEVELS", "all")  # diagnostic: "first" / "rest"
@@ -230,17 +235,32 @@ def main():
                 cur = nb.gather_points(cur.transpose(1, 2).contiguous(), slot["fps"][i]) \
                     .transpose(1, 2).contiguous()
 
-    def step_body(slot, nxt=None):
+    def fps_first(slot):
+        slot["fps"][0].copy_(model.backbone.fps_chain(slot["pts"], stop=1)[0])
+
+    def fps_rest(slot):
+        for dst, src in zip(slot["fps"][1:], model.backbone.fps_chain(slot["pts"], given=slot["fps"][:1])):
+            dst.copy_(src)
+
+    def step_body(slot, nxt=None, nxt2=None):
         """One training step on `slot`; with `nxt`, the FPS chain of the next batch is forked onto
-        the side stream after SA level `fork_level` and joined at the end of the step."""
+        the side stream after SA level `fork_level` and joined at the end of the step (split mode:
+        the remaining levels of `nxt` and the first level of `nxt2` on two branches)."""
         cur = torch.cuda.current_stream()
         hook = None
         if nxt is not None:
             def hook(i):
                 if i == fork_level and os.environ.get("NESIE_BENCH_SKIP_FPS") != "1":
                     side.wait_stream(cur)
-                    with torch.cuda.stream(side):
-                        fps_body(nxt)
+                    if nxt2 is None:
+                        with torch.cuda.stream(side):
+                            fps_body(nxt)
+                    else:
+                        side2.wait_stream(cur)
+                        with torch.cuda.stream(side):
+                            fps_first(nxt2)
+                        with torch.cuda.stream(side2):
+                            fps_rest(nxt)
         flat_grad.zero_()
         loss, _ = model.train_step_loss_padded(slot["pts"], *slot["gt"], fps_indices=slot["fps"],
                                                after_level=hook)
@@ -253,6 +273,8 @@ def main():
         s_loss.copy_(loss.detach())
         if nxt is not None:
             cur.wait_stream(side)
+            if nxt2 is not None:
+                cur.wait_stream(side2)
 
     def load_inputs(slot, pts, gt):
         slot["pts"].copy_(pts, non_blocking=True)
@@ -261,6 +283,9 @@ def main():
 
     def nxt_of(j):
         return slots[(j + 1) % NSLOT] if fork_level is not None else None
+
+    def nxt2_of(j):
+        return slots[(j + 2) % NSLOT] if split else None
 
     # warm up eagerly on the side stream (also initialises NCCL), then capture each piece once
     side.wait_stream(torch.cuda.current_stream())
@@ -273,7 +298,7 @@ def main():
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
     mode = "eager"
-    step_fn = [lambda j=j: step_body(slots[j], nxt_of(j)) for j in range(NSLOT)]
+    step_fn = [lambda j=j: step_body(slots[j], nxt_of(j), nxt2_of(j)) for j in range(NSLOT)]
     fps_fn = [lambda sl=sl: fps_body(sl) for sl in slots]
     graphs = []
     if os.environ.get("NESIE_BENCH_GRAPH", "1") != "0":
@@ -282,7 +307,7 @@ def main():
             for j, sl in enumerate(slots):
                 g1 = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g1):
-                    step_body(sl, nxt_of(j))
+                    step_body(sl, nxt_of(j), nxt2_of(j))
                 step_g.append(g1)
                 if fork_level is None:
                     g2 = torch.cuda.CUDAGraph()
@@ -305,7 +330,7 @@ def main():
         torch.cuda.synchronize()
 
     def load_async(i, src_pts, src_gt):
-        """copy stream: batch i -> slot i % 3, once the slot's previous step has finished."""
+        """copy stream: batch i -> slot i % NSLOT, once the slot's previous step has finished."""
         sl = slots[i % NSLOT]
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(sl["ev_step"])
@@ -323,11 +348,20 @@ def main():
             fps_fn[0]()
             slots[0]["ev_fps"].record(side)
         load_async(1, src_pts, src_gt)
+        if split:   # batch 1 needs its first FPS level before step 0 runs its remaining levels
+            with torch.cuda.stream(side):
+                side.wait_event(slots[1]["ev_load"])
+                fps_first(slots[1])
+                slots[1]["ev_fps"].record(side)
+            load_async(2, src_pts, src_gt)
+            main.wait_event(slots[1]["ev_fps"])
         main.wait_event(slots[0]["ev_fps"])
         for i in range(nsteps):
             sl, nx = slots[i % NSLOT], slots[(i + 1) % NSLOT]
-            load_async(i + 2, src_pts, src_gt)          # overlaps this step
+            load_async(i + NSLOT - 1, src_pts, src_gt)  # overlaps this step
             main.wait_event(nx["ev_load"])
+            if split:
+                main.wait_event(slots[(i + 2) % NSLOT]["ev_load"])
             if fork_level is None:
                 # FPS of batch i+1 on its own graph beside the step
                 with torch.cuda.stream(side):

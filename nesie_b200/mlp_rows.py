@@ -96,11 +96,14 @@ class _LinearStats(Function):
         y, parts = _gemm_fused(x, w, None, None, True)
         ctx.save_for_backward(x, w)
         ctx.mark_non_differentiable(parts)
+        ctx.set_materialize_grads(False)  # no zero-filled gradient tensor for `parts`
         return y, parts
 
     @staticmethod
     def backward(ctx, gy, _gparts):
         x, w = ctx.saved_tensors
+        if gy is None:
+            return None, None
         gy = gy.contiguous()
         gx = gemm_nt(gy, w, transpose_w=True) if ctx.needs_input_grad[0] else None
         gw = wgrad(gy, x) if ctx.needs_input_grad[1] else None
@@ -116,11 +119,14 @@ class _BNReLULinear(Function):
         y, parts = _gemm_fused(y_prev, w, stats[2], stats[3], True)
         ctx.save_for_backward(y_prev, stats, w)
         ctx.mark_non_differentiable(parts)
+        ctx.set_materialize_grads(False)
         return y, parts
 
     @staticmethod
     def backward(ctx, gy, _gparts):
         y_prev, stats, w = ctx.saved_tensors
+        if gy is None:
+            return (None,) * 9
         gy = gy.contiguous()
         R, C = y_prev.shape
         dev = y_prev.device

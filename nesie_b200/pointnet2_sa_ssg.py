@@ -91,17 +91,25 @@ class PointNet2SASSG(nn.Module):
                 idx.record_stream(main)
         return out
 
-    def fps_chain(self, points):
+    def fps_chain(self, points, given=(), stop=None):
         """The SA levels' FPS indices [(B, num_points[i]) int32] for `points`, on the current
         stream.  They depend on coordinates only, so an input pipeline can compute them for batch
-        t+1 while batch t trains and hand them to forward(points, fps_indices=...)."""
+        t+1 while batch t trains and hand them to forward(points, fps_indices=...).
+        given: indices of the first len(given) levels computed earlier (they are only gathered);
+        stop: number of levels to produce in total (default all).  Returns levels len(given)..stop-1,
+        which lets a pipeline run the long first level and the short remaining ones in separate
+        time slots."""
+        stop = self.num_sa if stop is None else stop
         cur = points[..., 0:3].contiguous()
         out = []
         with torch.no_grad():
-            for i in range(self.num_sa):
-                idx = furthest_point_sample(cur, self.num_points[i])
-                out.append(idx)
-                if i + 1 < self.num_sa:
+            for i in range(stop):
+                if i < len(given):
+                    idx = given[i]
+                else:
+                    idx = furthest_point_sample(cur, self.num_points[i])
+                    out.append(idx)
+                if i + 1 < stop:
                     cur = gather_points(cur.transpose(1, 2).contiguous(), idx) \
                         .transpose(1, 2).contiguous()
         return out
