@@ -457,8 +457,13 @@ extern "C" int nesie_fps(int b, int n, int m, const float *xyz, float *temp, int
     // fits the 32-slot register budget (fewer warps = cheaper reductions), else 256.
     int cl = 1;
     if (n > 4096) {
+      // NESIE_FPS_MAX_CLUSTER caps the CTAs per scene: a smaller cluster holds fewer SMs (the
+      // kernel is latency-bound, its CTAs mostly wait), which matters when it runs beside kernels
+      // that want the whole GPU
+      int max_cl = 16;
+      if (const char *e = getenv("NESIE_FPS_MAX_CLUSTER")) max_cl = atoi(e) >= 2 ? atoi(e) : 16;
       cl = 2;
-      while (cl * 2 <= 16 && b * cl * 2 <= num_sms()) cl *= 2;
+      while (cl * 2 <= max_cl && cl * 2 <= 16 && b * cl * 2 <= num_sms()) cl *= 2;
     }
     if (force_cl == 1 || force_cl == 2 || force_cl == 4 || force_cl == 8 || force_cl == 16)
       cl = force_cl;
