@@ -239,6 +239,15 @@ int nesie_sa_fused_forward(int b, int n, int npoints, int nsample, int c_in, int
                            const void *w1_img, const void *w2_img, const void *w3_img,
                            const float *bias, float *out, void *stream);
 
+/* Inverse-distance interpolation into row-major GEMM rows: the grid features of the SidePooling
+ * quality head (models/dense_heads/side_pooling_module.py:183-243, which builds them with a python
+ * index_select loop over the batch).  table_pm is the POINT-major (b, m, c) copy of the seed features,
+ * idx / weight (b, n, 3) the three neighbours and normalised weights of each of the n grid points,
+ * head (b, n, 3) the grid point relative to its box centre.  rows (b*n, ld) receives
+ * [ head | sum_j w_j * table[idx_j, :] | zero padding ], contraction as in three_interpolate. */
+int nesie_interp_rows(int b, int c, int m, int n, const float *table_pm, const int *idx,
+                      const float *weight, const float *head, float *rows, int ld, void *stream);
+
 /* ---------------------------------------------------------------------------------------
  * fp32-accurate row GEMM on tcgen05 (kind::tf32, 3xTF32 split, fp32 TMEM accumulation):
  *   C[r x n] = A[r x k] * B[n x k]^T,  A/C row-major fp32 with leading dimensions lda/ldc.

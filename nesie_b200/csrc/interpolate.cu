@@ -73,6 +73,32 @@ __global__ void __launch_bounds__(NN_THREADS) three_nn_kernel(int n, int m,
 
 constexpr int TI_THREADS = 128;
 
+// Inverse-distance interpolation straight into the row-major GEMM layout (the grid features of the
+// SidePooling quality head, models/dense_heads/side_pooling_module.py:183-243): one warp per target
+// row, lanes over channels of the POINT-major source table, so reads and writes are contiguous.
+//   rows[t, 0:3]   = head[t, :]              (the grid point relative to its box centre)
+//   rows[t, 3+j]   = fma(w2, T[i2, j], fma(w0, T[i0, j], w1 * T[i1, j]))
+//   rows[t, 3+c:]  = 0                        (padding up to the row stride)
+__global__ void __launch_bounds__(256) interp_rows_kernel(
+    int c, int m, int n, int ld, const float *__restrict__ table, const int *__restrict__ idx,
+    const float *__restrict__ weight, const float *__restrict__ head, float *__restrict__ rows) {
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const long long w0i = (long long)blockIdx.x * 8 + (threadIdx.x >> 5), nw = (long long)gridDim.x * 8;
+  table += (size_t)b * m * c;
+  for (long long t = w0i; t < n; t += nw) {
+    const size_t g = (size_t)b * n + t;
+    const int a0 = __ldg(idx + g * 3), a1 = __ldg(idx + g * 3 + 1), a2 = __ldg(idx + g * 3 + 2);
+    const float w0 = __ldg(weight + g * 3), w1 = __ldg(weight + g * 3 + 1), w2 = __ldg(weight + g * 3 + 2);
+    float *o = rows + g * ld;
+    if (lane < 3) o[lane] = __ldg(head + g * 3 + lane);
+    const float *t0 = table + (size_t)a0 * c, *t1 = table + (size_t)a1 * c, *t2 = table + (size_t)a2 * c;
+    for (int j = lane; j < c; j += 32)
+      o[3 + j] = __fmaf_rn(w2, __ldg(t2 + j), __fmaf_rn(w0, __ldg(t0 + j), __fmul_rn(w1, __ldg(t1 + j))));
+    if (lane < ld - 3 - c) o[3 + c + lane] = 0.f;
+  }
+}
+
 // grid: (ceil(n/128), channel slabs, b)
 __global__ void __launch_bounds__(TI_THREADS) three_interpolate_kernel(
     int c, int m, int n, int slab, const float *__restrict__ points,
@@ -169,4 +195,19 @@ extern "C" int nesie_three_interpolate_grad(int b, int c, int n, int m, const fl
   three_interpolate_grad_kernel<<<grid, TI_THREADS, 0, (cudaStream_t)stream>>>(
       c, n, m, slab, grad_out, idx, weight, grad_points);
   return check_launch("nesie_three_interpolate_grad");
+}
+
+extern "C" int nesie_interp_rows(int b, int c, int m, int n, const float *table_pm, const int *idx,
+                                 const float *weight, const float *head, float *rows, int ld,
+                                 void *stream) {
+  NESIE_REQUIRE(b >= 0 && c >= 1 && m >= 1 && n >= 0, "need b >= 0, c >= 1, m >= 1, n >= 0");
+  NESIE_REQUIRE(ld >= 3 + c && ld <= 3 + c + 32, "row stride must be in [3 + c, 3 + c + 32]");
+  if (b == 0 || n == 0) return NESIE_OK;
+  NESIE_REQUIRE(table_pm && idx && weight && head && rows, "null pointer");
+  NESIE_REQUIRE(b <= 65535, "b > 65535");
+  int gx = (n + 7) / 8;
+  if (gx > 8 * num_sms()) gx = 8 * num_sms();
+  interp_rows_kernel<<<dim3(gx, b), 256, 0, (cudaStream_t)stream>>>(c, m, n, ld, table_pm, idx, weight,
+                                                                   head, rows);
+  return check_launch("nesie_interp_rows");
 }

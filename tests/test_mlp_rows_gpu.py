@@ -82,3 +82,32 @@ def test_fused_mlp_with_large_mean_keeps_variance():
 def test_unsupported_shapes_are_reported():
     layers = _layers((7, 64), torch.float32, 3)
     assert not mlp_rows.supported(torch.randn(100, 7, device="cuda"), layers)
+
+
+def test_fused_entry_points_refuse_what_they_cannot_do():
+    """The fused C entry points fail loudly (status + message) instead of falling back."""
+    import ctypes
+    from nesie_b200 import _lib
+    from nesie_b200.linear_rows import _pack
+    R, K, N = 256, 6, 64                       # K not a multiple of 4: no TMA path for the operand
+    a = torch.randn(R, K, device="cuda")
+    w = torch.randn(N, K, device="cuda")
+    out = torch.empty(R, N, device="cuda")
+    img = _pack(w, N, K, K, 1)
+    sc = torch.ones(K, device="cuda")
+    assert not _lib.lib().nesie_gemm_fused_supported(R, N, K, ctypes.c_void_p(a.data_ptr()), K, N)
+    with pytest.raises(RuntimeError, match="not supported"):
+        _lib.call("nesie_gemm_nt_3xtf32_fused", R, N, K, _lib.ptr(a), K, _lib.ptr(img), _lib.ptr(out), N,
+                  _lib.ptr(sc), _lib.ptr(sc), None, _lib.stream())
+    gy = torch.randn(R, N, device="cuda")
+    ns = _lib.lib().nesie_gemm_wgrad_splits(R, N, K)
+    parts = torch.empty(ns, N, K, device="cuda")
+    with pytest.raises(RuntimeError, match="multiple of 4"):
+        _lib.call("nesie_gemm_wgrad_3xtf32_fused", R, N, K, _lib.ptr(gy), N, _lib.ptr(a), K,
+                  _lib.ptr(sc), _lib.ptr(sc), _lib.ptr(parts), ns, _lib.stream())
+    # scale without shift
+    a4 = torch.randn(R, 8, device="cuda")
+    img4 = _pack(torch.randn(N, 8, device="cuda"), N, 8, 8, 1)
+    with pytest.raises(RuntimeError, match="together"):
+        _lib.call("nesie_gemm_nt_3xtf32_fused", R, N, 8, _lib.ptr(a4), 8, _lib.ptr(img4), _lib.ptr(out), N,
+                  _lib.ptr(sc), None, None, _lib.stream())
