@@ -90,7 +90,7 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(clocks)}
 
 
-def cpu_reference_step_rate(steps, warmup, scenes=SCENES_PER_GPU):
+def cpu_reference_step_rate(steps, warmup, scenes=SCENES_PER_GPU, quality_head="conv"):
     """The oracle port of the step on the host cores (fwd + bwd + AdamW), `scenes` per step."""
     from nesie_b200.synthetic import make_batch
     from oracle.votenet_ref import VoteNetOracle
@@ -99,7 +99,7 @@ def cpu_reference_step_rate(steps, warmup, scenes=SCENES_PER_GPU):
     from oracle import cpu as oracle_cpu
     oracle_cpu.set_threads(cores)  # torchrun exports OMP_NUM_THREADS=1
     torch.manual_seed(0)
-    model = VoteNetOracle()
+    model = VoteNetOracle(quality_head=quality_head)
     opt = torch.optim.AdamW(model.parameters(), lr=0.008, weight_decay=0.01)
     pts, gb, gl = make_batch(scenes, N_POINTS, seed0=9000)
     times = []
@@ -122,7 +122,7 @@ def run_reference(args):
     if rank != 0:
         return
     steps, warmup = min(args.steps, 2), min(args.warmup, 1)
-    rate, sec, cores = cpu_reference_step_rate(steps, warmup)
+    rate, sec, cores = cpu_reference_step_rate(steps, warmup, quality_head=args.quality_head)
     sample = (f"{SCENES_PER_GPU} scenes/step ({N_POINTS} pts each), fwd+bwd+AdamW, "
               f"median of {steps} after {warmup} warm-up")
     line = {"impl": "reference", "metric": "train_scenes_per_s", "value": rate, "unit": "scenes/s",
@@ -145,6 +145,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="nesie_b200", choices=["nesie_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quality-head", default="conv", choices=["conv", "side_pooling"],
+                    help="side_pooling adds the reference's SidePooling quality head (SURVEY 8f-1) to the "
+                         "step; the default is the benchmarked pretrain step of BASELINE.json")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -169,7 +172,7 @@ def main():
     W, K = max(args.warmup, 3), args.steps
 
     torch.manual_seed(0)
-    model = VoteNetHarness().to(dev)
+    model = VoteNetHarness(quality_head=args.quality_head).to(dev)
     params = [p for p in model.parameters()]
     # one flat gradient buffer (every p.grad is a view): the DDP exchange of this path is ONE NCCL
     # all-reduce over it per step, issued inside the step so that it is graph-capturable
@@ -501,7 +504,8 @@ def main():
     line = {"metric": "train_scenes_per_s", "value": value, "unit": "scenes/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "scenes_per_gpu": SCENES_PER_GPU, "points": N_POINTS,
+            "config": {"workload": WORKLOAD + ("" if args.quality_head == "conv" else "+side_pooling"),
+                       "scenes_per_gpu": SCENES_PER_GPU, "points": N_POINTS,
                        "classes": 18, "parallelism": f"dp{world}",
                        "l2": "4 distinct resident batches cycled; per-step activations exceed L2",
                        "launch": mode,
@@ -512,7 +516,7 @@ def main():
             "gpu_launches": launches, "roofline": roofline, "clocks": clocks,
             "final_loss": final_loss}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rate, sec, cores = cpu_reference_step_rate(1, 1)
+        rate, sec, cores = cpu_reference_step_rate(1, 1, quality_head=args.quality_head)
         line["cpu_baseline"] = {"value": rate, "unit": "scenes/s", "cores": cores, "kind": "port",
                                 "sample": f"{SCENES_PER_GPU} scenes/step ({N_POINTS} pts each), fwd+bwd+"
                                           f"AdamW, 1 step after 1 warm-up ({sec:.2f} s/step)"}

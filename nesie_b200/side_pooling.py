@@ -114,6 +114,10 @@ class SidePooling(nn.Module):
         self.left_mask = [i // g * g * g + i % g for i in range(g * g)]
         self.right_mask = [i // g * g * g + i % g + g * (g - 1) for i in range(g * g)]
         self.iou_size = num_class if iou_class_depend else 1
+        # device copies of the face masks (not in the state_dict): indexing with the python lists
+        # would upload an index tensor on every call, which CUDA-graph capture forbids
+        self.register_buffer("_left_idx", torch.tensor(self.left_mask), persistent=False)
+        self.register_buffer("_right_idx", torch.tensor(self.right_mask), persistent=False)
 
         before, head = [], []
         for _ in range(6):   # six sides, then the whole box (same creation order as the reference)
@@ -155,8 +159,8 @@ class SidePooling(nn.Module):
         """-> (B, K, 6 * g^2, 3): front, back, top, down, left, right faces of the grid."""
         g = self.grid_size
         faces = [whole_grid[:, :, 0:g * g], whole_grid[:, :, -g * g:], whole_grid[:, :, g - 1::g],
-                 whole_grid[:, :, ::g], whole_grid[:, :, self.left_mask],
-                 whole_grid[:, :, self.right_mask]]
+                 whole_grid[:, :, ::g], whole_grid.index_select(2, self._left_idx),
+                 whole_grid.index_select(2, self._right_idx)]
         return self._to_world(torch.cat(faces, dim=-2), center, heading)
 
     def grid_for_bbox(self, whole_grid, center, heading):

@@ -93,10 +93,14 @@ class VoteNetHarness(nn.Module):
 
     def __init__(self, num_classes=NUM_CLASSES, num_points=(2048, 1024, 512, 256),
                  num_samples=(64, 32, 16, 16), radius=(0.2, 0.4, 0.8, 1.2), num_proposal=256,
-                 alpha=1.0):
+                 alpha=1.0, quality_head='conv'):
+        """quality_head: 'conv' -- iou / side scores from a 1x1 conv on the proposal features (the
+        benchmarked pretrain step); 'side_pooling' -- the reference's SidePooling head
+        (nesie_head.py:134,262-270) on the predicted boxes plus a jittered copy of them."""
         super().__init__()
         self.num_classes = num_classes
         self.alpha = alpha
+        self.quality_head = quality_head
         self.backbone = PointNet2SASSG(in_channels=4, num_points=num_points, radius=radius,
                                        num_samples=num_samples)
         self.vote_module = VoteModule(256, (256, 256))
@@ -108,12 +112,22 @@ class VoteNetHarness(nn.Module):
             ConvModule(128, 128, 1, conv_cfg=dict(type='Conv1d'), norm_cfg=dict(type='BN1d'), bias=True))
         self.conv_cls = nn.Conv1d(128, 2 + num_classes, 1)
         self.conv_reg = nn.Conv1d(128, 6 * (REG_MAX + 1), 1)
-        self.conv_quality = nn.Conv1d(128, num_classes + 6 * num_classes, 1)
+        if quality_head == 'side_pooling':
+            self.grid_conv = self._side_pooling_cls()(num_classes, 1, num_classes, None, num_proposal,
+                                                      'vote', seed_feat_dim=256)
+        else:
+            assert quality_head == 'conv'
+            self.conv_quality = nn.Conv1d(128, num_classes + 6 * num_classes, 1)
         self.register_buffer('bins', torch.linspace(0, 1, REG_MAX + 1))
         self.register_buffer('obj_class_weight', torch.tensor([0.2, 0.8]))
         self.max_side = 3.0  # a side lies within 3 m of its proposal point
 
     # ---- hot-path hooks (overridden by the CPU oracle harness) --------------------------------
+    @staticmethod
+    def _side_pooling_cls():
+        from .side_pooling import SidePooling
+        return SidePooling
+
     def _backbone(self, points, fps_indices=None, after_level=None):
         if fps_indices is not None or after_level is not None:
             return self.backbone(points, fps_indices=fps_indices, after_level=after_level)
@@ -141,12 +155,24 @@ class VoteNetHarness(nn.Module):
         surface_pred = torch.cat([agg_points - dist[..., :3], agg_points + dist[..., 3:]], dim=-1)
         size = surface_pred[..., 3:] - surface_pred[..., :3]
         center = 0.5 * (surface_pred[..., 3:] + surface_pred[..., :3])
-        q = conv1d_rows(self.conv_quality, x).transpose(2, 1).sigmoid()
+        if self.quality_head == 'side_pooling':
+            # boxes + a deterministically jittered copy (the reference jitters randomly,
+            # nesie_head.py:262-263), all detached like there (:264)
+            c2 = torch.cat([center, center + 0.05 * size], dim=1).detach()
+            s2 = torch.cat([size, size * 1.1], dim=1).detach().clamp(min=1e-2)
+            ep = self.grid_conv(c2, s2, torch.zeros_like(c2[..., 0]),
+                                dict(seed_points=seed_points, seed_features=seed_feats,
+                                     bbox_probs=prob))
+            iou_scores = ep['iou_scores'][:, :P].sigmoid()
+            side_scores = ep['side_scores'][..., :P].sigmoid().permute(1, 3, 0, 2)   # (B, P, 6, cls)
+        else:
+            q = conv1d_rows(self.conv_quality, x).transpose(2, 1).sigmoid()
+            iou_scores = q[..., :self.num_classes]
+            side_scores = q[..., self.num_classes:].reshape(B, P, 6, self.num_classes)
         return dict(seed_points=seed_points, vote_points=vote_points, aggregated_points=agg_points,
                     obj_scores=cls[..., :2], sem_scores=cls[..., 2:], surface_pred=surface_pred,
                     bbox_preds=torch.cat([center, size, torch.zeros_like(center[..., :1])], -1),
-                    iou_scores=q[..., :self.num_classes],
-                    side_scores=q[..., self.num_classes:].reshape(B, P, 6, self.num_classes))
+                    iou_scores=iou_scores, side_scores=side_scores)
 
     # ---- targets + losses ---------------------------------------------------------------------
     @staticmethod

@@ -9,6 +9,11 @@ from . import restate
 
 class VoteNetOracle(VoteNetHarness):
 
+    @staticmethod
+    def _side_pooling_cls():
+        from .side_pooling_ref import SidePoolingOracle
+        return SidePoolingOracle
+
     def _backbone(self, points, fps_indices=None, after_level=None):
         return om.backbone_forward(self.backbone, points)
 

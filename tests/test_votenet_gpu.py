@@ -17,11 +17,13 @@ from oracle.votenet_ref import VoteNetOracle
 pytestmark = pytest.mark.gpu
 
 
-def test_train_step_loss_and_grads_match_oracle():
+@pytest.mark.parametrize("quality_head", ["conv", "side_pooling"])
+def test_train_step_loss_and_grads_match_oracle(quality_head):
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
     torch.manual_seed(0)
-    kw = dict(num_points=(1024, 512, 256, 128), num_samples=(32, 16, 16, 16), num_proposal=128)
+    kw = dict(num_points=(1024, 512, 256, 128), num_samples=(32, 16, 16, 16), num_proposal=128,
+              quality_head=quality_head)
     ref = VoteNetOracle(**kw)
     gpu = VoteNetHarness(**kw)
     gpu.load_state_dict(copy.deepcopy(ref.state_dict()))
@@ -40,7 +42,9 @@ def test_train_step_loss_and_grads_match_oracle():
     for name, p in ref.named_parameters():
         if p.grad is None or not (name.startswith("backbone.SA_modules.0") or
                                   name.startswith("backbone.FP_modules.1") or
-                                  name.startswith("vote_aggregation")):
+                                  name.startswith("vote_aggregation") or
+                                  name.startswith("grid_conv.mlps_before.6.second_conv.0") or
+                                  name == "grid_conv.mlps_head.0.0.weight"):  # (its bias sits before a BN: zero gradient)
             continue
         g = pg[name].grad.cpu()
         err = (g - p.grad).norm() / p.grad.norm().clamp_min(1e-12)
