@@ -280,11 +280,14 @@ int nesie_gemm_nt_3xtf32_fused(long long r, int n, int k, const float *a, long l
 int nesie_gemm_debug_profile(long long *out16);
 /* Weight gradient of the same layer, W'[n x k] = sum over the r rows of A[r, n] * B[r, k]
  * (A = dY, B = X), split over the rows: the kernel writes nsplits partial [n x k] blocks
- * (nsplits = nesie_gemm_wgrad_splits(r, n, k)) into `partials` and the caller sums them
- * (deterministic; no atomics).  n <= 256, k <= 512. */
+ * (nsplits = nesie_gemm_wgrad_splits(r, n, k)) into `partials` and the caller sums them, e.g. with
+ * nesie_gemm_sum_partials (deterministic; no atomics).  n <= 256, k <= 512. */
 int nesie_gemm_wgrad_splits(long long r, int n, int k);
 int nesie_gemm_wgrad_3xtf32(long long r, int n, int k, const float *a, long long lda,
                             const float *b, long long ldb, float *partials, int nsplits,
+                            void *stream);
+/* out[count] = sum of the nparts partial blocks (ascending order: deterministic); count % 4 == 0. */
+int nesie_gemm_sum_partials(int nparts, long long count, const float *partials, float *out,
                             void *stream);
 /* ... with B = relu(b * scale + shift) applied on the fly (k floats each; TMA path only). */
 int nesie_gemm_wgrad_3xtf32_fused(long long r, int n, int k, const float *a, long long lda,

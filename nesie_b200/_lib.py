@@ -47,6 +47,7 @@ SIGNATURES = {
     "nesie_gemm_nt_3xtf32_fused": [_ll, _i, _i, _p, _ll, _p, _p, _ll, _p, _p, _p, _p],
     "nesie_gemm_wgrad_3xtf32_fused": [_ll, _i, _i, _p, _ll, _p, _ll, _p, _p, _p, _i, _p],
     "nesie_bn_rows_forward_fused": [_ll, _i, _i, _p, _p, _p, _f, _f, _p, _p, _p, _i, _p, _p, _p, _p, _p],
+    "nesie_gemm_sum_partials": [_i, _ll, _p, _p, _p],
     "nesie_gemm_wgrad_splits": [_ll, _i, _i],
     "nesie_gemm_wgrad_3xtf32": [_ll, _i, _i, _p, _ll, _p, _ll, _p, _i, _p],
     "nesie_bn_rows_workspace_bytes": [_i],

@@ -634,10 +634,63 @@ __global__ void __launch_bounds__(256) pack_b_tf32_kernel(int N, int K, int npad
   }
 }
 
+// out[i] = sum_p partials[p][i]: blockDim = (32 float4 columns, SP_SLICES slices of the partial
+// blocks); every slice adds its blocks in ascending order, the slices are combined in ascending order
+// through shared memory -- a fixed association, so the result is deterministic.
+constexpr int SP_SLICES = 8;
+__global__ void __launch_bounds__(32 * SP_SLICES) sum_partials_kernel(
+    int nparts, long long count4, const float4 *__restrict__ partials, float4 *__restrict__ out) {
+  __shared__ float4 s_acc[SP_SLICES][32];
+  const long long i = (long long)blockIdx.x * 32 + threadIdx.x;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i < count4) {
+    int p = threadIdx.y;
+    for (; p + 3 * SP_SLICES < nparts; p += 4 * SP_SLICES) {  // four independent loads in flight
+      const float4 a = __ldcs(partials + (size_t)p * count4 + i);
+      const float4 b = __ldcs(partials + (size_t)(p + SP_SLICES) * count4 + i);
+      const float4 c = __ldcs(partials + (size_t)(p + 2 * SP_SLICES) * count4 + i);
+      const float4 d = __ldcs(partials + (size_t)(p + 3 * SP_SLICES) * count4 + i);
+      acc.x = (((acc.x + a.x) + b.x) + c.x) + d.x;
+      acc.y = (((acc.y + a.y) + b.y) + c.y) + d.y;
+      acc.z = (((acc.z + a.z) + b.z) + c.z) + d.z;
+      acc.w = (((acc.w + a.w) + b.w) + c.w) + d.w;
+    }
+    for (; p < nparts; p += SP_SLICES) {
+      const float4 a = __ldcs(partials + (size_t)p * count4 + i);
+      acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+    }
+  }
+  s_acc[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && i < count4) {
+#pragma unroll
+    for (int y = 1; y < SP_SLICES; ++y) {
+      const float4 a = s_acc[y][threadIdx.x];
+      acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+    }
+    out[i] = acc;
+  }
+}
+
 }  // namespace
 }  // namespace nesie
 
 using namespace nesie;
+
+// out[count] = sum over the nparts partial blocks written by nesie_gemm_wgrad_3xtf32 (ascending
+// order, round-to-nearest fp32: deterministic).  count must be a multiple of 4, pointers 16-byte aligned.
+extern "C" int nesie_gemm_sum_partials(int nparts, long long count, const float *partials, float *out,
+                                       void *stream) {
+  NESIE_REQUIRE(nparts >= 1 && count >= 0 && (count & 3) == 0, "need nparts >= 1, count % 4 == 0");
+  if (count == 0) return NESIE_OK;
+  NESIE_REQUIRE(partials && out, "null pointer");
+  NESIE_REQUIRE(((reinterpret_cast<uintptr_t>(partials) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+                "pointers must be 16-byte aligned");
+  const long long count4 = count >> 2;
+  sum_partials_kernel<<<(unsigned)((count4 + 31) / 32), dim3(32, SP_SLICES), 0, (cudaStream_t)stream>>>(
+      nparts, count4, reinterpret_cast<const float4 *>(partials), reinterpret_cast<float4 *>(out));
+  return check_launch("nesie_gemm_sum_partials");
+}
 
 extern "C" long long nesie_gemm_b_image_bytes(int n, int k) {
   if (n <= 0 || k <= 0) return 0;

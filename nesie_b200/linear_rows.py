@@ -53,7 +53,20 @@ def wgrad(gy, x):
     with torch.cuda.device(gy.device):
         _lib.call("nesie_gemm_wgrad_3xtf32", R, N, K, _lib.ptr(gy), N, _lib.ptr(x), K,
                   _lib.ptr(parts), ns, _lib.stream())
-    return parts.sum(dim=0)
+    return sum_partials(parts)
+
+
+def sum_partials(parts):
+    """(ns, N, K) partial blocks -> (N, K), added in ascending order (deterministic)."""
+    ns, N, K = parts.shape
+    if ns == 1:
+        return parts[0]
+    if (N * K) % 4:
+        return parts.sum(dim=0)
+    out = torch.empty((N, K), dtype=torch.float32, device=parts.device)
+    with torch.cuda.device(parts.device):
+        _lib.call("nesie_gemm_sum_partials", ns, N * K, _lib.ptr(parts), _lib.ptr(out), _lib.stream())
+    return out
 
 
 def supported(n, k):

@@ -22,7 +22,7 @@ from torch.autograd import Function
 
 from . import _lib
 from . import bn_rows
-from .linear_rows import _pack, gemm_nt, wgrad
+from .linear_rows import _pack, gemm_nt, sum_partials, wgrad
 
 
 def enabled():
@@ -47,6 +47,17 @@ def supported(x, layers):
             return False
         k = n
     return _gemm_supported(x, layers[0][0].shape[0], x.shape[1])
+
+
+def supported_eval(x, wa, wb):
+    """Two chained GEMMs x @ wa.T -> (affine + ReLU prologue) @ wb.T on the fused kernel."""
+    if not (enabled() and x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and
+            x.is_contiguous() and x.shape[0] >= 1 and wa.shape[1] == x.shape[1]):
+        return False
+    for w in (wa, wb):
+        if not (w.shape[0] % 4 == 0 and 4 <= w.shape[0] <= 256 and w.shape[1] % 4 == 0):
+            return False
+    return wb.shape[1] == wa.shape[0] and _gemm_supported(x, wa.shape[0], x.shape[1])
 
 
 def _gemm_fused(x, w, scale, shift, want_stats):
@@ -74,7 +85,7 @@ def _wgrad_fused(gy, x, scale, shift):
     with torch.cuda.device(gy.device):
         _lib.call("nesie_gemm_wgrad_3xtf32_fused", R, N, K, _lib.ptr(gy), N, _lib.ptr(x), K,
                   _lib.ptr(scale), _lib.ptr(shift), _lib.ptr(parts), ns, _lib.stream())
-    return parts.sum(dim=0)
+    return sum_partials(parts)
 
 
 def _bn_stats(y, parts, gamma, beta, rm, rv, eps, momentum):

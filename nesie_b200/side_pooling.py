@@ -79,6 +79,14 @@ def _conv_bn_relu_conv(rows, conv_a, bn, conv_b):
         rm, rv = mlp_rows._bn_buffers(bn)
         y2, _ = mlp_rows._BNReLULinear.apply(y1, parts, bn.weight, bn.bias, rm, rv, bn.eps,
                                              bn.momentum, wb)
+    elif (not bn.training and not torch.is_grad_enabled() and bn.track_running_stats and
+          mlp_rows.supported_eval(rows, wa, wb)):
+        # inference: the BatchNorm is the affine map y * s + t of its running statistics, applied
+        # with the ReLU in the second GEMM's operand prologue (no elementwise sweep at all)
+        scale = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
+        shift = bn.bias - bn.running_mean * scale
+        y1, _ = mlp_rows._gemm_fused(rows, wa, None, None, False)
+        y2, _ = mlp_rows._gemm_fused(y1, wb, scale.contiguous(), shift.contiguous(), False)
     else:
         y1 = linear_rows(rows, wa)
         if bn.training and bn_rows.supported(y1, bn):
