@@ -239,6 +239,21 @@ int nesie_sa_fused_forward(int b, int n, int npoints, int nsample, int c_in, int
                            const void *w1_img, const void *w2_img, const void *w3_img,
                            const float *bias, float *out, void *stream);
 
+/* ---------------------------------------------------------------------------------------
+ * points_in_boxes.  Replace points_in_boxes_launcher / points_in_boxes_batch_launcher
+ *   (batch_size, boxes_num, pts_num, boxes, pts, box_idx_of_points)
+ *   ops/roiaware_pool3d/src/points_in_boxes_cuda.cu:107-155 (kernels :49-105), wrappers :157-200.
+ * boxes (b, nbox, 7) = x, y, z (bottom centre), w, l, h, rz in LiDAR coordinates; pts (b, npts, 3).
+ *   nesie_points_in_boxes       : out (b, npts) int32, index of the first containing box;
+ *                                 caller-initialised to -1 (points_in_boxes.py:29-30)
+ *   nesie_points_in_boxes_batch : out (b, npts, nbox) int32, 1 where inside, 0 elsewhere (every
+ *                                 element is written: unlike the reference no zero fill is needed)
+ * Bit-identical masks to the reference kernels (same float / double mix). */
+int nesie_points_in_boxes(int b, int nbox, int npts, const float *boxes, const float *pts,
+                          int *box_idx_of_points, void *stream);
+int nesie_points_in_boxes_batch(int b, int nbox, int npts, const float *boxes, const float *pts,
+                                int *box_idx_of_points, void *stream);
+
 /* Inverse-distance interpolation into row-major GEMM rows: the grid features of the SidePooling
  * quality head (models/dense_heads/side_pooling_module.py:183-243, which builds them with a python
  * index_select loop over the batch).  table_pm is the POINT-major (b, m, c) copy of the seed features,

@@ -19,6 +19,7 @@ from .pointnet_modules import (ConvModule, PointFPModule, PointSAModule, PointSA
 from .pseudo_label import get_pseudo_labels, lhs_3d_faster_samecls, lhs_3d_faster_samecls_batched
 from .side_loss import bbox2surface, side_uncertainty_loss
 from .side_pooling import MiniPointNet, SidePooling
+from .points_in_boxes import points_in_boxes_batch, points_in_boxes_gpu
 from .teacher_ema import TeacherEMA
 
 __all__ = [
@@ -28,5 +29,5 @@ __all__ = [
     'three_nn', 'PointNet2SASSG', 'ConvModule', 'PointFPModule', 'PointSAModule',
     'PointSAModuleMSG', 'build_sa_module', 'get_pseudo_labels', 'lhs_3d_faster_samecls',
     'lhs_3d_faster_samecls_batched', 'bbox2surface', 'side_uncertainty_loss', 'TeacherEMA',
-    'SidePooling', 'MiniPointNet',
+    'SidePooling', 'MiniPointNet', 'points_in_boxes_gpu', 'points_in_boxes_batch',
 ]

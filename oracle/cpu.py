@@ -144,3 +144,24 @@ def three_interpolate_grad(grad_out, indices, weight, m):
     lib().nesie_oracle_three_interpolate_grad(B, C, n, m, _p(grad_out), _p(indices), _p(weight),
                                               _p(g))
     return g
+
+
+def points_in_boxes_gpu(points, boxes):
+    """(B, M, 3), (B, T, 7) -> (B, M) int32 index of the first containing box, -1 for none
+    (the arithmetic of the reference's CUDA kernel, run on the CPU)."""
+    points, boxes = _f32(points), _f32(boxes)
+    B, M, _ = points.shape
+    T = boxes.shape[1]
+    out = torch.full((B, M), -1, dtype=torch.int32)
+    lib().nesie_oracle_points_in_boxes(B, T, M, _p(boxes), _p(points), _p(out), 0)
+    return out
+
+
+def points_in_boxes_batch(points, boxes):
+    """(B, M, 3), (B, T, 7) -> (B, M, T) int32 membership mask."""
+    points, boxes = _f32(points), _f32(boxes)
+    B, M, _ = points.shape
+    T = boxes.shape[1]
+    out = torch.zeros((B, M, T), dtype=torch.int32)
+    lib().nesie_oracle_points_in_boxes(B, T, M, _p(boxes), _p(points), _p(out), 1)
+    return out

@@ -280,3 +280,45 @@ void nesie_oracle_three_interpolate_grad(int b, int c, int n, int m, const float
       }
     }
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * points_in_boxes / points_in_boxes_batch (reference:
+ * ops/roiaware_pool3d/src/points_in_boxes_cuda.cu:24-105).  One loop iteration per reference CUDA
+ * thread.  The reference mixes float and double exactly as restated here (`h / 2.0`, `M_PI / 2`
+ * and the comparisons are double; the rotated coordinates are float with the contraction nvcc
+ * emits, checked in its sm_100a SASS:  lx = fma(sx, cos, -(sy * sin)),  ly = fma(sy, cos, sx * sin)).
+ * cosf / sinf are libm's here and CUDA's there: they agree for the yaw-0 boxes of this path
+ * (ScanNet), for other yaws a point within rounding of a face may differ.
+ * batch == 0: out (b, npts) int32 = index of the first containing box, caller-initialised to -1;
+ * batch != 0: out (b, npts, nbox) int32 = 1 where the point is inside, caller-initialised to 0. */
+static int pib_check(const float *pt, const float *box) {
+  const float x = pt[0], y = pt[1], z = pt[2];
+  const float cx = box[0], cy = box[1];
+  float cz = box[2];
+  const float w = box[3], l = box[4], h = box[5], rz = box[6];
+  cz = (float)((double)cz + (double)h / 2.0);
+  if ((double)fabsf(z - cz) > (double)h / 2.0) return 0;
+  const float sx = x - cx, sy = y - cy;
+  const float rot = (float)((double)rz + M_PI / 2);
+  const float cosa = cosf(rot), sina = sinf(rot);
+  const float lx = fmaf(sx, cosa, -(sy * sina));
+  const float ly = fmaf(sy, cosa, sx * sina);
+  return ((double)lx > -(double)l / 2.0) & ((double)lx < (double)l / 2.0) &
+         ((double)ly > -(double)w / 2.0) & ((double)ly < (double)w / 2.0);
+}
+
+void nesie_oracle_points_in_boxes(int b, int nbox, int npts, const float *boxes, const float *pts,
+                                  int *out, int batch) {
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int bi = 0; bi < b; ++bi)
+    for (int p = 0; p < npts; ++p) {
+      const float *pt = pts + ((size_t)bi * npts + p) * 3;
+      const float *bx = boxes + (size_t)bi * nbox * 7;
+      for (int k = 0; k < nbox; ++k) {
+        if (pib_check(pt, bx + (size_t)k * 7)) {
+          if (batch) out[((size_t)bi * npts + p) * nbox + k] = 1;
+          else { out[(size_t)bi * npts + p] = k; break; }
+        }
+      }
+    }
+}

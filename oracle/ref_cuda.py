@@ -132,3 +132,43 @@ def three_interpolate_grad(grad_out, indices, weight, m):
     g = torch.zeros((B, C, m), dtype=torch.float32, device=grad_out.device)
     _fn("three_interpolate_grad")(B, C, n, m, _p(grad_out), _p(indices), _p(weight), _p(g), _s())
     return g
+
+
+# ---- points_in_boxes (roiaware_pool3d/src/points_in_boxes_cuda.cu), library built by `make ref_pib`
+PIB_LIB_PATH = os.path.join(_HERE, "_ref", "libnesie_ref_pib.so")
+_pib = None
+
+
+def pib_available():
+    return os.path.exists(PIB_LIB_PATH) and torch.cuda.is_available()
+
+
+def _pib_fn(name):
+    global _pib
+    if _pib is None:
+        _pib = ctypes.CDLL(PIB_LIB_PATH)      # resolves libtorch through its rpath
+    f = getattr(_pib, name)
+    f.restype = None
+    return f
+
+
+def points_in_boxes_gpu(points, boxes):
+    """Reference launcher (default stream): (B, M, 3), (B, T, 7) -> (B, M) int32, -1 = none."""
+    B, M, _ = points.shape
+    out = torch.full((B, M), -1, dtype=torch.int32, device=points.device)
+    torch.cuda.synchronize()
+    _pib_fn("_Z24points_in_boxes_launcheriiiPKfS0_Pi")(B, boxes.shape[1], M, _p(boxes.contiguous()),
+                                                      _p(points.contiguous()), _p(out))
+    torch.cuda.synchronize()
+    return out
+
+
+def points_in_boxes_batch(points, boxes):
+    B, M, _ = points.shape
+    T = boxes.shape[1]
+    out = torch.zeros((B, M, T), dtype=torch.int32, device=points.device)
+    torch.cuda.synchronize()
+    _pib_fn("_Z30points_in_boxes_batch_launcheriiiPKfS0_Pi")(B, T, M, _p(boxes.contiguous()),
+                                                            _p(points.contiguous()), _p(out))
+    torch.cuda.synchronize()
+    return out
