@@ -14,7 +14,8 @@ namespace {
 constexpr int G_MAX_DYN_SMEM = 232448 - 1024;
 constexpr int G_SMEM_BUDGET = 224 * 1024;          // stages (+ epilogue staging); + 1 KB alignment slack
 
-constexpr unsigned G_WAIT_BACKOFF_NS = 64;
+// back-off between failed barrier polls (ns); NESIE_GEMM_BACKOFF_NS overrides it at the first launch
+__device__ unsigned g_wait_backoff_ns = 64;
 constexpr int G_TILE = 128;
 constexpr int G_SLABK = 32;            // fp32 elements per 128-byte swizzle row
 constexpr int G_MAXSTAGES = 4;
@@ -100,7 +101,7 @@ __device__ __forceinline__ void g_mbar_wait(unsigned mbar, unsigned parity) {
     // back off: ~20 warps of a CTA poll barriers most of the time, and a warp scheduler that keeps
     // re-issuing a failing poll starves a co-resident CTA of another kernel (measured: an FPS CTA
     // sharing the SM ran 2-40x slower without the sleep)
-    __nanosleep(G_WAIT_BACKOFF_NS);
+    if (const unsigned ns = g_wait_backoff_ns) __nanosleep(ns);
   }
 }
 __device__ __forceinline__ void g_bulk_g2s(unsigned dst, const void *src, unsigned bytes,

@@ -642,7 +642,18 @@ inline int gemm_tma_regs() {
   return r <= 64 ? 64 : (r <= 88 ? 88 : 96);
 }
 
+inline void gemm_apply_env_once() {
+  static bool done = false;
+  if (done) return;
+  done = true;
+  if (const char *e = getenv("NESIE_GEMM_BACKOFF_NS")) {
+    const unsigned v = (unsigned)atoi(e);
+    cudaMemcpyToSymbol(g_wait_backoff_ns, &v, sizeof(v));
+  }
+}
+
 inline bool gemm_tma_enabled() {
+  gemm_apply_env_once();
   const char *e = getenv("NESIE_GEMM_PATH");
   return !(e && e[0] == 'r');  // NESIE_GEMM_PATH=reg selects the register-staged loaders
 }
