@@ -35,9 +35,9 @@ SCENES_PER_GPU = 8
 N_POINTS = 40000
 WORKLOAD = "votenet_pretrain_fwd_bwd_adamw_b8_per_gpu_40kpts_18cls"
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the roofline kernel at the shape timed
-# below, from the ncu --set full capture summarised in profiles/r01_ncu_notes.md (268.5 MB read +
-# 480.0 MB written; 57 MB of the 537 MB output were still in L2 when the kernel ended)
-GEMM_DRAM_TRAFFIC = 748.6e6
+# below, from the ncu --set full capture summarised in profiles/r01_ncu_notes.md (268.6 MB read +
+# 481.3 MB written; 56 MB of the 537 MB output were still in L2 when the kernel ended)
+GEMM_DRAM_TRAFFIC = 749.8e6
 
 
 def peaks():
