@@ -254,6 +254,18 @@ int nesie_points_in_boxes(int b, int nbox, int npts, const float *boxes, const f
 int nesie_points_in_boxes_batch(int b, int nbox, int npts, const float *boxes, const float *pts,
                                 int *box_idx_of_points, void *stream);
 
+/* Max over groups of k consecutive rows of x (groups*k, c) + bias (nullable), the pooling steps of the
+ * SidePooling MiniPointNets (models/dense_heads/side_pooling_module.py:360-370):
+ *   concat == 0: out (groups, c) = group maxima (torch.max(feature, dim=-1).values)
+ *   concat == 1: out (groups*k, 2c) = [ maxima broadcast to the group's rows | x + bias ]
+ *                (torch.cat([feature_global.expand(..), feature], dim=1))
+ * arg (groups, c) u8 = first maximising row.  _backward writes d_x (groups*k, c) from d_out of the
+ * forward's output shape; the maximum's gradient goes to row arg (as torch.max(dim) routes it). */
+int nesie_group_max_rows_forward(long long groups, int k, int c, const float *x, const float *bias,
+                                 float *out, unsigned char *arg, int concat, void *stream);
+int nesie_group_max_rows_backward(long long groups, int k, int c, const float *d_out,
+                                  const unsigned char *arg, float *d_x, int concat, void *stream);
+
 /* Inverse-distance interpolation into row-major GEMM rows: the grid features of the SidePooling
  * quality head (models/dense_heads/side_pooling_module.py:183-243, which builds them with a python
  * index_select loop over the batch).  table_pm is the POINT-major (b, m, c) copy of the seed features,

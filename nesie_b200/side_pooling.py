@@ -25,6 +25,7 @@ import torch.nn.functional as F
 
 from . import _lib
 from . import bn_rows
+from . import group_max
 from . import mlp_rows
 from .interpolate import three_nn
 from .linear_rows import linear_rows
@@ -68,8 +69,9 @@ def _pad_cols(x, mult=4):
     return F.pad(x, (0, pad)) if pad else x
 
 
-def _conv_bn_relu_conv(rows, conv_a, bn, conv_b):
-    """rows (R, Ka) -> conv_b(relu(bn(conv_a(rows)))) as (R, Nb); conv_a has no bias."""
+def _conv_bn_relu_conv(rows, conv_a, bn, conv_b, add_bias=True):
+    """rows (R, Ka) -> conv_b(relu(bn(conv_a(rows)))) as (R, Nb); conv_a has no bias.
+    add_bias=False leaves conv_b's bias to the caller (it is folded into the group-max kernel)."""
     wa = conv_a.weight.flatten(1)
     if rows.shape[1] != wa.shape[1]:           # zero-padded input columns
         wa = F.pad(wa, (0, rows.shape[1] - wa.shape[1]))
@@ -97,7 +99,7 @@ def _conv_bn_relu_conv(rows, conv_a, bn, conv_b):
             a = F.relu(F.batch_norm(y1, bn.running_mean, bn.running_var, bn.weight, bn.bias,
                                     bn.training, bn.momentum, bn.eps))
         y2 = linear_rows(a, wb)
-    return y2 + conv_b.bias if conv_b.bias is not None else y2
+    return y2 + conv_b.bias if (add_bias and conv_b.bias is not None) else y2
 
 
 class SidePooling(nn.Module):
@@ -205,13 +207,13 @@ class SidePooling(nn.Module):
 
     def _mini_pointnet(self, mpn, rows, G):
         """rows (R, ld) with every G consecutive rows one box -> (R / G, feature_dim)."""
-        feat = _conv_bn_relu_conv(rows, mpn.first_conv[0], mpn.first_conv[1], mpn.first_conv[3])
-        n = feat.shape[1]
-        grp = feat.view(-1, G, n)
-        glob = grp.amax(dim=1, keepdim=True).expand(-1, G, -1)
-        feat = torch.cat([glob, grp], dim=2).reshape(-1, 2 * n)
-        feat = _conv_bn_relu_conv(feat, mpn.second_conv[0], mpn.second_conv[1], mpn.second_conv[3])
-        return feat.view(-1, G, feat.shape[1]).amax(dim=1)
+        feat = _conv_bn_relu_conv(rows, mpn.first_conv[0], mpn.first_conv[1], mpn.first_conv[3],
+                                  add_bias=False)
+        # [max over the box's grid points, broadcast | feature] with the conv bias folded in
+        feat = group_max.group_max_concat_rows(feat, mpn.first_conv[3].bias, G)
+        feat = _conv_bn_relu_conv(feat, mpn.second_conv[0], mpn.second_conv[1], mpn.second_conv[3],
+                                  add_bias=False)
+        return group_max.group_max_rows(feat, mpn.second_conv[3].bias, G)
 
     def _head(self, seq, x):
         """Conv1d / BatchNorm1d / ReLU stack on x (B, C, K) -> (B, C_out, K), as row GEMMs."""

@@ -107,3 +107,23 @@ def test_refuses_cpu_tensors():
     boxes, ep = _inputs(1, 8, 20, 5, 1)
     with pytest.raises((RuntimeError, AssertionError)):
         mod(*boxes, ep)
+
+
+@pytest.mark.parametrize("k,concat", [(16, False), (16, True), (64, True), (5, False)])
+def test_group_max_rows_matches_torch(k, concat):
+    from nesie_b200.group_max import group_max_concat_rows, group_max_rows
+    torch.manual_seed(k)
+    groups, C = 300, 128
+    x = torch.randn(groups * k, C, device="cuda", requires_grad=True)
+    b = torch.randn(C, device="cuda", requires_grad=True)
+    xr, br = x.detach().clone().requires_grad_(True), b.detach().clone().requires_grad_(True)
+    f = (xr + br).view(groups, k, C)
+    gmax = f.max(dim=1).values
+    want = torch.cat([gmax.unsqueeze(1).expand(-1, k, -1), f], dim=2).reshape(groups * k, 2 * C) if concat else gmax
+    got = (group_max_concat_rows if concat else group_max_rows)(x, b, k)
+    assert torch.equal(got, want)
+    g = torch.randn_like(want)
+    got.backward(g)
+    want.backward(g)
+    assert torch.allclose(x.grad, xr.grad, rtol=1e-5, atol=2e-5)   # sum over k rows: order differs
+    assert torch.allclose(b.grad, br.grad, rtol=1e-4, atol=1e-4)
