@@ -9,6 +9,36 @@ from torch.autograd import Function
 from . import _lib
 
 
+_deferred = None   # list of counters while inside defer_batch_counters()
+
+
+class defer_batch_counters:
+    """Inside this context the `num_batches_tracked += 1` of every BatchNorm evaluated by this repo's
+    row kernels is collected and applied as ONE multi-tensor launch on exit (23 one-element kernels
+    per training step otherwise); the counters end up exactly as nn.BatchNorm leaves them."""
+
+    def __enter__(self):
+        global _deferred
+        self._outer = _deferred
+        _deferred = []
+        return self
+
+    def __exit__(self, *exc):
+        global _deferred
+        pending, _deferred = _deferred, self._outer
+        if pending:
+            torch._foreach_add_(pending, 1)
+        return False
+
+
+def count_batch(bn):
+    """bn.num_batches_tracked += 1 (deferred inside defer_batch_counters())."""
+    if _deferred is not None:
+        _deferred.append(bn.num_batches_tracked)
+    else:
+        bn.num_batches_tracked.add_(1)
+
+
 def supported(y, bn, k=0):
     R, C = y.shape
     return (y.is_cuda and y.dtype == torch.float32 and bn.training and bn.affine and
@@ -72,7 +102,7 @@ def bn_relu_rows(y, bn, k=0, col_partials=None):
     max-pools every k consecutive rows -> (R/k, C).  Updates bn's running statistics.
     col_partials: optional (nparts, 2, C) column sums of y and y^2 from the producing GEMM."""
     if bn.track_running_stats:
-        bn.num_batches_tracked.add_(1)
+        count_batch(bn)
         rm, rv = bn.running_mean, bn.running_var
     else:
         rm = rv = None

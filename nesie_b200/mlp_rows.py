@@ -157,7 +157,7 @@ class _BNReLULinear(Function):
 
 def _bn_buffers(bn):
     if bn.track_running_stats:
-        bn.num_batches_tracked.add_(1)
+        bn_rows.count_batch(bn)
         return bn.running_mean, bn.running_var
     return None, None
 

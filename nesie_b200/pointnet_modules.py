@@ -210,7 +210,7 @@ class BasePointSAModule(nn.Module):
                     return x.view(B, M, -1).transpose(1, 2)
                 continue
             if bn.training and bn.track_running_stats:
-                bn.num_batches_tracked.add_(1)
+                bn_rows.count_batch(bn)
             x = F.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias,
                              bn.training or not bn.track_running_stats, bn.momentum, bn.eps)
             x = F.relu(x, inplace=True)
@@ -335,7 +335,7 @@ class PointFPModule(nn.Module):
                 x = bn_rows.bn_relu_rows(x, bn)
                 continue
             if bn.training and bn.track_running_stats:
-                bn.num_batches_tracked.add_(1)
+                bn_rows.count_batch(bn)
             x = F.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias,
                              bn.training or not bn.track_running_stats, bn.momentum, bn.eps)
             x = F.relu(x, inplace=True)

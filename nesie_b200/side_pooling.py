@@ -95,7 +95,7 @@ def _conv_bn_relu_conv(rows, conv_a, bn, conv_b, add_bias=True):
             a = bn_rows.bn_relu_rows(y1, bn)
         else:
             if bn.training and bn.track_running_stats:
-                bn.num_batches_tracked.add_(1)
+                bn_rows.count_batch(bn)
             a = F.relu(F.batch_norm(y1, bn.running_mean, bn.running_var, bn.weight, bn.bias,
                                     bn.training, bn.momentum, bn.eps))
         y2 = linear_rows(a, wb)
@@ -238,7 +238,7 @@ class SidePooling(nn.Module):
                     r = bn_rows.bn_relu_rows(r, m)
                 else:
                     if m.training and m.track_running_stats:
-                        m.num_batches_tracked.add_(1)
+                        bn_rows.count_batch(m)
                     r = F.batch_norm(r, m.running_mean, m.running_var, m.weight, m.bias, m.training,
                                      m.momentum, m.eps)
                     if relu:

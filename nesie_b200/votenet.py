@@ -60,7 +60,7 @@ def conv1d_rows(seq, x):
                 r = bn_rows.bn_relu_rows(r, bn)
                 continue
             if bn.training and bn.track_running_stats:
-                bn.num_batches_tracked.add_(1)
+                bn_rows.count_batch(bn)
             r = F.batch_norm(r, bn.running_mean, bn.running_var, bn.weight, bn.bias,
                              bn.training or not bn.track_running_stats, bn.momentum, bn.eps)
             r = F.relu(r, inplace=True)
@@ -142,6 +142,10 @@ class VoteNetHarness(nn.Module):
 
     # ---- forward ------------------------------------------------------------------------------
     def forward(self, points, fps_indices=None, after_level=None):
+        with bn_rows.defer_batch_counters():
+            return self._forward(points, fps_indices, after_level)
+
+    def _forward(self, points, fps_indices=None, after_level=None):
         feat = self._backbone(points, fps_indices, after_level) \
             if (fps_indices is not None or after_level is not None) else self._backbone(points)
         seed_points, seed_feats = feat['fp_xyz'][-1], feat['fp_features'][-1]
