@@ -51,3 +51,14 @@ def test_wgrad_matches_float64(R, N, K):
     got = wgrad(gy, x)
     err = ((got.double() - want).abs().max() / want.abs().max()).item()
     assert err < 2e-5, err  # weight gradient: in-TMEM accumulation truncates (see gemm_3xtf32.cu)
+
+
+@pytest.mark.parametrize("ns,N,K", [(148, 64, 64), (1, 128, 132), (37, 256, 260), (5, 4, 4)])
+def test_sum_partials_is_deterministic_and_exact_enough(ns, N, K):
+    from nesie_b200.linear_rows import sum_partials
+    torch.manual_seed(ns)
+    parts = torch.randn(ns, N, K, device="cuda")
+    got = sum_partials(parts)
+    assert torch.equal(got, sum_partials(parts))                       # fixed association
+    want = parts.double().sum(0)
+    assert ((got.double() - want).abs().max() / want.abs().max()).item() < 2e-6

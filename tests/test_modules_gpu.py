@@ -114,6 +114,12 @@ def test_backbone_with_precomputed_fps_chain_is_identical():
     want = bb(pts)
     chain = bb2.fps_chain(pts)
     assert [tuple(c.shape) for c in chain] == [(2, 512), (2, 256), (2, 128), (2, 64)]
+    # the chain in two pieces (first level now, the rest later) is the same chain
+    first = bb2.fps_chain(pts, stop=1)
+    rest = bb2.fps_chain(pts, given=first)
+    assert len(first) == 1 and len(rest) == 3
+    for a, b in zip(first + rest, chain):
+        assert torch.equal(a, b)
     seen = []
     got = bb2(pts, fps_indices=chain, after_level=seen.append)
     assert seen == [0, 1, 2, 3]
