@@ -146,11 +146,6 @@ __device__ __forceinline__ void slot_rq(const FpsParams &pr, int g, int s, int &
 // Dynamic smem: 3*nslots*blockDim floats (a copy of the CTA's coordinates, read by candidate
 // lanes) followed, in cluster mode, by 2 * CL * MAX_WARPS_CL candidate slots.
 // ------------------------------------------------------------------------------------------
-// Up to this many points per thread the candidate's coordinates are picked from the registers with a
-// select chain instead of a shared-memory copy: the small single-CTA launches then need < 1 KB of
-// shared memory and can share an SM with a CTA of another kernel (see bench.py's input pipeline).
-constexpr int FPS_SELECT_PPT = 8;
-
 template <int CL, int PPT, int MAXT>
 __global__ void __launch_bounds__(MAXT) fps_reg_kernel(FpsParams pr,
                                                        const float *__restrict__ xyz,
@@ -170,8 +165,7 @@ __global__ void __launch_bounds__(MAXT) fps_reg_kernel(FpsParams pr,
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float *s_pts = reinterpret_cast<float *>(smem_raw);  // [3][nslots][NT]
-  Cand *s_cl = reinterpret_cast<Cand *>(
-      smem_raw + (PPT > FPS_SELECT_PPT ? (((size_t)3 * nslots * NT * 4 + 15) & ~(size_t)15) : 0));
+  Cand *s_cl = reinterpret_cast<Cand *>(smem_raw + (((size_t)3 * nslots * NT * 4 + 15) & ~(size_t)15));
   __shared__ Cand s_wk[2][32];                         // single-CTA mode only
   __shared__ __align__(8) unsigned long long s_mbar[2];
 
@@ -189,11 +183,9 @@ __global__ void __launch_bounds__(MAXT) fps_reg_kernel(FpsParams pr,
         z = xyz[k * 3 + 2];
         d = temp ? temp[k] : 1e10f;  // furthest_point_sample.py:30
       }
-      if constexpr (PPT > FPS_SELECT_PPT) {
-        s_pts[(0 * nslots + s) * NT + tid] = x;
-        s_pts[(1 * nslots + s) * NT + tid] = y;
-        s_pts[(2 * nslots + s) * NT + tid] = z;
-      }
+      s_pts[(0 * nslots + s) * NT + tid] = x;
+      s_pts[(1 * nslots + s) * NT + tid] = y;
+      s_pts[(2 * nslots + s) * NT + tid] = z;
     }
     px[s] = x; py[s] = y; pz[s] = z; md[s] = d;
   }
@@ -234,17 +226,9 @@ __global__ void __launch_bounds__(MAXT) fps_reg_kernel(FpsParams pr,
     const float best = odd ? b1 : b0;
     const int bslot = odd ? s1 : s0;
     // candidate coordinates (issued before the reductions so the LDS latency overlaps them)
-    float bx, by, bz;
-    if constexpr (PPT > FPS_SELECT_PPT) {
-      bx = s_pts[(0 * nslots + bslot) * NT + tid];
-      by = s_pts[(1 * nslots + bslot) * NT + tid];
-      bz = s_pts[(2 * nslots + bslot) * NT + tid];
-    } else {
-      bx = px[0]; by = py[0]; bz = pz[0];
-#pragma unroll
-      for (int s = 1; s < PPT; ++s)
-        if (bslot == s) { bx = px[s]; by = py[s]; bz = pz[s]; }
-    }
+    const float bx = s_pts[(0 * nslots + bslot) * NT + tid];
+    const float by = s_pts[(1 * nslots + bslot) * NT + tid];
+    const float bz = s_pts[(2 * nslots + bslot) * NT + tid];
     unsigned kd = 0u, kp = 0xffffffffu;
     if (best >= 0.f) {
       int r, q;
@@ -407,9 +391,7 @@ int launch_reg(int CL, int NT, int b, FpsParams pr, const float *xyz, float *tem
     case 16: fn = pick_ppt<16>(pr.nslots); break;
   }
   if (!fn) return NESIE_ERR_UNSUPPORTED;
-  // the kernel instantiation holds ceil(nslots / 4) * 4 points per thread (pick_ppt)
-  const bool select = ((pr.nslots + 3) & ~3) <= FPS_SELECT_PPT;
-  size_t smem = select ? 0 : ((((size_t)3 * pr.nslots * NT * sizeof(float)) + 15) & ~(size_t)15);
+  size_t smem = (((size_t)3 * pr.nslots * NT * sizeof(float)) + 15) & ~(size_t)15;
   if (CL > 1) smem += (size_t)2 * CL * MAX_WARPS_CL * sizeof(Cand);
   if (smem > 32 * 1024)  // static smem counts against the 48 KB default too
     NESIE_CUDA(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
