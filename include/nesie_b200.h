@@ -351,6 +351,32 @@ int nesie_bn_relu_rows_backward(long long r, int c, int k, const float *y, const
                                 const unsigned char *arg, const float *stats, float *d_y,
                                 float *d_gamma, float *d_beta, void *workspace, void *stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Target assignment of the train step.
+ *
+ * nesie_vote_targets: vote part of NesieHead.get_targets_single
+ *   (models/dense_heads/nesie_head.py:618-654) = DepthInstance3DBoxes.points_in_boxes
+ *   (core/bbox/structures/depth_box3d.py:251-277 -> points_in_boxes_batch_launcher,
+ *   ops/roiaware_pool3d/src/points_in_boxes_cuda.cu:128-155) + the per-box python loop.
+ *   pts (b, n, pts_stride >= 3) depth frame; boxes (b, g, 7) depth frame, bottom centre, of which
+ *   the first nvalid[b] (nullable: all g) are real; idx (b, rows) int64 (nullable: rows == n, every
+ *   point) selects the points to evaluate (the vote loss only reads the seeds).  Writes
+ *   vote_targets (b, rows, 9) = three (gravity centre - point) slots and vote_mask (b, rows) int64.
+ * nesie_chamfer_assign: the argmins of chamfer_distance (models/losses/chamfer_distance.py:49-56),
+ *   squared-L2 criterion: idx1 (b, n) = nearest of the first nvalid[b] dst points for every src
+ *   point, idx2 (b, m) = nearest src point for every dst point (either may be NULL).
+ * nesie_sort_vertices: replaces sort_vertices_wrapper(b, n, m, vertices, mask, num_valid, idx)
+ *   (ops/rotated_iou/cuda_op/sort_vert_kernel.cu:136-139, kernel :42-134): vertices (b, n, 24, 2)
+ *   normalised around their mean, mask (b, n, 24) bool, num_valid (b, n) int32 -> idx (b, n, 9).
+ *   Runs on `stream` (the reference launches on the legacy default stream). */
+int nesie_vote_targets(int b, int n, int g, int rows, const float *pts, int pts_stride,
+                       const float *boxes, const int *nvalid, const long long *idx,
+                       float *vote_targets, long long *vote_mask, void *stream);
+int nesie_chamfer_assign(int b, int n, int m, const float *src, const float *dst,
+                         const int *nvalid, long long *idx1, long long *idx2, void *stream);
+int nesie_sort_vertices(int b, int n, int m, const float *vertices, const unsigned char *mask,
+                        const int *num_valid, int *idx, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

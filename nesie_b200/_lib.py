@@ -59,6 +59,9 @@ SIGNATURES = {
     "nesie_bn_relu_rows_backward": [_ll, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     "nesie_sa_fused_supported": [_i, _i, _i, _i, _i],
     "nesie_pack_features_bf16": [_i, _i, _i, _p, _p, _p],
+    "nesie_vote_targets": [_i, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p],
+    "nesie_chamfer_assign": [_i, _i, _i, _p, _p, _p, _p, _p, _p],
+    "nesie_sort_vertices": [_i, _i, _i, _p, _p, _p, _p, _p],
     "nesie_sa_fused_forward": [_i] * 8 + [_p, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p],
 }
 

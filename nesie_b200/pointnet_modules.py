@@ -44,8 +44,10 @@ class ConvModule(nn.Module):
 
     def __init__(self, in_channels, out_channels, kernel_size=1, stride=1,
                  conv_cfg=dict(type='Conv2d'), norm_cfg=dict(type='BN2d'),
-                 act_cfg=dict(type='ReLU'), bias='auto'):
+                 act_cfg=dict(type='ReLU'), bias='auto', padding=0, inplace=True):
         super().__init__()
+        assert padding == 0, "the hot path only has 1x1 convolutions"
+
         self.with_norm = norm_cfg is not None
         self.with_activation = act_cfg is not None
         if bias == 'auto':

@@ -165,3 +165,16 @@ def points_in_boxes_batch(points, boxes):
     out = torch.zeros((B, M, T), dtype=torch.int32)
     lib().nesie_oracle_points_in_boxes(B, T, M, _p(boxes), _p(points), _p(out), 1)
     return out
+
+
+def sort_vertices(vertices, mask, num_valid):
+    """ops/rotated_iou/cuda_op (sort_vertices_forward): vertices (B, N, 24, 2) normalised around
+    their mean, mask (B, N, 24) bool, num_valid (B, N) int32 -> (B, N, 9) int32 anticlockwise
+    vertex order, first index repeated, padded with an invalid intersection slot."""
+    v = _f32(vertices)
+    mk = mask.detach().cpu().contiguous().to(torch.uint8)
+    nv = _i32(num_valid)
+    B, N, M, _ = v.shape
+    idx = torch.zeros((B, N, 9), dtype=torch.int32)
+    lib().nesie_oracle_sort_vertices(B, N, M, _p(v), _p(mk), _p(nv), _p(idx))
+    return idx

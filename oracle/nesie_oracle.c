@@ -322,3 +322,72 @@ void nesie_oracle_points_in_boxes(int b, int nbox, int npts, const float *boxes,
       }
     }
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * sort_vertices (reference: ops/rotated_iou/cuda_op/sort_vert_kernel.cu:16-134).
+ * One loop iteration per reference CUDA thread (= one polygon).  `EPSILON` is the double literal
+ * 1e-8 there, so the comparisons against it are double; n = x*x + y*y contracts to
+ * fma(x, x, y*y) in float, then `+ EPSILON` in double, rounded back to float.  The reference's
+ * comparator has no return statement when one of the two y's is exactly 0 (or NaN); nvcc's code
+ * for that path returns false (checked in the sm_100a SASS of the reference kernel), restated. */
+#define SV_MAX_IDX 9
+#define SV_INTER_OFF 8
+static int sv_less(float x1, float y1, float x2, float y2) {
+  const double EPS = 1e-8;
+  if ((double)fabsf(x1 - x2) < EPS && (double)fabsf(y2 - y1) < EPS) return 0;
+  if (y1 > 0 && y2 < 0) return 1;
+  if (y1 < 0 && y2 > 0) return 0;
+  const float n1 = (float)((double)fmaf(x1, x1, y1 * y1) + EPS);
+  const float n2 = (float)((double)fmaf(x2, x2, y2 * y2) + EPS);
+  const float d = fabsf(x1) * x1 / n1 - fabsf(x2) * x2 / n2;
+  if (y1 > 0 && y2 > 0) return (double)d > EPS;
+  if (y1 < 0 && y2 < 0) return (double)d < EPS;
+  return 0;
+}
+
+void nesie_oracle_sort_vertices(int b, int n, int m, const float *vertices,
+                                const unsigned char *mask, const int *num_valid, int *idx) {
+#pragma omp parallel for schedule(static)
+  for (long p = 0; p < (long)b * n; ++p) {
+    const float *v = vertices + (size_t)p * m * 2;
+    const unsigned char *mk = mask + (size_t)p * m;
+    int *out = idx + (size_t)p * SV_MAX_IDX;
+    const int nv = num_valid[p];
+    int pad = 0;
+    for (int j = SV_INTER_OFF; j < m; ++j)
+      if (!mk[j]) { pad = j; break; }
+    if (nv < 3) {
+      for (int j = 0; j < SV_MAX_IDX; ++j) out[j] = pad;
+      continue;
+    }
+    for (int j = 0; j < nv; ++j) {
+      float x_min = 1.f, y_min = (float)(-1e-8);
+      int take = 0;
+      for (int k = 0; k < m; ++k) {
+        const float x = v[2 * k], y = v[2 * k + 1];
+        if (j == 0) {
+          if (mk[k] && sv_less(x, y, x_min, y_min)) { x_min = x; y_min = y; take = k; }
+        } else {
+          const int i2 = out[j - 1];
+          const float x2 = v[2 * i2], y2 = v[2 * i2 + 1];
+          if (mk[k] && sv_less(x, y, x_min, y_min) && sv_less(x2, y2, x, y)) {
+            x_min = x; y_min = y; take = k;
+          }
+        }
+      }
+      if (j < SV_MAX_IDX) out[j] = take;
+    }
+    out[nv] = out[0];
+    for (int j = nv + 1; j < SV_MAX_IDX; ++j) out[j] = pad;
+    if (nv == 8) {
+      int counter = 0;
+      for (int j = 0; j < 4; ++j)
+        for (int k = 4; k < SV_INTER_OFF; ++k)
+          if (out[k] == out[j]) counter++;
+      if (counter == 4) {
+        out[4] = out[0];
+        for (int j = 5; j < SV_MAX_IDX; ++j) out[j] = pad;
+      }
+    }
+  }
+}

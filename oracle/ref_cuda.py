@@ -172,3 +172,30 @@ def points_in_boxes_batch(points, boxes):
                                                             _p(points.contiguous()), _p(out))
     torch.cuda.synchronize()
     return out
+
+
+SORTV_PATH = os.path.join(_HERE, "_ref", "libnesie_ref_sortv.so")
+_sortv = None
+
+
+def sortv_available():
+    return os.path.exists(SORTV_PATH) and torch.cuda.is_available()
+
+
+def sort_vertices(vertices, mask, num_valid):
+    """The reference's sort_vertices_wrapper (ops/rotated_iou/cuda_op/sort_vert_kernel.cu:136-139),
+    which launches on the legacy default stream: synchronise around it."""
+    global _sortv
+    if _sortv is None:
+        _sortv = ctypes.CDLL(SORTV_PATH)
+    fn = getattr(_sortv, "_Z21sort_vertices_wrapperiiiPKfPKbPKiPi")
+    fn.restype = None
+    vertices = vertices.contiguous().float()
+    mask = mask.contiguous().bool()
+    num_valid = num_valid.contiguous().int()
+    B, N, M, _ = vertices.shape
+    idx = torch.zeros((B, N, 9), dtype=torch.int32, device=vertices.device)
+    torch.cuda.synchronize()
+    fn(B, N, M, _p(vertices), _p(mask), _p(num_valid), _p(idx))
+    torch.cuda.synchronize()
+    return idx
