@@ -26,6 +26,9 @@ class TeacherEMA:
         total = sum(p.numel() for p in self.params)
         dev = self.params[0].device
         _lib.need_cuda(self.params[0])
+        for n, p in zip(self.names, self.params):
+            assert p.dtype == torch.float32 and p.device == dev and p.layout == torch.strided, \
+                f"TeacherEMA needs dense fp32 parameters on one CUDA device ({n})"
         # re-home every parameter into one flat buffer (views keep the module API unchanged)
         self.flat_param = torch.empty(total, dtype=torch.float32, device=dev)
         off = 0
@@ -45,6 +48,19 @@ class TeacherEMA:
             out[f"ema_{name.replace('.', '_')}"] = self.flat_ema[off:off + n].view_as(p.data)
             off += n
         return out
+
+    def load_ema_state_dict(self, state, strict=True):
+        """Fill the EMA copies from `ema_*` entries of a reference checkpoint (the hook registers them
+        as model buffers, simi_teacher_hook.py:47-51, so `epoch_N.pth` / `epoch_N_ema.pth` carry
+        them).  Returns the consumed keys: drop them before a strict module.load_state_dict()."""
+        used = []
+        for key, dst in self.ema_state_dict().items():
+            if key in state:
+                dst.copy_(state[key].to(dst.device, dst.dtype).view_as(dst))
+                used.append(key)
+            elif strict:
+                raise KeyError(f"missing EMA buffer {key}")
+        return used
 
     def after_train_iter(self, curr_step):
         momentum = min(self.momentum, (1 + curr_step) / (self.warm_up + curr_step))
