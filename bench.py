@@ -1,21 +1,33 @@
 #!/usr/bin/env python
 """bench.py -- Nesie-VoteNet train scenes/s on synthetic 40k-point ScanNet-shaped scenes.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload W] [--impl reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One step = forward + backward + AdamW update of the VoteNet harness (nesie_b200/votenet.py:
-PointNet2SASSG backbone, vote module, vote-aggregation SA, prediction head, losses incl. the
-side-uncertainty loss) on 8 scenes per GPU; scenes shard across ranks (DDP, one NCCL gradient
-all-reduce per step) -> weak scaling.  Prints ONE JSON line (rank 0).
+Workloads (BASELINE.json configs):
+  pretrain      configs[2] (default): VoteNet pretrain step = PointNet2SASSG -> NesieHead.forward
+                (vote module, vote aggregation SA, prediction convs, side2box, random box jitter,
+                SidePooling quality head) -> NesieHead.loss (reference target assignment, all 8 loss
+                terms) -> backward -> gradient all-reduce -> clip -> AdamW; 8 scenes per GPU.
+  mean_teacher  configs[3]: student forward on 16 scenes (8 labeled + 8 unlabeled), teacher forward on
+                the same 16 under swapped EMA weights, device-side pseudo-label filter + box transform,
+                supervised + unsupervised losses, backward, all-reduce, AdamW, EMA update.
+  stress        configs[4]: SAQE-shaped stress, 100k-point scenes, 4096 SA1 centres, 16 scenes per GPU,
+                SAQE uncertainty weighting.
+  pretrain_conv round-1 harness (quality scores from a 1x1 conv instead of SidePooling), kept as a
+                named variant for comparison.
+Scenes shard across ranks (nesie_b200.ddp.FlatGradDDP: bucketed NCCL all-reduce overlapped with the
+backward pass) -> weak scaling.  Prints ONE JSON line (rank 0).
 
-  value  : scenes/s with the batch already resident in HBM (CUDA events, max over ranks)
-  e2e    : scenes/s through the same public API with the batch in pinned host memory: every step
+  value  : scenes/s with the batches already resident in HBM (CUDA events, max over ranks)
+  e2e    : scenes/s through the same public API with the batches in pinned host memory: every step
            copies its inputs host->device and reads the loss back
-  roofline: the dominant hand-written kernel on the critical path (tcgen05 row GEMM at its largest
-           shape), timed live with CUDA events; FPS (off the critical path) is reported beside it
-  cpu_baseline: the same step on the host cores with the oracle port of the reference kernels
-           (the reference has no CPU path of its own), bounded to 1 scene per step
+  roofline: the hand-written kernel family with the largest summed time in the step, STEP-WEIGHTED:
+           sum of algorithmic bytes of its launches / sum of their durations, every distinct launch
+           shape timed live with CUDA events; the best single shape is reported beside it
+  cpu_baseline: the same step on the host cores with the oracle port of the reference kernels (the
+           reference has no CPU path of its own), median of 3 steps, plus the 1-scene forward of
+           BASELINE configs[0]
 `--impl reference` times that CPU port alone (all host threads).
 """
 import argparse
@@ -23,20 +35,28 @@ import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
+import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-SCENES_PER_GPU = 8
-N_POINTS = 40000
-WORKLOAD = "votenet_pretrain_fwd_bwd_adamw_b8_per_gpu_40kpts_18cls"
-# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the roofline kernel at the shape timed
-# below, from the ncu --set full capture summarised in profiles/r01_ncu_notes.md (268.6 MB read +
-# 481.3 MB written; 56 MB of the 537 MB output were still in L2 when the kernel ended)
+WORKLOADS = {
+    "pretrain": dict(scenes=8, points=40000, gt_pad=16,
+                     name="votenet_pretrain_fwd_bwd_adamw_b8_per_gpu_40kpts_18cls+side_pooling"),
+    "pretrain_conv": dict(scenes=8, points=40000, gt_pad=16,
+                          name="votenet_pretrain_fwd_bwd_adamw_b8_per_gpu_40kpts_18cls"),
+    "mean_teacher": dict(scenes=16, points=40000, gt_pad=16,
+                         name="nesie_mean_teacher_step_8lb_8ulb_per_gpu_40kpts_18cls"),
+    "stress": dict(scenes=16, points=100000, gt_pad=16,
+                   name="saqe_stress_fwd_bwd_adamw_b16_per_gpu_100kpts_4096seeds"),
+}
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch of gemm_nt_tma_kernel at its largest
+# shape (SA1 layer 3, 524288 x 64 -> 128), ncu --set full capture summarised in profiles/r01_ncu_notes.md
 GEMM_DRAM_TRAFFIC = 749.8e6
 
 
@@ -90,45 +110,161 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(clocks)}
 
 
-def cpu_reference_step_rate(steps, warmup, scenes=SCENES_PER_GPU, quality_head="conv"):
-    """The oracle port of the step on the host cores (fwd + bwd + AdamW), `scenes` per step."""
+# ------------------------------------------------------------------------------------------------
+# models and synthetic batches
+# ------------------------------------------------------------------------------------------------
+def mean_size_file():
+    path = os.path.join(tempfile.mkdtemp(), "scannet_means.npz")
+    np.savez(path, np.ones((18, 3), dtype=np.float32))
+    return path
+
+
+def build_model(workload, oracle=False):
+    """The detector of a workload: product classes, or their CPU twins (oracle=True)."""
+    from nesie_b200 import detectors as D
+    if oracle:
+        from oracle import detectors_ref as R
+    if workload == "pretrain_conv":
+        if oracle:
+            from oracle.votenet_ref import VoteNetOracle
+            return VoteNetOracle(quality_head="conv")
+        from nesie_b200.votenet import VoteNetHarness
+        return VoteNetHarness(quality_head="conv")
+    head = D.nesie_head_cfg(mean_size_arr_path=mean_size_file())
+    if workload == "pretrain":
+        return (R.VoteNetRef if oracle else D.VoteNet)(bbox_head=head)
+    if workload == "mean_teacher":
+        return (R.VoteNetNesieRef if oracle else D.VoteNetNesie)(bbox_head=head, n_lb=120, n_ulb=1081)
+    if workload == "stress":
+        head["uncertainty"] = "saqe"
+        backbone = dict(in_channels=4, num_points=(4096, 1024, 512, 256))
+        return (R.VoteNetRef if oracle else D.VoteNet)(backbone=backbone, bbox_head=head)
+    raise ValueError(workload)
+
+
+def make_host_batch(workload, seed0, scenes=None):
+    """One batch as a flat dict of CPU tensors with static shapes (pinned by the caller)."""
+    from nesie_b200 import targets as T
     from nesie_b200.synthetic import make_batch
-    from oracle.votenet_ref import VoteNetOracle
+    cfg = WORKLOADS[workload]
+    S = scenes or cfg["scenes"]
+    cpu = torch.device("cpu")
+    if workload == "pretrain_conv":
+        from nesie_b200.votenet import VoteNetHarness
+        pts, gb, gl = make_batch(S, cfg["points"], seed0=seed0)
+        b, l, v = VoteNetHarness._pad_gt(gb, gl, cpu, pad_to=cfg["gt_pad"])
+        return dict(pts=pts, gt_boxes=b, gt_labels=l, gt_valid=v)
+    pts, gb, gl = make_batch(S, cfg["points"], seed0=seed0, origin="bottom")
+    if workload in ("pretrain", "stress"):
+        b, l, v = T.pad_gt(gb, gl, cpu, pad_to=cfg["gt_pad"])
+        return dict(pts=pts, gt_boxes=b, gt_labels=l, gt_valid=v)
+    # mean teacher: scenes [0, S/2) labeled, [S/2, S) unlabeled; student / teacher views of each
+    from nesie_b200.detectors import BoxAug, transform_boxes
+    g = torch.Generator().manual_seed(seed0)
+    aug_s, aug_t = BoxAug.random(S, cpu, g), BoxAug.random(S, cpu, g)
+    nl = S // 2
+    b, l, v = T.pad_gt(gb[:nl], gl[:nl], cpu, pad_to=cfg["gt_pad"])
+    b = transform_boxes(b, aug_s.index(torch.arange(nl))) * v.unsqueeze(-1)     # GT in the student frame
+    pts_all = torch.cat([aug_s.apply_points(pts), aug_t.apply_points(pts)], dim=0)   # (2S, N, 4)
+    out = dict(pts=pts_all, gt_boxes=b, gt_labels=l, gt_valid=v,
+               ulb_pos=(torch.randperm(1081, generator=g)[:S - nl]).long())
+    for tag, a in (("s", aug_s), ("t", aug_t)):
+        out.update({f"aug_{tag}_hf": a.hf, f"aug_{tag}_vf": a.vf, f"aug_{tag}_rot": a.rot,
+                    f"aug_{tag}_scale": a.scale, f"aug_{tag}_trans": a.trans})
+    return out
+
+
+def step_loss(workload, model, inp, fps=None, hook=None, static=None):
+    """Forward + losses of one step on the tensors of a batch dict -> scalar loss."""
+    kw = {}
+    if fps is not None:
+        kw = dict(fps_indices=fps, after_level=hook)
+    if workload == "pretrain_conv":
+        return model.train_step_loss_padded(inp["pts"], inp["gt_boxes"], inp["gt_labels"], inp["gt_valid"],
+                                            **kw)[0]
+    if workload in ("pretrain", "stress"):
+        return sum(model.forward_train_padded(inp["pts"], inp["gt_boxes"], inp["gt_labels"],
+                                              inp["gt_valid"], **kw).values())
+    from nesie_b200.detectors import BoxAug
+    S = inp["pts"].shape[0] // 2
+    aug = {t: BoxAug(*(inp[f"aug_{t}_{k}"] for k in ("hf", "vf", "rot", "scale", "trans"))) for t in "st"}
+    skw = tkw = None
+    if fps is not None:
+        skw = dict(fps_indices=[f[:S] for f in fps], after_level=hook)
+        tkw = dict(fps_indices=[f[S:] for f in fps])
+    losses = model.forward_train_padded(
+        inp["pts"][:S], inp["pts"][S:], inp["gt_boxes"], inp["gt_labels"], inp["gt_valid"],
+        static["sup_index"], static["unsup_index"], inp["ulb_pos"], aug["t"], aug["s"],
+        student_kw=skw, teacher_kw=tkw)
+    return sum(losses.values())
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference arm (oracle port)
+# ------------------------------------------------------------------------------------------------
+def cpu_reference(workload, steps, warmup, scenes=None, forward_only_scene=False):
+    """The oracle port of the step on the host cores -> (scenes/s, s/step, cores, scenes per step)."""
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     from oracle import cpu as oracle_cpu
-    oracle_cpu.set_threads(cores)  # torchrun exports OMP_NUM_THREADS=1
+    oracle_cpu.set_threads(cores)            # torchrun exports OMP_NUM_THREADS=1
     torch.manual_seed(0)
-    model = VoteNetOracle(quality_head=quality_head)
+    model = build_model(workload, oracle=True)
+    if workload == "mean_teacher":
+        model.init_teacher()
+    S = scenes or WORKLOADS[workload]["scenes"]
+    inp = make_host_batch(workload, 9000, S)
+    static = None
+    if workload == "mean_teacher":
+        static = dict(sup_index=torch.arange(S // 2), unsup_index=torch.arange(S // 2, S))
+    if forward_only_scene:
+        pts = inp["pts"][:1]
+        times = []
+        with torch.no_grad():
+            for it in range(warmup + steps):
+                t0 = time.perf_counter()
+                model.predict(pts) if hasattr(model, "predict") else model.forward(pts)
+                if it >= warmup:
+                    times.append(time.perf_counter() - t0)
+        times.sort()
+        return 1.0 / times[len(times) // 2], times[len(times) // 2], cores, 1
     opt = torch.optim.AdamW(model.parameters(), lr=0.008, weight_decay=0.01)
-    pts, gb, gl = make_batch(scenes, N_POINTS, seed0=9000)
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
         opt.zero_grad(set_to_none=True)
-        loss, _ = model.train_step_loss(pts, gb, gl)
+        loss = step_loss(workload, model, inp, static=static)
         loss.backward()
         torch.nn.utils.clip_grad_norm_(model.parameters(), 10.0)
         opt.step()
+        if workload == "mean_teacher":
+            model.after_train_iter(it)
         if it >= warmup:
             times.append(time.perf_counter() - t0)
     times.sort()
     sec = times[len(times) // 2]
-    return scenes / sec, sec, cores
+    return S / sec, sec, cores, S
+
+
+def cpu_sample_scenes(workload):
+    """Bounded CPU sample: full batch for the 40k-point steps, 2 scenes for the 100k-point stress."""
+    return 2 if workload == "stress" else WORKLOADS[workload]["scenes"]
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = min(args.steps, 2), min(args.warmup, 1)
-    rate, sec, cores = cpu_reference_step_rate(steps, warmup, quality_head=args.quality_head)
-    sample = (f"{SCENES_PER_GPU} scenes/step ({N_POINTS} pts each), fwd+bwd+AdamW, "
+    wl = args.workload
+    steps, warmup = max(min(args.steps, 3), 1), min(args.warmup, 1)
+    S = cpu_sample_scenes(wl)
+    rate, sec, cores, S = cpu_reference(wl, steps, warmup, scenes=S)
+    sample = (f"{S} scenes/step ({WORKLOADS[wl]['points']} pts each), full step on the host cores, "
               f"median of {steps} after {warmup} warm-up")
     line = {"impl": "reference", "metric": "train_scenes_per_s", "value": rate, "unit": "scenes/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": WORKLOAD, "scenes_per_step": SCENES_PER_GPU},
+            "data": "synthetic", "config": {"workload": WORKLOADS[wl]["name"], "scenes_per_step": S},
             "cpu_baseline": {"value": rate, "unit": "scenes/s", "cores": cores, "kind": "port",
                              "sample": sample},
             "e2e": {"value": rate, "unit": "scenes/s", "h2d_bytes_per_step": 0,
@@ -138,16 +274,82 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------
+# per-shape census of the GEMM kernels of one step (roofline)
+# ------------------------------------------------------------------------------------------------
+def gemm_census(trace, dev, min_reps=5):
+    """trace: [(entry point, args)] of one eager step.  Times every distinct GEMM launch shape live
+    (back to back, CUDA events) and returns per-family step-weighted numbers."""
+    from nesie_b200 import _lib
+    from nesie_b200 import linear_rows as lr
+    fam = {"nesie_gemm_nt_3xtf32": "gemm_nt", "nesie_gemm_nt_3xtf32_fused": "gemm_nt",
+           "nesie_gemm_wgrad_3xtf32": "gemm_wgrad", "nesie_gemm_wgrad_3xtf32_fused": "gemm_wgrad"}
+    shapes = {}
+    for name, a in trace:
+        if name in fam:
+            key = (fam[name], int(a[0]), int(a[1]), int(a[2]))
+            shapes[key] = shapes.get(key, 0) + 1
+    out = {}
+    for (family, R, N, K), count in sorted(shapes.items()):
+        if R < 1:
+            continue
+        if family == "gemm_nt":
+            # operands rotate through enough copies that nothing is served from the 126 MB L2
+            per = 4 * R * (K + N)
+            ncopy = max(1, min(8, int(300e6 // max(per, 1)) + 1))
+            xs = [torch.randn(R, K, device=dev) for _ in range(ncopy)]
+            ys = [torch.empty(R, N, device=dev) for _ in range(ncopy)]
+            img = lr._pack(torch.randn(N, K, device=dev), N, K, K, 1)
+
+            def launch(i):
+                _lib.call("nesie_gemm_nt_3xtf32", R, N, K, _lib.ptr(xs[i % ncopy]), K, _lib.ptr(img),
+                          _lib.ptr(ys[i % ncopy]), N, _lib.stream())
+        else:
+            if N > 256 or K > 512:
+                continue
+            per = 4 * R * (K + N)
+            ncopy = max(1, min(8, int(300e6 // max(per, 1)) + 1))
+            gs = [torch.randn(R, N, device=dev) for _ in range(ncopy)]
+            xs = [torch.randn(R, K, device=dev) for _ in range(ncopy)]
+            ns = _lib.lib().nesie_gemm_wgrad_splits(R, N, K)
+            parts = torch.empty((ns, N, K), device=dev)
+
+            def launch(i):
+                _lib.call("nesie_gemm_wgrad_3xtf32", R, N, K, _lib.ptr(gs[i % ncopy]), N,
+                          _lib.ptr(xs[i % ncopy]), K, _lib.ptr(parts), ns, _lib.stream())
+        reps = max(min_reps, ncopy)
+        for i in range(2):
+            launch(i)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(reps):
+            launch(i)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / reps
+        f = out.setdefault(family, dict(bytes=0.0, ms=0.0, launches=0, flops=0.0, best=None))
+        f["bytes"] += count * per
+        f["ms"] += count * ms
+        f["launches"] += count
+        f["flops"] += count * 2.0 * R * N * K
+        gbs = per / (ms * 1e-3) / 1e9
+        if per >= 64e6 and (f["best"] is None or gbs > f["best"]["gbs"]):
+            f["best"] = dict(shape=[R, K, N], ms=ms, gbs=gbs, bytes=per)
+        del xs
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="nesie_b200", choices=["nesie_b200", "reference"])
+    ap.add_argument("--workload", default="pretrain", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--quality-head", default="conv", choices=["conv", "side_pooling"],
-                    help="side_pooling adds the reference's SidePooling quality head (SURVEY 8f-1) to the "
-                         "step; the default is the benchmarked pretrain step of BASELINE.json")
+    ap.add_argument("--no-census", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -155,9 +357,11 @@ def main():
     import torch.distributed as dist
     import nesie_b200 as nb
     from nesie_b200 import _lib
-    from nesie_b200.synthetic import make_batch
-    from nesie_b200.votenet import VoteNetHarness
+    from nesie_b200.ddp import FlatGradDDP
 
+    wl = args.workload
+    cfg = WORKLOADS[wl]
+    S = cfg["scenes"]
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -172,89 +376,66 @@ def main():
     W, K = max(args.warmup, 3), args.steps
 
     torch.manual_seed(0)
-    model = VoteNetHarness(quality_head=args.quality_head).to(dev)
-    params = [p for p in model.parameters()]
-    # one flat gradient buffer (every p.grad is a view): the DDP exchange of this path is ONE NCCL
-    # all-reduce over it per step, issued inside the step so that it is graph-capturable
-    flat_grad = torch.zeros(sum(p.numel() for p in params), device=dev)
-    off = 0
-    for p in params:
-        p.grad = flat_grad[off:off + p.numel()].view_as(p)
-        off += p.numel()
-    if world > 1:  # identical replicas to start from
-        for t in list(model.parameters()) + list(model.buffers()):
-            dist.broadcast(t.data, 0)
+    model = build_model(wl).to(dev)
+    if wl == "mean_teacher":
+        model.init_teacher()             # re-homes the parameters into one flat buffer
+    ddp = FlatGradDDP(model)             # flat gradient buffer, bucketed all-reduce, broadcast of rank 0
+    params = ddp.params
     opt = torch.optim.AdamW(params, lr=0.008, weight_decay=0.01, fused=True, capturable=True)
+    backbone = model.backbone
+    static = None
+    if wl == "mean_teacher":
+        static = dict(sup_index=torch.arange(S // 2, device=dev), unsup_index=torch.arange(S // 2, S, device=dev))
 
     # a pool of distinct batches (so no step re-reads the previous step's inputs from L2)
-    NB, G = 4, 16
-    host = [make_batch(SCENES_PER_GPU, N_POINTS, seed0=1000 * rank + 100 * i) for i in range(NB)]
-    host_pts = [h[0].pin_memory() for h in host]
-    padded = [model._pad_gt(h[1], h[2], torch.device("cpu"), pad_to=G) for h in host]
-    host_gt = [tuple(t.pin_memory() for t in pg) for pg in padded]
-    dev_pts = [p.to(dev) for p in host_pts]
-    dev_gt = [tuple(t.to(dev) for t in pg) for pg in host_gt]
+    NB = 4
+    host = [make_host_batch(wl, 1000 * rank + 100 * i) for i in range(NB)]
+    host = [{k: v.pin_memory() for k, v in h.items()} for h in host]
+    resident = [{k: v.to(dev) for k, v in h.items()} for h in host]
+    h2d = sum(v.numel() * v.element_size() for v in host[0].values())
     # Input pipeline.  The FPS chain depends on coordinates only, so the chain of batch t+1 is computed
-    # while batch t trains (three input slots: one training, one being sampled, one being loaded).
-    # FPS is a serial, latency-bound kernel whose CTAs cannot share an SM with the persistent GEMM
-    # CTAs (registers), so WHERE it runs matters: forked at the start of the step it collides with
-    # the large SA1 / SA2 GEMMs; NESIE_BENCH_FPS_AT=<level> forks it inside the captured step right
-    # after SA level <level> has been issued (default 3 = after the last SA level: it then overlaps
-    # the small-grid middle of the step; measured 8.52 ms per step vs 8.84 at level 1 and 8.8-9.3
-    # beside the step), NESIE_BENCH_FPS_AT=start keeps it on a separate graph launched beside the step.
-    fps_at = os.environ.get("NESIE_BENCH_FPS_AT", "3")
-    fork_level = None if fps_at == "start" else int(fps_at)
-    # NESIE_BENCH_FPS_SPLIT=1 (fork mode only): the long first FPS level (128 SMs, 2.1 ms) of batch
-    # t+2 and the short remaining levels (8 SMs, 1.1 ms) of batch t+1 run side by side on two forked
-    # branches, so the FPS window of a step shrinks from 3.3 to 2.1 ms (four input slots; measured
-    # 8.38 vs 8.46 ms per step).
-    split = fork_level is not None and os.environ.get("NESIE_BENCH_FPS_SPLIT", "1") == "1"
+    # while batch t trains.  FPS is a serial, latency-bound kernel whose CTAs cannot share an SM with
+    # the persistent GEMM CTAs, so WHERE it runs matters: it is forked inside the captured step after
+    # SA level NESIE_BENCH_FPS_AT (default 3 = after the last SA level, beside the small-grid middle of
+    # the step); split mode runs the long first FPS level of batch t+2 and the short remaining levels of
+    # batch t+1 side by side on two branches (four input slots).
+    fork_level = int(os.environ.get("NESIE_BENCH_FPS_AT", "3"))
+    split = os.environ.get("NESIE_BENCH_FPS_SPLIT", "1") == "1"
     NSLOT = 4 if split else 3
+    n_fps_scenes = resident[0]["pts"].shape[0]
     slots = []
     for _ in range(NSLOT):
-        slots.append(dict(pts=torch.empty_like(dev_pts[0]),
-                          gt=tuple(torch.empty_like(t) for t in dev_gt[0]),
-                          fps=[torch.zeros((SCENES_PER_GPU, n), dtype=torch.int32, device=dev)
-                               for n in model.backbone.num_points],
+        slots.append(dict(inp={k: torch.empty_like(v) for k, v in resident[0].items()},
+                          fps=[torch.zeros((n_fps_scenes, n), dtype=torch.int32, device=dev)
+                               for n in backbone.num_points],
                           ev_fps=torch.cuda.Event(), ev_step=torch.cuda.Event(),
                           ev_load=torch.cuda.Event()))
     s_loss = torch.zeros((), device=dev)
     side = torch.cuda.Stream()
     side2 = torch.cuda.Stream()
     copy_stream = torch.cuda.Stream()
-
-    fps_levels = os.environ.get("NESIE_BENCH_FPS_LEVELS", "all")  # diagnostic: "first" / "rest"
+    step_no = {"n": 0}
 
     def fps_body(slot):
-        if fps_levels == "all":
-            for dst, src in zip(slot["fps"], model.backbone.fps_chain(slot["pts"])):
-                dst.copy_(src)
-            return
-        # timing diagnostics only (the indices of the skipped levels stay stale)
-        cur = slot["pts"][..., 0:3].contiguous()
-        for i in range(model.backbone.num_sa):
-            if (fps_levels == "first") == (i == 0):
-                slot["fps"][i].copy_(nb.furthest_point_sample(cur, model.backbone.num_points[i]))
-            if i + 1 < model.backbone.num_sa:
-                cur = nb.gather_points(cur.transpose(1, 2).contiguous(), slot["fps"][i]) \
-                    .transpose(1, 2).contiguous()
+        for dst, src in zip(slot["fps"], backbone.fps_chain(slot["inp"]["pts"])):
+            dst.copy_(src)
 
     def fps_first(slot):
-        slot["fps"][0].copy_(model.backbone.fps_chain(slot["pts"], stop=1)[0])
+        slot["fps"][0].copy_(backbone.fps_chain(slot["inp"]["pts"], stop=1)[0])
 
     def fps_rest(slot):
-        for dst, src in zip(slot["fps"][1:], model.backbone.fps_chain(slot["pts"], given=slot["fps"][:1])):
+        for dst, src in zip(slot["fps"][1:], backbone.fps_chain(slot["inp"]["pts"], given=slot["fps"][:1])):
             dst.copy_(src)
 
     def step_body(slot, nxt=None, nxt2=None):
-        """One training step on `slot`; with `nxt`, the FPS chain of the next batch is forked onto
-        the side stream after SA level `fork_level` and joined at the end of the step (split mode:
-        the remaining levels of `nxt` and the first level of `nxt2` on two branches)."""
+        """One training step on `slot`; with `nxt`, the FPS chain of the next batch is forked onto the
+        side stream after SA level `fork_level` and joined at the end of the step (split mode: the
+        remaining levels of `nxt` and the first level of `nxt2` on two branches)."""
         cur = torch.cuda.current_stream()
         hook = None
         if nxt is not None:
             def hook(i):
-                if i == fork_level and os.environ.get("NESIE_BENCH_SKIP_FPS") != "1":
+                if i == fork_level:
                     side.wait_stream(cur)
                     if nxt2 is None:
                         with torch.cuda.stream(side):
@@ -265,28 +446,26 @@ def main():
                             fps_first(nxt2)
                         with torch.cuda.stream(side2):
                             fps_rest(nxt)
-        flat_grad.zero_()
-        loss, _ = model.train_step_loss_padded(slot["pts"], *slot["gt"], fps_indices=slot["fps"],
-                                               after_level=hook)
+        ddp.zero_grad()
+        loss = step_loss(wl, model, slot["inp"], slot["fps"], hook, static)
         loss.backward()
-        if world > 1:
-            dist.all_reduce(flat_grad)
-            flat_grad.div_(world)
+        ddp.finish()
         torch.nn.utils.clip_grad_norm_(params, 10.0)
         opt.step()
+        if wl == "mean_teacher":
+            model.after_train_iter(10 + step_no["n"])   # past the warm-up: constant momentum 0.001
         s_loss.copy_(loss.detach())
         if nxt is not None:
             cur.wait_stream(side)
             if nxt2 is not None:
                 cur.wait_stream(side2)
 
-    def load_inputs(slot, pts, gt):
-        slot["pts"].copy_(pts, non_blocking=True)
-        for d, t in zip(slot["gt"], gt):
-            d.copy_(t, non_blocking=True)
+    def load_inputs(slot, src):
+        for k, d in slot["inp"].items():
+            d.copy_(src[k], non_blocking=True)
 
     def nxt_of(j):
-        return slots[(j + 1) % NSLOT] if fork_level is not None else None
+        return slots[(j + 1) % NSLOT]
 
     def nxt2_of(j):
         return slots[(j + 2) % NSLOT] if split else None
@@ -295,7 +474,7 @@ def main():
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
         for sl in slots:
-            load_inputs(sl, dev_pts[0], dev_gt[0])
+            load_inputs(sl, resident[0])
             fps_body(sl)
         for _ in range(3):
             step_body(slots[0])
@@ -307,21 +486,12 @@ def main():
     graphs = []
     if os.environ.get("NESIE_BENCH_GRAPH", "1") != "0":
         try:
-            step_g, fps_g = [], []
             for j, sl in enumerate(slots):
                 g1 = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g1):
                     step_body(sl, nxt_of(j), nxt2_of(j))
-                step_g.append(g1)
-                if fork_level is None:
-                    g2 = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g2):
-                        fps_body(sl)
-                    fps_g.append(g2)
-            graphs = step_g + fps_g
-            step_fn = [g.replay for g in step_g]
-            if fps_g:
-                fps_fn = [g.replay for g in fps_g]
+                graphs.append(g1)
+            step_fn = [g.replay for g in graphs]
             mode = "cuda_graph"
         except Exception as e:  # noqa: BLE001 -- fall back to eager launches
             graphs = []
@@ -333,54 +503,46 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def load_async(i, src_pts, src_gt):
+    def load_async(i, src):
         """copy stream: batch i -> slot i % NSLOT, once the slot's previous step has finished."""
         sl = slots[i % NSLOT]
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(sl["ev_step"])
-            load_inputs(sl, src_pts[i % NB], src_gt[i % NB])
+            load_inputs(sl, src[i % NB])
             sl["ev_load"].record(copy_stream)
 
-    def run_pipeline(nsteps, src_pts, src_gt, after_step=None):
-        main = torch.cuda.current_stream()
+    def run_pipeline(nsteps, src, after_step=None):
+        main_s = torch.cuda.current_stream()
         for sl in slots:
-            sl["ev_step"].record(main)
-        # prologue: batch 0 loaded and sampled, batch 1 loaded
-        load_async(0, src_pts, src_gt)
+            sl["ev_step"].record(main_s)
+        # prologue: batch 0 loaded and sampled, batch 1 loaded (split: + its first FPS level)
+        load_async(0, src)
         with torch.cuda.stream(side):
             side.wait_event(slots[0]["ev_load"])
             fps_fn[0]()
             slots[0]["ev_fps"].record(side)
-        load_async(1, src_pts, src_gt)
-        if split:   # batch 1 needs its first FPS level before step 0 runs its remaining levels
+        load_async(1, src)
+        if split:
             with torch.cuda.stream(side):
                 side.wait_event(slots[1]["ev_load"])
                 fps_first(slots[1])
                 slots[1]["ev_fps"].record(side)
-            load_async(2, src_pts, src_gt)
-            main.wait_event(slots[1]["ev_fps"])
-        main.wait_event(slots[0]["ev_fps"])
+            load_async(2, src)
+            main_s.wait_event(slots[1]["ev_fps"])
+        main_s.wait_event(slots[0]["ev_fps"])
         for i in range(nsteps):
             sl, nx = slots[i % NSLOT], slots[(i + 1) % NSLOT]
-            load_async(i + NSLOT - 1, src_pts, src_gt)  # overlaps this step
-            main.wait_event(nx["ev_load"])
+            load_async(i + NSLOT - 1, src)                 # overlaps this step
+            main_s.wait_event(nx["ev_load"])
             if split:
-                main.wait_event(slots[(i + 2) % NSLOT]["ev_load"])
-            if fork_level is None:
-                # FPS of batch i+1 on its own graph beside the step
-                with torch.cuda.stream(side):
-                    side.wait_event(nx["ev_load"])
-                    side.wait_event(nx["ev_step"])
-                    if os.environ.get("NESIE_BENCH_SKIP_FPS") != "1":
-                        fps_fn[(i + 1) % NSLOT]()
-                    nx["ev_fps"].record(side)
-                main.wait_event(sl["ev_fps"])
-            step_fn[i % NSLOT]()                         # fork mode: samples batch i+1 inside
-            sl["ev_step"].record(main)
+                main_s.wait_event(slots[(i + 2) % NSLOT]["ev_load"])
+            step_fn[i % NSLOT]()                           # samples batch i+1 (and i+2) inside
+            step_no["n"] += 1
+            sl["ev_step"].record(main_s)
             if after_step is not None:
                 after_step()
-        main.wait_stream(side)
-        main.wait_stream(copy_stream)
+        main_s.wait_stream(side)
+        main_s.wait_stream(copy_stream)
 
     def timed(fn):
         barrier()
@@ -397,21 +559,13 @@ def main():
         return ms
 
     # ---- device-resident throughput -----------------------------------------------------------
-    run_pipeline(W, dev_pts, dev_gt)
+    run_pipeline(W, resident)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms = timed(lambda: run_pipeline(K, dev_pts, dev_gt))
+    ms = timed(lambda: run_pipeline(K, resident))
     clocks = sampler.stop() if rank == 0 else None
-    value = world * SCENES_PER_GPU * K / (ms / 1e3)
-    # kernels of this repo launched per step (python-side counter; graph replays bypass it, so one
-    # step + one FPS chain are counted eagerly)
-    l0 = _lib.LAUNCHES
-    with torch.cuda.stream(side):
-        fps_body(slots[0])
-        step_body(slots[0])
-    torch.cuda.synchronize()
-    launches = (_lib.LAUNCHES - l0) * K
+    value = world * S * K / (ms / 1e3)
 
     # ---- end to end: pinned host -> device every step, loss read back every step ---------------
     # The loss of every step is copied to pinned host memory right behind the step; the host waits
@@ -429,106 +583,87 @@ def main():
             seen["last"] = float(sinks[(i - 1) & 1][0])
         seen["n"] = i + 1
 
-    def drain_loss():
-        i = seen["n"]
-        if i > 0:
-            sink_ev[(i - 1) & 1].synchronize()
-            seen["last"] = float(sinks[(i - 1) & 1][0])
-
     def e2e_run(n):
-        run_pipeline(n, host_pts, host_gt, read_loss)
-        drain_loss()
+        run_pipeline(n, host, read_loss)
+        if seen["n"] > 0:
+            sink_ev[(seen["n"] - 1) & 1].synchronize()
+            seen["last"] = float(sinks[(seen["n"] - 1) & 1][0])
 
     e2e_run(2)
     ms_e2e = timed(lambda: e2e_run(K))
-    e2e_value = world * SCENES_PER_GPU * K / (ms_e2e / 1e3)
-    h2d = host_pts[0].numel() * 4 + sum(t.numel() * t.element_size() for t in host_gt[0])
+    e2e_value = world * S * K / (ms_e2e / 1e3)
     final_loss = seen["last"]
 
-    # ---- dominant hand-written kernel, timed live ---------------------------------------------
-    # By time on the step's critical path that is the tcgen05 row GEMM of the SA shared MLPs
-    # (gemm_nt_tma_kernel: ~1.8 ms per step over 56 launches; FPS is longer as a single launch but
-    # runs off the critical path in the input pipeline).  Its largest launch is SA1 layer 3
-    # (forward 64 -> 128 channels; the data gradient has the mirrored shape and the same bytes):
-    # R = 8 scenes x 2048 groups x 64 samples rows.  HBM-bound: algorithmic bytes = 4 R (K + N).
-    from nesie_b200 import linear_rows as lr
-    R_, K_, N_ = SCENES_PER_GPU * 2048 * 64, 64, 128
-    ga = torch.randn(R_, K_, device=dev)
-    gw = torch.randn(N_, K_, device=dev)
-    gout = torch.empty(R_, N_, device=dev)
-    gimg = lr._pack(gw, N_, K_, K_, 1)
-
-    def one_gemm():
-        _lib.call("nesie_gemm_nt_3xtf32", R_, N_, K_, _lib.ptr(ga), K_, _lib.ptr(gimg),
-                  _lib.ptr(gout), N_, _lib.stream())
-
-    for _ in range(5):
-        one_gemm()
+    # ---- kernels of this repo per step + per-shape GEMM census (eager, outside the timed region) --
+    _lib.TRACE = []
+    l0 = _lib.LAUNCHES
+    with torch.cuda.stream(side):
+        fps_body(slots[0])
+        step_body(slots[0])
     torch.cuda.synchronize()
-    reps, ts = 10, []
-    for _ in range(max(K // 2, 5)):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(reps):      # back to back: 805 MB per launch, nothing survives in the 126 MB L2
-            one_gemm()
-        b.record()
-        torch.cuda.synchronize()
-        ts.append(a.elapsed_time(b) / reps)
-    gemm_ms = sum(ts) / len(ts)
-    del ga, gout
-    xyz = dev_pts[0][..., :3].contiguous()
-    for _ in range(3):
-        nb.furthest_point_sample(xyz, 2048)
-    torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(5):
-        nb.furthest_point_sample(xyz, 2048)
-    b.record()
-    torch.cuda.synchronize()
-    fps_ms = a.elapsed_time(b) / 5
+    launches = (_lib.LAUNCHES - l0) * K
+    trace, _lib.TRACE = _lib.TRACE, None
     pk, pk_kind = peaks()
-    alg_bytes = 4.0 * R_ * (K_ + N_)
-    achieved = alg_bytes / (gemm_ms * 1e-3) / 1e9
-    roofline = {"kernel": f"gemm_nt_tma_kernel (3xTF32 tcgen05 row GEMM, SA1 layer 3: {R_} x {K_} -> {N_})",
-                "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / pk["hbm_gbs"], "traffic": GEMM_DRAM_TRAFFIC, "peak_source": pk_kind,
-                "kernel_ms": gemm_ms, "algorithmic_bytes": alg_bytes,
-                "tensor_tflops_fp32_equiv": 2.0 * R_ * K_ * N_ / (gemm_ms * 1e-3) / 1e12,
-                "off_critical_path": {"kernel": "fps_reg_kernel (FPS 40000->2048, batch 8)",
-                                      "kernel_ms": fps_ms,
-                                      "point_updates_per_s": SCENES_PER_GPU * 2047 * N_POINTS / (fps_ms * 1e-3),
-                                      "note": "2047 dependent argmax steps: latency-bound (3.9 MB of "
-                                              "algorithmic bytes), overlapped with the previous step"}}
+    roofline = None
+    if rank == 0 and not args.no_census:
+        census = gemm_census(trace, dev)
+        if census:
+            name = max(census, key=lambda k: census[k]["ms"])
+            c = census[name]
+            achieved = c["bytes"] / (c["ms"] * 1e-3) / 1e9
+            kern = {"gemm_nt": "gemm_nt_tma_kernel (3xTF32 tcgen05 row GEMM: forward + data gradient)",
+                    "gemm_wgrad": "gemm_wgrad_tma_kernel (3xTF32 tcgen05 weight gradient)"}[name]
+            roofline = {"kernel": kern, "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"],
+                        "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": GEMM_DRAM_TRAFFIC,
+                        "peak_source": pk_kind, "weighting": "step-weighted: sum of algorithmic bytes "
+                        "4*R*(K+N) of the family's launches in one step / sum of their live-timed durations",
+                        "launches_per_step": c["launches"], "kernel_ms_per_step": c["ms"],
+                        "algorithmic_bytes_per_step": c["bytes"],
+                        "tensor_tflops_fp32_equiv": c["flops"] / (c["ms"] * 1e-3) / 1e12,
+                        "best_shape": c["best"],
+                        "best_shape_frac": (c["best"]["gbs"] / pk["hbm_gbs"]) if c["best"] else None,
+                        "families": {k: dict(ms_per_step=v["ms"], launches=v["launches"],
+                                             gbs=v["bytes"] / (v["ms"] * 1e-3) / 1e9,
+                                             frac=v["bytes"] / (v["ms"] * 1e-3) / 1e9 / pk["hbm_gbs"])
+                                     for k, v in census.items()}}
 
     line = {"metric": "train_scenes_per_s", "value": value, "unit": "scenes/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD + ("" if args.quality_head == "conv" else "+side_pooling"),
-                       "scenes_per_gpu": SCENES_PER_GPU, "points": N_POINTS,
+            "config": {"workload": cfg["name"], "scenes_per_gpu": S, "points": cfg["points"],
                        "classes": 18, "parallelism": f"dp{world}",
                        "l2": "4 distinct resident batches cycled; per-step activations exceed L2",
-                       "launch": mode,
-                       "input_pipeline": ("batch t+2 copied and batch t+1 sampled (FPS chain) during step t; FPS forked "
-                                          + ("beside the step" if fork_level is None else f"inside the captured step after SA level {fork_level}"))},
+                       "launch": mode, "ddp": f"{len(ddp.buckets)} gradient buckets, {ddp.flat.numel() * 4} bytes, "
+                                              "all-reduce overlapped with backward",
+                       "input_pipeline": f"batch t+2 copied and batch t+1 sampled (FPS chain) during step t; "
+                                         f"FPS forked inside the captured step after SA level {fork_level}"},
             "e2e": {"value": e2e_value, "unit": "scenes/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / K},
             "gpu_launches": launches, "roofline": roofline, "clocks": clocks,
             "final_loss": final_loss}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rate, sec, cores = cpu_reference_step_rate(1, 1, quality_head=args.quality_head)
+        Sc = cpu_sample_scenes(wl)
+        rate, sec, cores, Sc = cpu_reference(wl, 3, 1, scenes=Sc)
         line["cpu_baseline"] = {"value": rate, "unit": "scenes/s", "cores": cores, "kind": "port",
-                                "sample": f"{SCENES_PER_GPU} scenes/step ({N_POINTS} pts each), fwd+bwd+"
-                                          f"AdamW, 1 step after 1 warm-up ({sec:.2f} s/step)"}
+                                "sample": f"{Sc} scenes/step ({cfg['points']} pts each), full step, "
+                                          f"median of 3 after 1 warm-up ({sec:.2f} s/step)"}
+        if wl != "pretrain_conv":
+            r1, s1, _, _ = cpu_reference(wl, 3, 1, scenes=2, forward_only_scene=True)
+            line["cpu_baseline"]["forward_1scene"] = {
+                "value": r1, "unit": "scenes/s", "ms": s1 * 1e3,
+                "what": "BASELINE configs[0]: detector forward on 1 scene, batch 1, median of 3"}
     if rank == 0:
         print(json.dumps(line), flush=True)
-    # Tear down without NCCL/graph destructors: a captured graph that holds an NCCL all-reduce can
-    # make destroy_process_group() hang at exit.  Everything is flushed and synchronised first.
+    # Orderly teardown: graphs first (they hold the captured NCCL work), then the process group.  A
+    # watchdog ends the process if NCCL's destructor wedges, so a hang can never hold the box.
     sys.stdout.flush()
     sys.stderr.flush()
-    del graphs
+    threading.Thread(target=lambda: (time.sleep(90), os._exit(0)), daemon=True).start()
+    del step_fn, graphs
+    ddp.remove_hooks()
     barrier()
-    os._exit(0)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

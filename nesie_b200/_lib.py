@@ -111,7 +111,12 @@ def need_cuda(*tensors):
 LAUNCHES = 0  # kernels launched through the C ABI by this process (every entry point = 1 launch)
 
 
+TRACE = None  # when a list: every call appends (name, args) -- bench.py's per-shape kernel census
+
+
 def call(name, *args):
     global LAUNCHES
     LAUNCHES += 1
+    if TRACE is not None:
+        TRACE.append((name, args))
     check(getattr(lib(), name)(*args), name)

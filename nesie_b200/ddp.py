@@ -1,0 +1,131 @@
+"""Data-parallel gradient exchange of the train step.
+
+The reference wraps the detector in mmcv's MMDistributedDataParallel (built inside
+mmdet.apis.train_detector, reached from mmdet3d/apis/train.py:27-34; `broadcast_buffers=False` as in
+test.py:186-189): scenes shard by batch, every rank holds a full replica, the only collective of the
+path is the gradient all-reduce (~12.4 MB fp32).  Here:
+
+  * every parameter's .grad is a VIEW into one flat fp32 buffer, laid out bucket by bucket in the
+    order the backward pass produces gradients (head first, SA1 last), so a bucket is one contiguous
+    slice and one NCCL all-reduce -- no gradient copies, no per-tensor launches;
+  * a post-accumulate hook per parameter counts the bucket's ready gradients; the last one launches
+    the bucket's all-reduce on a communication stream, so the head / FP buckets are reduced while
+    the backward pass still runs through the SA levels; `finish()` joins the stream;
+  * everything is stream-ordered (no host sync), so a step that calls backward() + finish() can be
+    captured in a CUDA graph together with the optimizer;
+  * averaging: ReduceOp.AVG on NCCL, SUM then scale on backends without it (gloo in the CPU tests).
+
+BatchNorm statistics stay per-rank (plain BN2d/BN1d in the configs, not SyncBN) and buffers are not
+broadcast after construction, as in the reference.  The teacher EMA needs no communication: every
+rank applies the same update to identical weights.
+"""
+import torch
+import torch.distributed as dist
+
+
+def default_buckets(model, bucket_bytes=4 << 20):
+    """Parameters in REVERSE registration order (the order their gradients become ready, to a good
+    approximation: modules are registered in forward order), cut into buckets of ~bucket_bytes."""
+    params = [p for p in model.parameters() if p.requires_grad]
+    buckets, cur, size = [], [], 0
+    for p in reversed(params):
+        cur.append(p)
+        size += p.numel() * 4
+        if size >= bucket_bytes:
+            buckets.append(cur)
+            cur, size = [], 0
+    if cur:
+        buckets.append(cur)
+    return buckets
+
+
+class FlatGradDDP:
+
+    def __init__(self, model, process_group=None, bucket_bytes=4 << 20, buckets=None,
+                 broadcast_parameters=True, overlap=True):
+        self.model = model
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.buckets = buckets if buckets is not None else default_buckets(model, bucket_bytes)
+        self.params = [p for b in self.buckets for p in b]
+        assert len({id(p) for p in self.params}) == len(self.params), "a parameter appears in two buckets"
+        dev = self.params[0].device
+        assert all(p.dtype == torch.float32 and p.device == dev for p in self.params)
+        self.device = dev
+        self.flat = torch.zeros(sum(p.numel() for p in self.params), dtype=torch.float32, device=dev)
+        self.slices, self._bucket_of, off = [], {}, 0
+        for bi, bucket in enumerate(self.buckets):
+            start = off
+            for p in bucket:
+                p.grad = self.flat[off:off + p.numel()].view_as(p)
+                self._bucket_of[id(p)] = bi
+                off += p.numel()
+            self.slices.append(self.flat[start:off])
+        self._pending = [len(b) for b in self.buckets]
+        self._launched = [False] * len(self.buckets)
+        self.overlap = overlap and dev.type == "cuda" and self.world > 1
+        self.comm_stream = torch.cuda.Stream(device=dev) if self.overlap else None
+        backend = dist.get_backend(process_group) if self.world > 1 else None
+        self._avg = backend == "nccl"
+        self._hooks = []
+        if self.world > 1:
+            for p in self.params:
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
+            if broadcast_parameters:
+                self.broadcast()
+
+    # ---- replica consistency --------------------------------------------------------------------
+    def broadcast(self, src=0):
+        """Identical replicas to start from (parameters and buffers, once)."""
+        for t in list(self.model.parameters()) + list(self.model.buffers()):
+            dist.broadcast(t.data, src, group=self.group)
+
+    # ---- per step ---------------------------------------------------------------------------------
+    def zero_grad(self):
+        """Clear the flat buffer (gradients accumulate into its views) and re-arm the buckets."""
+        self.flat.zero_()
+        self._pending = [len(b) for b in self.buckets]
+        self._launched = [False] * len(self.buckets)
+
+    def _reduce(self, bi):
+        buf = self.slices[bi]
+        if self._avg:
+            dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=self.group)
+        else:
+            dist.all_reduce(buf, group=self.group)
+            buf.div_(self.world)
+        self._launched[bi] = True
+
+    def _on_grad(self, p):
+        bi = self._bucket_of[id(p)]
+        self._pending[bi] -= 1
+        if self._pending[bi] != 0:
+            return
+        if self.overlap:
+            self.comm_stream.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(self.comm_stream):
+                self._reduce(bi)
+        else:
+            self._reduce(bi)
+
+    def finish(self):
+        """Call after backward(): reduces the buckets whose last gradient never arrived (parameters
+        without a gradient this step) and makes the current stream wait for the exchange."""
+        if self.world == 1:
+            return
+        late = [bi for bi, done in enumerate(self._launched) if not done]
+        if self.overlap:
+            if late:
+                self.comm_stream.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(self.comm_stream):
+                    for bi in late:
+                        self._reduce(bi)
+            torch.cuda.current_stream(self.device).wait_stream(self.comm_stream)
+        else:
+            for bi in late:
+                self._reduce(bi)
+
+    def remove_hooks(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []

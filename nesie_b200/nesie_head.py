@@ -157,7 +157,7 @@ def quality_focal_loss(pred, label, score, weight, beta=2.0, loss_weight=1.0):
     neg = F.binary_cross_entropy(pred, torch.zeros_like(pred), reduction='none') * pred.pow(beta)
     p_pos = torch.gather(pred, 1, label.unsqueeze(1)).squeeze(1)
     pos = F.binary_cross_entropy(p_pos, score, reduction='none') * (score - p_pos).abs().pow(beta)
-    onehot = F.one_hot(label, pred.shape[1]).bool()
+    onehot = label.unsqueeze(1) == torch.arange(pred.shape[1], device=pred.device).unsqueeze(0)
     loss = torch.where(onehot, pos.unsqueeze(1), neg).sum(dim=1)
     return loss_weight * (loss * weight).sum()
 
@@ -194,6 +194,13 @@ class NesieHead(nn.Module):
                                               num_bbox_out_channels=self.n_reg_outs,
                                               num_heading_out_channels=2, reg_max=reg_max)
         self.integral = Integral(reg_max)
+        # constants as non-persistent buffers (the state_dict stays the reference's; no host -> device
+        # copies at run time, so the step can be captured in a CUDA graph)
+        sx, sy, sz = self.sizes
+        self.register_buffer('_scale_vec', torch.tensor([sx, sy, sz, sx, sy, sz]), persistent=False)
+        cw = self.loss_cfg['objectness'].get('class_weight')
+        self.register_buffer('_obj_class_weight', torch.tensor(cw) if cw is not None else None,
+                             persistent=False)
         self.grid_conv = self._k_side_pooling_cls()(**grid_conv_cfg)
 
     # ---- kernels (the CPU oracle twin overrides these) ------------------------------------------
@@ -235,8 +242,7 @@ class NesieHead(nn.Module):
         B, P = reg_rows.shape[:2]
         prob = F.softmax(reg_rows[..., :self.n_reg_outs].reshape(B, P, 6, self.reg_max + 1), dim=3)
         res = F.linear(prob, self.integral.project.type_as(prob))                   # (B, P, 6)
-        sx, sy, sz = self.sizes
-        scale = res.new_tensor([sx, sy, sz, sx, sy, sz]).expand(B, P, 6)
+        scale = self._scale_vec.to(res.dtype).expand(B, P, 6)
         d = res * scale
         lo, hi = aggregated_points - d[..., :3], aggregated_points + d[..., 3:]
         results['surface_pred'] = torch.cat([lo, hi], dim=-1)
@@ -384,8 +390,7 @@ class NesieHead(nn.Module):
                                               bbox_preds['seed_indices'], t['vote_target_masks'],
                                               t['vote_targets'], at_seeds=t['at_seeds'])
         ocfg = self.loss_cfg['objectness']
-        cw = ocfg.get('class_weight')
-        cw = bbox_preds['obj_scores'].new_tensor(cw) if cw is not None else None
+        cw = self._obj_class_weight
         objectness_loss = ocfg.get('loss_weight', 1.0) * (F.cross_entropy(
             bbox_preds['obj_scores'].transpose(2, 1), t['objectness_targets'], weight=cw,
             reduction='none') * t['objectness_weights']).sum()

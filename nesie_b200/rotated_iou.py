@@ -16,6 +16,17 @@ from torch.autograd import Function
 from . import _lib
 
 EPSILON = 1e-8
+_CORNER_SIGNS = {}
+
+
+def _corner_signs(ref):
+    """(+-0.5 corner pattern x, y) on ref's device; cached so that no host -> device copy happens
+    inside a CUDA-graph capture (the first, eager call creates them)."""
+    key = (ref.device, ref.dtype)
+    if key not in _CORNER_SIGNS:
+        _CORNER_SIGNS[key] = (torch.tensor([0.5, -0.5, -0.5, 0.5], dtype=ref.dtype, device=ref.device),
+                              torch.tensor([0.5, 0.5, -0.5, -0.5], dtype=ref.dtype, device=ref.device))
+    return _CORNER_SIGNS[key]
 
 
 class _SortVertices(Function):
@@ -49,8 +60,7 @@ def sort_vertices(vertices, mask, num_valid):
 def box2corners(box):
     """(B, N, 5) x, y, w, h, alpha -> (B, N, 4, 2) corners (oriented_iou_loss.py:6-35)."""
     x, y, w, h, alpha = box.unbind(-1)
-    sx = box.new_tensor([0.5, -0.5, -0.5, 0.5])
-    sy = box.new_tensor([0.5, 0.5, -0.5, -0.5])
+    sx, sy = _corner_signs(box)
     lx = sx * w.unsqueeze(-1)
     ly = sy * h.unsqueeze(-1)
     c, s = torch.cos(alpha).unsqueeze(-1), torch.sin(alpha).unsqueeze(-1)
@@ -103,8 +113,8 @@ def oriented_box_intersection_2d(c1, c2, sort_fn=sort_vertices):
 
 def cal_iou_3d(box3d1, box3d2, sort_fn=sort_vertices):
     """(B, N, 7) x, y, z, w, h, l, alpha boxes -> (B, N) IoU (oriented_iou_loss.py:86-109)."""
-    b1 = box3d1[..., [0, 1, 3, 4, 6]]
-    b2 = box3d2[..., [0, 1, 3, 4, 6]]
+    bev = lambda b: torch.cat([b[..., 0:2], b[..., 3:5], b[..., 6:7]], dim=-1)   # noqa: E731  x, y, w, h, alpha
+    b1, b2 = bev(box3d1), bev(box3d2)
     zmax1, zmin1 = box3d1[..., 2] + box3d1[..., 5] * 0.5, box3d1[..., 2] - box3d1[..., 5] * 0.5
     zmax2, zmin2 = box3d2[..., 2] + box3d2[..., 5] * 0.5, box3d2[..., 2] - box3d2[..., 5] * 0.5
     z_overlap = (torch.min(zmax1, zmax2) - torch.max(zmin1, zmin2)).clamp_min(0.)

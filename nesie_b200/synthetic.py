@@ -58,7 +58,11 @@ def make_scene(seed, n_points=40000, dup_frac=0.005):
     return torch.from_numpy(pts), torch.from_numpy(boxes), torch.from_numpy(labels)
 
 
-def make_batch(batch, n_points=40000, seed0=0):
-    """-> points (B,N,4) fp32 (CPU), list of gt boxes, list of gt labels."""
+def make_batch(batch, n_points=40000, seed0=0, origin='gravity'):
+    """-> points (B,N,4) fp32 (CPU), list of gt boxes, list of gt labels.  origin='bottom': boxes as
+    DepthInstance3DBoxes stores them (z of the bottom face; what NesieHead.loss expects)."""
     scenes = [make_scene(seed0 + i, n_points) for i in range(batch)]
+    if origin == 'bottom':
+        for s in scenes:
+            s[1][:, 2] -= 0.5 * s[1][:, 5]
     return (torch.stack([s[0] for s in scenes]), [s[1] for s in scenes], [s[2] for s in scenes])

@@ -1,10 +1,12 @@
-"""N > 1 path on the CPU (gloo, world_size 2): scenes shard by rank, DDP averages gradients, and
-every rank ends a step with identical weights -- the only collective on this path."""
+"""N > 1 path on the CPU (gloo, world_size 2) through the PRODUCT's data-parallel class
+(nesie_b200.ddp.FlatGradDDP: flat gradient buffer, bucketed all-reduce launched from
+post-accumulate hooks): scenes shard by rank, replicas start identical, the exchanged gradient is the
+mean of the two ranks' gradients bit for bit, and both ranks end the optimizer step with identical
+weights.  The model is the CPU twin of the VoteNet step (the product's kernels need a GPU)."""
 import os
 import socket
 import sys
 
-import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -20,29 +22,50 @@ def _free_port():
     return port
 
 
+def tiny_votenet(cls):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from head_cases import mean_size_file
+    from nesie_b200.detectors import nesie_head_cfg
+    head = nesie_head_cfg(mean_size_arr_path=mean_size_file(), num_proposal=16)
+    head["vote_module_cfg"] = dict(head["vote_module_cfg"], in_channels=32, conv_channels=(32, 32))
+    head["vote_aggregation_cfg"] = dict(head["vote_aggregation_cfg"], mlp_channels=[32, 32, 32, 32], num_sample=8)
+    head["pred_layer_cfg"] = dict(in_channels=32, shared_conv_channels=(32, 32), bias=True)
+    head["grid_conv_cfg"] = dict(head["grid_conv_cfg"], seed_feat_dim=32)
+    backbone = dict(in_channels=4, num_points=(128, 64, 32, 16), radius=(0.4, 0.8, 1.2, 1.6),
+                    num_samples=(8, 8, 8, 8), sa_channels=((16, 16, 32), (32, 32, 32), (32, 32, 32), (32, 32, 32)),
+                    fp_channels=((32, 32), (32, 32)))
+    return cls(backbone=backbone, bbox_head=head)
+
+
 def _worker(rank, world, port, out):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
+    from nesie_b200.ddp import FlatGradDDP
     from nesie_b200.synthetic import make_batch
-    from oracle.votenet_ref import VoteNetOracle
-    torch.manual_seed(0)
+    from oracle.detectors_ref import VoteNetRef
     torch.set_num_threads(2)
-    model = VoteNetOracle(num_points=(128, 64, 32, 16), num_samples=(8, 8, 8, 8), num_proposal=16)
-
-    class Step(torch.nn.Module):
-        def __init__(self, m):
-            super().__init__()
-            self.m = m
-
-        def forward(self, pts, gb, gl):
-            return self.m.train_step_loss(pts, gb, gl)[0]
-
-    ddp = torch.nn.parallel.DistributedDataParallel(Step(model), broadcast_buffers=False)
-    opt = torch.optim.AdamW(model.parameters(), lr=0.008, weight_decay=0.01)
-    pts, gb, gl = make_batch(2, 2048, seed0=100 * rank)  # each rank: its own scenes
-    loss = ddp(pts, gb, gl)
+    torch.manual_seed(rank)                       # replicas start DIFFERENT: broadcast must fix it
+    model = tiny_votenet(VoteNetRef)
+    ddp = FlatGradDDP(model, bucket_bytes=64 << 10)
+    assert len(ddp.buckets) > 2
+    opt = torch.optim.AdamW(ddp.params, lr=0.008, weight_decay=0.01)
+    pts, gb, gl = make_batch(2, 1024, seed0=100 * rank, origin='bottom')   # each rank: its own scenes
+    ddp.zero_grad()
+    torch.manual_seed(7)                          # same jitter noise stream on both ranks
+    loss = sum(model.forward_train(pts, gb, gl).values())
     loss.backward()
+    ddp.finish()
+    reduced = ddp.flat.clone()
+    # the local (pre-exchange) gradient is gone once the hooks have fired: recompute it without them
+    ddp.remove_hooks()
+    ddp.zero_grad()
+    torch.manual_seed(7)
+    sum(model.forward_train(pts, gb, gl).values()).backward()
+    local = ddp.flat.clone()
+    both = [torch.zeros_like(local) for _ in range(world)]
+    dist.all_gather(both, local)
+    ddp.flat.copy_(reduced)
     opt.step()
     flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
     gathered = [torch.zeros_like(flat) for _ in range(world)]
@@ -53,6 +76,9 @@ def _worker(rank, world, port, out):
         out["same_weights"] = bool(torch.equal(gathered[0], gathered[1]))
         out["different_data"] = bool(abs(float(losses[0]) - float(losses[1])) > 0)
         out["finite"] = bool(torch.isfinite(flat).all())
+        mean = (both[0] + both[1]) / world
+        out["grad_is_mean"] = bool(torch.allclose(reduced, mean, rtol=1e-6, atol=1e-9))
+        out["grad_nonzero"] = bool(reduced.abs().sum() > 0)
     dist.destroy_process_group()
 
 
@@ -61,3 +87,4 @@ def test_two_rank_gloo_step_keeps_replicas_identical():
     out = mgr.dict()
     mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
     assert out["finite"] and out["same_weights"] and out["different_data"]
+    assert out["grad_is_mean"] and out["grad_nonzero"]
