@@ -328,6 +328,9 @@ def gemm_census(trace, dev, min_reps=5):
         b.record()
         torch.cuda.synchronize()
         ms = a.elapsed_time(b) / reps
+        if os.environ.get("NESIE_BENCH_CENSUS_DUMP"):
+            sys.stderr.write(f"[census] {family} R={R} K={K} N={N} x{count}: {ms * 1e3:.1f} us, "
+                             f"{per / (ms * 1e-3) / 1e9:.0f} GB/s, {2.0 * R * N * K / (ms * 1e-3) / 1e12:.1f} TF/s fp32-equiv\n")
         f = out.setdefault(family, dict(bytes=0.0, ms=0.0, launches=0, flops=0.0, best=None))
         f["bytes"] += count * per
         f["ms"] += count * ms

@@ -52,14 +52,15 @@ class FlatGradDDP:
         dev = self.params[0].device
         assert all(p.dtype == torch.float32 and p.device == dev for p in self.params)
         self.device = dev
-        self.flat = torch.zeros(sum(p.numel() for p in self.params), dtype=torch.float32, device=dev)
+        pad = lambda n: (n + 63) // 64 * 64      # noqa: E731  every gradient starts 256-byte aligned
+        self.flat = torch.zeros(sum(pad(p.numel()) for p in self.params), dtype=torch.float32, device=dev)
         self.slices, self._bucket_of, off = [], {}, 0
         for bi, bucket in enumerate(self.buckets):
             start = off
             for p in bucket:
                 p.grad = self.flat[off:off + p.numel()].view_as(p)
                 self._bucket_of[id(p)] = bi
-                off += p.numel()
+                off += pad(p.numel())
             self.slices.append(self.flat[start:off])
         self._pending = [len(b) for b in self.buckets]
         self._launched = [False] * len(self.buckets)

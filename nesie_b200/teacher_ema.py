@@ -13,6 +13,9 @@ import torch
 from . import _lib
 
 
+ALIGN = 64   # floats
+
+
 class TeacherEMA:
 
     def __init__(self, model, momentum=0.001, interval=1, warm_up=10):
@@ -23,30 +26,31 @@ class TeacherEMA:
         self.warm_up = warm_up
         self.params = [p for _, p in model.named_parameters(recurse=True)]
         self.names = [n for n, _ in model.named_parameters(recurse=True)]
-        total = sum(p.numel() for p in self.params)
+        # every parameter starts on a 256-byte boundary of the flat buffer: the kernels read weights and
+        # BatchNorm vectors with 16-byte accesses / TMA (the padding floats are zero in both buffers)
+        self.offsets, total = [], 0
+        for p in self.params:
+            self.offsets.append(total)
+            total += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
         dev = self.params[0].device
         _lib.need_cuda(self.params[0])
         for n, p in zip(self.names, self.params):
             assert p.dtype == torch.float32 and p.device == dev and p.layout == torch.strided, \
                 f"TeacherEMA needs dense fp32 parameters on one CUDA device ({n})"
         # re-home every parameter into one flat buffer (views keep the module API unchanged)
-        self.flat_param = torch.empty(total, dtype=torch.float32, device=dev)
-        off = 0
-        for p in self.params:
+        self.flat_param = torch.zeros(total, dtype=torch.float32, device=dev)
+        for p, off in zip(self.params, self.offsets):
             n = p.numel()
             self.flat_param[off:off + n].copy_(p.data.reshape(-1))
             p.data = self.flat_param[off:off + n].view_as(p.data)
-            off += n
         self.flat_ema = self.flat_param.clone()
 
     def ema_state_dict(self):
         """EMA copies under the reference's buffer names `ema_<param name with dots -> _>`
         (simi_teacher_hook.py:47-51)."""
-        out, off = {}, 0
-        for name, p in zip(self.names, self.params):
-            n = p.numel()
-            out[f"ema_{name.replace('.', '_')}"] = self.flat_ema[off:off + n].view_as(p.data)
-            off += n
+        out = {}
+        for name, p, off in zip(self.names, self.params, self.offsets):
+            out[f"ema_{name.replace('.', '_')}"] = self.flat_ema[off:off + p.numel()].view_as(p.data)
         return out
 
     def load_ema_state_dict(self, state, strict=True):

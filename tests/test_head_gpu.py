@@ -77,8 +77,8 @@ def test_padding_beyond_the_largest_box_count_changes_nothing(head):
     preds, points, boxes, labels, _ = loss_inputs(G, "lossA", DEV)
     a = head.loss(preds, points, boxes, labels)
     b = head.loss_padded(preds, points, *T.pad_gt(boxes, labels, DEV, pad_to=16))
-    for k in LOSS_KEYS:
-        assert torch.equal(a[k], b[k]), k
+    for k in LOSS_KEYS:   # the padded zeros only change the shape of torch's summation tree
+        assert torch.allclose(a[k], b[k], rtol=2e-6, atol=0), k
 
 
 def test_forward_matches_reference():

@@ -1,4 +1,5 @@
-"""Per-kernel GPU time of one VoteNet harness train step (torch.profiler, CUDA kernels only)."""
+"""Per-kernel GPU time of one train step of a bench.py workload (torch.profiler, CUDA kernels only).
+    python tools/step_profile.py [pretrain|mean_teacher|stress|pretrain_conv] > profiles/rNN_step_profile.md"""
 import os
 import sys
 
@@ -7,26 +8,32 @@ from torch.profiler import ProfilerActivity, profile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from nesie_b200.synthetic import make_batch  # noqa: E402
-from nesie_b200.votenet import VoteNetHarness  # noqa: E402
+import bench  # noqa: E402
 
+wl = sys.argv[1] if len(sys.argv) > 1 else "pretrain"
 torch.backends.cuda.matmul.allow_tf32 = False
 torch.backends.cudnn.allow_tf32 = False
 torch.manual_seed(0)
-model = VoteNetHarness().cuda()
+dev = torch.device("cuda:0")
+model = bench.build_model(wl).to(dev)
+if wl == "mean_teacher":
+    model.init_teacher()
 opt = torch.optim.AdamW(model.parameters(), lr=0.008, weight_decay=0.01, fused=True)
-pts, gb, gl = make_batch(8, 40000)
-pts = pts.cuda()
-gb = [b.cuda() for b in gb]
-gl = [l.cuda() for l in gl]
+inp = {k: v.to(dev) for k, v in bench.make_host_batch(wl, 0).items()}
+S = bench.WORKLOADS[wl]["scenes"]
+static = dict(sup_index=torch.arange(S // 2, device=dev), unsup_index=torch.arange(S // 2, S, device=dev))
+it = [0]
 
 
 def step():
     opt.zero_grad(set_to_none=True)
-    loss, _ = model.train_step_loss(pts, gb, gl)
+    loss = bench.step_loss(wl, model, inp, static=static)
     loss.backward()
     torch.nn.utils.clip_grad_norm_(model.parameters(), 10.0)
     opt.step()
+    if wl == "mean_teacher":
+        model.after_train_iter(10 + it[0])
+    it[0] += 1
 
 
 for _ in range(3):
@@ -41,7 +48,8 @@ rows = [(e.key, e.self_device_time_total / NS, e.count / NS) for e in prof.key_a
         if e.self_device_time_total > 0]
 rows.sort(key=lambda r: -r[1])
 total = sum(r[1] for r in rows)
-print(f"total kernel time per step: {total / 1000:.2f} ms over {sum(r[2] for r in rows):.0f} launches")
+print(f"workload {wl}: total kernel time per step {total / 1000:.2f} ms over "
+      f"{sum(r[2] for r in rows):.0f} launches (eager, FPS chain inside the step)")
 print("| kernel | us/step | launches/step | share |\n|---|---:|---:|---:|")
-for k, us, n in rows[:40]:
+for k, us, n in rows[:45]:
     print(f"| `{k[:110]}` | {us:.0f} | {n:.0f} | {100 * us / total:.1f}% |")
