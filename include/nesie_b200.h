@@ -263,8 +263,12 @@ int nesie_points_in_boxes_batch(int b, int nbox, int npts, const float *boxes, c
  * forward's output shape; the maximum's gradient goes to row arg (as torch.max(dim) routes it). */
 int nesie_group_max_rows_forward(long long groups, int k, int c, const float *x, const float *bias,
                                  float *out, unsigned char *arg, int concat, void *stream);
+/* d_bias_part (nullable): (nesie_group_max_bias_parts(groups, c), c) per-CTA column sums of d_x, i.e.
+ * partial gradients of `bias`, to be summed over dim 0 by the caller (0 parts: not available for this c). */
+int nesie_group_max_bias_parts(long long groups, int c);
 int nesie_group_max_rows_backward(long long groups, int k, int c, const float *d_out,
-                                  const unsigned char *arg, float *d_x, int concat, void *stream);
+                                  const unsigned char *arg, float *d_x, int concat,
+                                  float *d_bias_part, void *stream);
 
 /* Inverse-distance interpolation into row-major GEMM rows: the grid features of the SidePooling
  * quality head (models/dense_heads/side_pooling_module.py:183-243, which builds them with a python

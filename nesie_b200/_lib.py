@@ -35,7 +35,8 @@ SIGNATURES = {
     "nesie_points_in_boxes": [_i, _i, _i, _p, _p, _p, _p],
     "nesie_points_in_boxes_batch": [_i, _i, _i, _p, _p, _p, _p],
     "nesie_group_max_rows_forward": [_ll, _i, _i, _p, _p, _p, _p, _i, _p],
-    "nesie_group_max_rows_backward": [_ll, _i, _i, _p, _p, _p, _i, _p],
+    "nesie_group_max_bias_parts": [_ll, _i],
+    "nesie_group_max_rows_backward": [_ll, _i, _i, _p, _p, _p, _i, _p, _p],
     "nesie_interp_rows": [_i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _p],
     "nesie_aligned_3d_nms_batched": [_i, _i, _p, _p, _p, _p, _f, _p, _p, _p],
     "nesie_lhs_nms_batched": [_i, _i, _p, _p, _d, _i, _p, _p, _p],

@@ -49,12 +49,17 @@ __global__ void __launch_bounds__(GM_THREADS) group_max_fwd_kernel(
   }
 }
 
+// d_bias_part (nullable): (gridDim.x, c) per-CTA column sums of d_x (= the gradient of the folded conv
+// bias), summed by the caller; requires (c / 4) | GM_THREADS so that a thread keeps its 4 channels over
+// the grid-stride loop (ATen's column sum of the tall d_x matrix cost more than this whole kernel).
 template <bool CONCAT>
 __global__ void __launch_bounds__(GM_THREADS) group_max_bwd_kernel(
     long long groups, int k, int c, const float *__restrict__ d_out,
-    const unsigned char *__restrict__ arg, float *__restrict__ d_x) {
+    const unsigned char *__restrict__ arg, float *__restrict__ d_x, float *__restrict__ d_bias_part) {
+  __shared__ float4 s_red[GM_THREADS];
   const int tpr = c >> 2;
   const long long total = groups * tpr;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (long long i = (long long)blockIdx.x * GM_THREADS + threadIdx.x; i < total;
        i += (long long)gridDim.x * GM_THREADS) {
     const long long g = i / tpr;
@@ -78,6 +83,20 @@ __global__ void __launch_bounds__(GM_THREADS) group_max_bwd_kernel(
       if (r == a.z) v.z += s.z;
       if (r == a.w) v.w += s.w;
       *reinterpret_cast<float4 *>(d_x + (g * k + r) * c + ch) = v;
+      if (CONCAT) { acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+    }
+    if (!CONCAT) { acc.x += s.x; acc.y += s.y; acc.z += s.z; acc.w += s.w; }
+  }
+  if (d_bias_part) {   // fixed-order tree over the threads that own the same channels: deterministic
+    s_red[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x < tpr) {
+      float4 t = s_red[threadIdx.x];
+      for (int j = threadIdx.x + tpr; j < GM_THREADS; j += tpr) {
+        const float4 u = s_red[j];
+        t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+      }
+      *reinterpret_cast<float4 *>(d_bias_part + (size_t)blockIdx.x * c + threadIdx.x * 4) = t;
     }
   }
 }
@@ -108,16 +127,22 @@ extern "C" int nesie_group_max_rows_forward(long long groups, int k, int c, cons
   return check_launch("nesie_group_max_rows_forward");
 }
 
+extern "C" int nesie_group_max_bias_parts(long long groups, int c) {
+  if (c < 4 || (c & 3) || GM_THREADS % (c >> 2)) return 0;   // 0: column sums not available in-kernel
+  return gm_grid(groups * (c >> 2));
+}
+
 extern "C" int nesie_group_max_rows_backward(long long groups, int k, int c, const float *d_out,
                                              const unsigned char *arg, float *d_x, int concat,
-                                             void *stream) {
+                                             float *d_bias_part, void *stream) {
   NESIE_REQUIRE(groups >= 0 && k >= 1 && k <= 255 && c >= 4 && (c & 3) == 0, "need 1 <= k <= 255, c % 4 == 0");
   if (groups == 0) return NESIE_OK;
   NESIE_REQUIRE(d_out && arg && d_x, "null pointer");
+  NESIE_REQUIRE(!d_bias_part || GM_THREADS % (c >> 2) == 0, "d_bias_part needs (c / 4) | 256");
   const int grid = gm_grid(groups * (c >> 2));
   if (concat)
-    group_max_bwd_kernel<true><<<grid, GM_THREADS, 0, (cudaStream_t)stream>>>(groups, k, c, d_out, arg, d_x);
+    group_max_bwd_kernel<true><<<grid, GM_THREADS, 0, (cudaStream_t)stream>>>(groups, k, c, d_out, arg, d_x, d_bias_part);
   else
-    group_max_bwd_kernel<false><<<grid, GM_THREADS, 0, (cudaStream_t)stream>>>(groups, k, c, d_out, arg, d_x);
+    group_max_bwd_kernel<false><<<grid, GM_THREADS, 0, (cudaStream_t)stream>>>(groups, k, c, d_out, arg, d_x, d_bias_part);
   return check_launch("nesie_group_max_rows_backward");
 }

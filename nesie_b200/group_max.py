@@ -31,10 +31,15 @@ class _GroupMaxRows(Function):
         groups, k, C, concat, has_bias = ctx.meta
         d_out = d_out.contiguous()
         d_x = torch.empty((groups * k, C), dtype=torch.float32, device=d_out.device)
+        want_bias = has_bias and ctx.needs_input_grad[1]
+        nparts = _lib.lib().nesie_group_max_bias_parts(groups, C) if want_bias else 0
+        parts = torch.empty((nparts, C), dtype=torch.float32, device=d_out.device) if nparts else None
         with torch.cuda.device(d_out.device):
             _lib.call("nesie_group_max_rows_backward", groups, k, C, _lib.ptr(d_out), _lib.ptr(arg),
-                      _lib.ptr(d_x), int(concat), _lib.stream())
-        d_bias = d_x.sum(dim=0) if has_bias and ctx.needs_input_grad[1] else None
+                      _lib.ptr(d_x), int(concat), _lib.ptr(parts), _lib.stream())
+        d_bias = None
+        if want_bias:   # column sums of d_x: per-CTA partials from the kernel (a few thousand rows)
+            d_bias = parts.sum(dim=0) if nparts else d_x.sum(dim=0)
         return d_x, d_bias, None, None
 
 

@@ -184,26 +184,38 @@ class SidePooling(nn.Module):
         return stat.permute(1, 0, 2, 3).repeat(1, 1, 1, 2)
 
     # ---- hot path hooks ----------------------------------------------------------------------
-    def _grid_rows(self, origin_xyz, origin_features, grid, center):
-        """grid (B, T, 3) world points, T = K * G -> rows (B*T, ld) = [grid - centre | features
-        interpolated from the 3 nearest seeds with normalised inverse-distance weights | 0 pad]."""
+    def _grid_rows(self, origin_xyz, origin_features, grid, center, sides=1):
+        """grid (B, T, 3) world points, T = K * sides * G ordered (box, side, grid point) -> per side
+        rows (B*K*G, ld) = [grid - centre | features interpolated from the 3 nearest seeds with
+        normalised inverse-distance weights | 0 pad]; one tensor when sides == 1, else a list.
+        Each side gets its own contiguous row block (the MiniPointNet of a side reads only its rows):
+        the 3-NN search runs once over all grid points, the row kernel once per side."""
         _lib.need_cuda(origin_xyz, origin_features, grid, center)
         B, T = grid.shape[:2]
         K = center.shape[1]
+        G = T // (K * sides)
         C = origin_features.shape[1]
         with torch.no_grad():
             dist, idx = three_nn(grid, origin_xyz)
             weight = 1.0 / (dist + 1e-8)
-            weight = (weight / weight.sum(dim=2, keepdim=True)).contiguous()
-            head = (grid.view(B, K, T // K, 3) - center.unsqueeze(2)).reshape(B, T, 3).contiguous()
+            weight = weight / weight.sum(dim=2, keepdim=True)
+            head = grid.view(B, K, sides * G, 3) - center.unsqueeze(2)
             table = origin_features.transpose(1, 2).contiguous()          # (B, N, C) point-major
             ld = -(-(3 + C) // 4) * 4
-            rows = torch.empty((B * T, ld), dtype=torch.float32, device=grid.device)
-            with torch.cuda.device(grid.device):
-                _lib.call("nesie_interp_rows", B, C, origin_xyz.shape[1], T, _lib.ptr(table),
-                          _lib.ptr(idx), _lib.ptr(weight), _lib.ptr(head), _lib.ptr(rows), ld,
-                          _lib.stream())
-        return rows
+            out = []
+            for i in range(sides):
+                pick = lambda t: t.view(B, K, sides, G, 3)[:, :, i].reshape(B, K * G, 3).contiguous()  # noqa: E731
+                rows = torch.empty((B * K * G, ld), dtype=torch.float32, device=grid.device)
+                with torch.cuda.device(grid.device):
+                    _lib.call("nesie_interp_rows", B, C, origin_xyz.shape[1], K * G, _lib.ptr(table),
+                              _lib.ptr(pick(idx)), _lib.ptr(pick(weight)), _lib.ptr(pick(head)),
+                              _lib.ptr(rows), ld, _lib.stream())
+                out.append(rows)
+        return out[0] if sides == 1 else out
+
+    def _side_rows(self, origin_xyz, origin_features, side_grid, center):
+        """Rows of the six face grids, one contiguous block per side."""
+        return self._grid_rows(origin_xyz, origin_features, side_grid, center, sides=6)
 
     def _mini_pointnet(self, mpn, rows, G):
         """rows (R, ld) with every G consecutive rows one box -> (R / G, feature_dim)."""
@@ -260,15 +272,13 @@ class SidePooling(nn.Module):
         whole_grid = self.generate_grid(size)
         side_grid = self.grid_for_side(whole_grid, center, heading).reshape(B, -1, 3).contiguous()
         bbox_grid = self.grid_for_bbox(whole_grid, center, heading).reshape(B, -1, 3).contiguous()
-        side_rows = self._grid_rows(origin_xyz, origin_features, side_grid, center)
+        side_rows = self._side_rows(origin_xyz, origin_features, side_grid, center)
         bbox_rows = self._grid_rows(origin_xyz, origin_features, bbox_grid, center)
         dist_feature = self.dist_feature(end_points, prefix)
 
-        side_rows = side_rows.view(B * K, 6, g2, -1)
         scores = []
         for i in range(6):
-            rows_i = side_rows[:, i].reshape(B * K * g2, -1)
-            feats = self._mini_pointnet(self.mlps_before[i], rows_i, g2)          # (B*K, 128)
+            feats = self._mini_pointnet(self.mlps_before[i], side_rows[i], g2)    # (B*K, 128)
             feats = feats.view(B, K, -1).transpose(1, 2)
             feats = torch.cat((feats, dist_feature[i]), dim=1)
             scores.append(self._head(self.mlps_head[i], feats))

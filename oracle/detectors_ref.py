@@ -69,6 +69,8 @@ class VoteNetNesieRef(D.VoteNetNesie):
                 n = boxes[i].shape[0]
                 if n:
                     pb[i, :n], pl[i, :n], pv[i, :n], pq[i, :n] = boxes[i], labels[i].long(), True, quality[i]
+            dev = points_t.device        # (the reference transforms the boxes on the CPU, :313-316)
+            pb, pl, pv, pq = pb.to(dev), pl.to(dev), pv.to(dev), pq.to(dev)
             pb = D.transformation_bbox_preds(pb, aug_t, aug_s) * pv.unsqueeze(-1)
             self.teacher.swap()
         return pb, pl, pv, pq

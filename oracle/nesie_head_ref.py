@@ -58,8 +58,8 @@ def chamfer_assign_ref(src, dst, n_valid=None, want=(True, True)):
     src, dst = src.detach(), dst.detach()
     B, N, _ = src.shape
     M = dst.shape[1]
-    i1 = torch.zeros((B, N), dtype=torch.long)
-    i2 = torch.zeros((B, M), dtype=torch.long)
+    i1 = torch.zeros((B, N), dtype=torch.long, device=src.device)
+    i2 = torch.zeros((B, M), dtype=torch.long, device=src.device)
     for b in range(B):
         s = src[b].unsqueeze(1).repeat(1, M, 1)
         d = dst[b].unsqueeze(0).repeat(N, 1, 1)

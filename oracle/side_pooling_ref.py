@@ -35,6 +35,12 @@ class SidePoolingOracle(SidePooling):
         head = grid.view(B, K, T // K, 3) - center.unsqueeze(2)
         return torch.cat([head.reshape(B * T, 3), feats.reshape(B * T, C)], dim=1)
 
+    def _side_rows(self, origin_xyz, origin_features, side_grid, center):
+        rows = self._grid_rows(origin_xyz, origin_features, side_grid, center)
+        B, K = center.shape[:2]
+        rows = rows.view(B * K, 6, -1, rows.shape[-1])
+        return [rows[:, i].reshape(-1, rows.shape[-1]) for i in range(6)]
+
     def _mini_pointnet(self, mpn, rows, G):
         R, C = rows.shape
         points = rows.view(R // G, G, C).permute(2, 0, 1).unsqueeze(0)    # (1, C, boxes, G)

@@ -53,3 +53,15 @@ print(f"workload {wl}: total kernel time per step {total / 1000:.2f} ms over "
 print("| kernel | us/step | launches/step | share |\n|---|---:|---:|---:|")
 for k, us, n in rows[:45]:
     print(f"| `{k[:110]}` | {us:.0f} | {n:.0f} | {100 * us / total:.1f}% |")
+
+if os.environ.get("NESIE_PROFILE_ATEN"):
+    # which ATen ops (by input shape) the library kernels of the step come from
+    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True) as prof2:
+        step()
+        torch.cuda.synchronize()
+    ev = [e for e in prof2.key_averages(group_by_input_shape=True)
+          if e.key.startswith("aten::") and e.self_device_time_total > 0]
+    ev.sort(key=lambda e: -e.self_device_time_total)
+    print("\n| aten op | input shapes | us/step | calls |\n|---|---|---:|---:|")
+    for e in ev[:40]:
+        print(f"| `{e.key}` | `{str(e.input_shapes)[:120]}` | {e.self_device_time_total:.0f} | {e.count} |")
