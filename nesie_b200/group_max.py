@@ -17,9 +17,10 @@ class _GroupMaxRows(Function):
         dev = x.device
         out = torch.empty((R, 2 * C) if concat else (groups, C), dtype=torch.float32, device=dev)
         arg = torch.empty((groups, C), dtype=torch.uint8, device=dev)
+        bias_c = bias.contiguous() if bias is not None else None   # alive across the launch
         with torch.cuda.device(dev):
             _lib.call("nesie_group_max_rows_forward", groups, k, C, _lib.ptr(x),
-                      _lib.ptr(bias.contiguous()) if bias is not None else None, _lib.ptr(out),
+                      _lib.ptr(bias_c), _lib.ptr(out),
                       _lib.ptr(arg), int(concat), _lib.stream())
         ctx.save_for_backward(arg)
         ctx.meta = (groups, k, C, bool(concat), bias is not None)

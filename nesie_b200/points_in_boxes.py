@@ -23,8 +23,9 @@ def points_in_boxes_gpu(points, boxes):
     B, M, _ = points.shape
     out = points.new_zeros((B, M), dtype=torch.int).fill_(-1)
     with torch.cuda.device(points.device):
-        _lib.call("nesie_points_in_boxes", B, boxes.shape[1], M, _lib.ptr(boxes.float().contiguous()),
-                  _lib.ptr(points.float().contiguous()), _lib.ptr(out), _lib.stream())
+        boxes_f, points_f = boxes.float().contiguous(), points.float().contiguous()   # alive across the launch
+        _lib.call("nesie_points_in_boxes", B, boxes.shape[1], M, _lib.ptr(boxes_f),
+                  _lib.ptr(points_f), _lib.ptr(out), _lib.stream())
     return out
 
 
@@ -36,6 +37,7 @@ def points_in_boxes_batch(points, boxes):
     # every (point, box) flag is written by the kernel: no zero fill of the 4*B*M*T byte output
     out = torch.empty((B, M, T), dtype=torch.int, device=points.device)
     with torch.cuda.device(points.device):
-        _lib.call("nesie_points_in_boxes_batch", B, T, M, _lib.ptr(boxes.float().contiguous()),
-                  _lib.ptr(points.float().contiguous()), _lib.ptr(out), _lib.stream())
+        boxes_f, points_f = boxes.float().contiguous(), points.float().contiguous()   # alive across the launch
+        _lib.call("nesie_points_in_boxes_batch", B, T, M, _lib.ptr(boxes_f),
+                  _lib.ptr(points_f), _lib.ptr(out), _lib.stream())
     return out

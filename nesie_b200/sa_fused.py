@@ -69,8 +69,9 @@ def pack_features(features, B, N):
     if features is None:
         raise ValueError("pack_features needs a device; pass zeros for xyz-only SA modules")
     table = torch.empty((B, N, c8), dtype=torch.bfloat16, device=dev)
+    features_c = features.contiguous()   # alive across the launch
     with torch.cuda.device(dev):
-        _lib.call("nesie_pack_features_bf16", B, c, N, _lib.ptr(features.contiguous()),
+        _lib.call("nesie_pack_features_bf16", B, c, N, _lib.ptr(features_c),
                   _lib.ptr(table), _lib.stream())
     return table
 
@@ -83,9 +84,10 @@ def sa_fused_forward(points_xyz, center_xyz, features, idx, radius, packed):
     M, K = idx.shape[1], idx.shape[2]
     table = pack_features(features, B, N)
     out = torch.empty((B, packed['c3'], M), dtype=torch.float32, device=points_xyz.device)
+    xyz_c, center_c, idx = points_xyz.contiguous(), center_xyz.contiguous(), idx.contiguous()
     with torch.cuda.device(points_xyz.device):
         _lib.call("nesie_sa_fused_forward", B, N, M, K, packed['c_in'], packed['c1'], packed['c2'],
-                  packed['c3'], _lib.ptr(points_xyz.contiguous()), _lib.ptr(center_xyz.contiguous()),
+                  packed['c3'], _lib.ptr(xyz_c), _lib.ptr(center_c),
                   _lib.ptr(table), _lib.ptr(idx), float(radius), _lib.ptr(packed['w1']),
                   _lib.ptr(packed['w2']), _lib.ptr(packed['w3']), _lib.ptr(packed['scale_shift']),
                   _lib.ptr(out), _lib.stream())

@@ -206,9 +206,10 @@ class SidePooling(nn.Module):
             for i in range(sides):
                 pick = lambda t: t.view(B, K, sides, G, 3)[:, :, i].reshape(B, K * G, 3).contiguous()  # noqa: E731
                 rows = torch.empty((B * K * G, ld), dtype=torch.float32, device=grid.device)
+                idx_i, w_i, head_i = pick(idx), pick(weight), pick(head)   # kept alive across the launch
                 with torch.cuda.device(grid.device):
                     _lib.call("nesie_interp_rows", B, C, origin_xyz.shape[1], K * G, _lib.ptr(table),
-                              _lib.ptr(pick(idx)), _lib.ptr(pick(weight)), _lib.ptr(pick(head)),
+                              _lib.ptr(idx_i), _lib.ptr(w_i), _lib.ptr(head_i),
                               _lib.ptr(rows), ld, _lib.stream())
                 out.append(rows)
         return out[0] if sides == 1 else out
