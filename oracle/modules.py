@@ -121,7 +121,7 @@ def backbone_forward(backbone, points):
     xyz = points[..., 0:3].contiguous()
     features = points[..., 3:].transpose(1, 2).contiguous() if points.size(-1) > 3 else None
     B, N = xyz.shape[:2]
-    indices = torch.arange(N, dtype=torch.long).unsqueeze(0).repeat(B, 1)
+    indices = torch.arange(N, dtype=torch.long, device=xyz.device).unsqueeze(0).repeat(B, 1)
     sa_xyz, sa_features, sa_indices = [xyz], [features], [indices]
     for i in range(backbone.num_sa):
         cx, cf, ci = sa_forward(backbone.SA_modules[i], sa_xyz[i], sa_features[i])

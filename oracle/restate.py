@@ -76,7 +76,7 @@ def side_uncertainty_loss(surface_pred, box_targets, side_scores, sem_scores, we
     loss = loss_weight * (loss * weight)
     indx = sem_scores.max(dim=-1)[1].reshape(-1)
     rows = indx.shape[0]
-    side = side_scores[torch.arange(rows), :, indx].reshape(-1, 6)
+    side = side_scores[torch.arange(rows, device=indx.device), :, indx].reshape(-1, 6)
     sigma = 0.8 * side * side - 1.8 * side + torch.ones_like(side)
     out = torch.exp(-sigma) * loss + alpha * sigma * weight
     return out.sum(), sigma
