@@ -21,6 +21,10 @@ from .side_loss import bbox2surface, side_uncertainty_loss
 from .side_pooling import MiniPointNet, SidePooling
 from .points_in_boxes import points_in_boxes_batch, points_in_boxes_gpu
 from .teacher_ema import TeacherEMA
+from .nesie_head import NesieHead, ReliableConvBboxHead, VoteModule
+from .detectors import BoxAug, VoteNet, VoteNetNesie, transformation_bbox_preds
+from .ddp import FlatGradDDP
+from .rotated_iou import cal_iou_3d, sort_vertices
 
 __all__ = [
     'ball_query', 'aligned_3d_nms', 'aligned_3d_nms_batched', 'Points_Sampler',
@@ -30,4 +34,6 @@ __all__ = [
     'PointSAModuleMSG', 'build_sa_module', 'get_pseudo_labels', 'lhs_3d_faster_samecls',
     'lhs_3d_faster_samecls_batched', 'bbox2surface', 'side_uncertainty_loss', 'TeacherEMA',
     'SidePooling', 'MiniPointNet', 'points_in_boxes_gpu', 'points_in_boxes_batch',
+    'NesieHead', 'ReliableConvBboxHead', 'VoteModule', 'VoteNet', 'VoteNetNesie', 'BoxAug',
+    'transformation_bbox_preds', 'FlatGradDDP', 'cal_iou_3d', 'sort_vertices',
 ]
