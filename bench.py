@@ -247,8 +247,9 @@ def cpu_reference(workload, steps, warmup, scenes=None, forward_only_scene=False
 
 
 def cpu_sample_scenes(workload):
-    """Bounded CPU sample: full batch for the 40k-point steps, 2 scenes for the 100k-point stress."""
-    return 2 if workload == "stress" else WORKLOADS[workload]["scenes"]
+    """Bounded CPU sample (10-30 s of host work for 1 warm-up + 3 timed steps): 4 scenes per step for
+    the 40k-point workloads, 2 for the 100k-point stress."""
+    return {"stress": 2, "pretrain_conv": 8}.get(workload, 4)
 
 
 def run_reference(args):

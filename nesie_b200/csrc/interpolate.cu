@@ -23,51 +23,73 @@ namespace nesie {
 namespace {
 
 constexpr int NN_THREADS = 128;
-constexpr int NN_TILE = 1024;  // source points per smem tile (12 KB)
+constexpr int NN_TILE = 1024;  // source points per smem tile (16 KB as float4)
 
+// T targets per thread: one broadcast LDS.128 of a source serves T distance evaluations (with one
+// target per thread the three 4-byte shared loads per pair, not the arithmetic, set the pace -- the
+// SidePooling grids ask for 650 k targets x 1024 sources per step).  Targets of a thread are
+// NN_THREADS apart so loads and stores stay coalesced.
+template <int T>
 __global__ void __launch_bounds__(NN_THREADS) three_nn_kernel(int n, int m,
                                                               const float *__restrict__ unknown,
                                                               const float *__restrict__ known,
                                                               float *__restrict__ dist2,
                                                               int *__restrict__ idx) {
-  __shared__ float s_k[NN_TILE * 3];
+  __shared__ float4 s_k[NN_TILE];
   const int b = blockIdx.y;
-  const int pt = blockIdx.x * NN_THREADS + threadIdx.x;
+  const int pt0 = blockIdx.x * (NN_THREADS * T) + threadIdx.x;
   unknown += (size_t)b * n * 3;
   known += (size_t)b * m * 3;
-  const bool ok = pt < n;
-  const float ux = ok ? unknown[pt * 3 + 0] : 0.f;
-  const float uy = ok ? unknown[pt * 3 + 1] : 0.f;
-  const float uz = ok ? unknown[pt * 3 + 2] : 0.f;
-  float best1 = CUDART_INF_F, best2 = CUDART_INF_F, best3 = CUDART_INF_F;
-  int i1 = 0, i2 = 0, i3 = 0;
+  float ux[T], uy[T], uz[T], best1[T], best2[T], best3[T];
+  int i1[T], i2[T], i3[T];
+#pragma unroll
+  for (int j = 0; j < T; ++j) {
+    const int pt = pt0 + j * NN_THREADS;
+    const bool ok = pt < n;
+    ux[j] = ok ? unknown[pt * 3 + 0] : 0.f;
+    uy[j] = ok ? unknown[pt * 3 + 1] : 0.f;
+    uz[j] = ok ? unknown[pt * 3 + 2] : 0.f;
+    best1[j] = best2[j] = best3[j] = CUDART_INF_F;
+    i1[j] = i2[j] = i3[j] = 0;
+  }
   for (int t0 = 0; t0 < m; t0 += NN_TILE) {
     const int tn = min(NN_TILE, m - t0);
     __syncthreads();
-    for (int i = threadIdx.x; i < tn * 3; i += NN_THREADS) s_k[i] = __ldg(known + (size_t)t0 * 3 + i);
+    for (int i = threadIdx.x; i < tn; i += NN_THREADS) {
+      const float *q = known + (size_t)(t0 + i) * 3;
+      s_k[i] = make_float4(__ldg(q), __ldg(q + 1), __ldg(q + 2), 0.f);
+    }
     __syncthreads();
-    if (ok) {
-#pragma unroll 4
-      for (int k = 0; k < tn; ++k) {
-        const float d = sqdist_ref(ux, uy, uz, s_k[k * 3 + 0], s_k[k * 3 + 1], s_k[k * 3 + 2]);
-        if (d < best1) {
-          best3 = best2; i3 = i2;
-          best2 = best1; i2 = i1;
-          best1 = d; i1 = t0 + k;
-        } else if (d < best2) {
-          best3 = best2; i3 = i2;
-          best2 = d; i2 = t0 + k;
-        } else if (d < best3) {
-          best3 = d; i3 = t0 + k;
+#pragma unroll 2
+    for (int k = 0; k < tn; ++k) {
+      const float4 s = s_k[k];
+#pragma unroll
+      for (int j = 0; j < T; ++j) {
+        const float d = sqdist_ref(ux[j], uy[j], uz[j], s.x, s.y, s.z);
+        if (d < best3[j]) {            // strict '<': the earliest source keeps its place on ties
+          if (d < best1[j]) {
+            best3[j] = best2[j]; i3[j] = i2[j];
+            best2[j] = best1[j]; i2[j] = i1[j];
+            best1[j] = d; i1[j] = t0 + k;
+          } else if (d < best2[j]) {
+            best3[j] = best2[j]; i3[j] = i2[j];
+            best2[j] = d; i2[j] = t0 + k;
+          } else {
+            best3[j] = d; i3[j] = t0 + k;
+          }
         }
       }
     }
   }
-  if (ok) {
-    float *od = dist2 + ((size_t)b * n + pt) * 3;
-    int *oi = idx + ((size_t)b * n + pt) * 3;
-    od[0] = best1; od[1] = best2; od[2] = best3;
-    oi[0] = i1; oi[1] = i2; oi[2] = i3;
+#pragma unroll
+  for (int j = 0; j < T; ++j) {
+    const int pt = pt0 + j * NN_THREADS;
+    if (pt < n) {
+      float *od = dist2 + ((size_t)b * n + pt) * 3;
+      int *oi = idx + ((size_t)b * n + pt) * 3;
+      od[0] = best1[j]; od[1] = best2[j]; od[2] = best3[j];
+      oi[0] = i1[j]; oi[1] = i2[j]; oi[2] = i3[j];
+    }
   }
 }
 
@@ -162,8 +184,14 @@ extern "C" int nesie_three_nn(int b, int n, int m, const float *unknown, const f
   NESIE_REQUIRE(unknown && known && dist2 && idx, "null pointer");
   if (b == 0 || n == 0) return NESIE_OK;
   NESIE_REQUIRE(b <= 65535, "b > 65535");
-  dim3 grid(ceil_div(n, NN_THREADS), b);
-  three_nn_kernel<<<grid, NN_THREADS, 0, (cudaStream_t)stream>>>(n, m, unknown, known, dist2, idx);
+  // 4 targets per thread once that still leaves two CTAs per SM; one otherwise (the FP layers)
+  if ((long long)ceil_div(n, NN_THREADS * 4) * b >= 2LL * num_sms()) {
+    dim3 grid(ceil_div(n, NN_THREADS * 4), b);
+    three_nn_kernel<4><<<grid, NN_THREADS, 0, (cudaStream_t)stream>>>(n, m, unknown, known, dist2, idx);
+  } else {
+    dim3 grid(ceil_div(n, NN_THREADS), b);
+    three_nn_kernel<1><<<grid, NN_THREADS, 0, (cudaStream_t)stream>>>(n, m, unknown, known, dist2, idx);
+  }
   return check_launch("nesie_three_nn");
 }
 

@@ -279,3 +279,15 @@ class VoteNetNesie(VoteNet):
     def after_train_iter(self, curr_step):
         """SimiRunnerHook.after_train_iter -> SimiTeacherHook.hooks_after_train_iter."""
         self.teacher.after_train_iter(curr_step)
+
+
+class VoteNetSAQE(VoteNetNesie):
+    """SAQE variant (detectors/votenet_saqe.py differs from votenet_nesie.py at :121,170,201): quality
+    polynomial 0.8 s^2 - 1.8 s + 1 in the pseudo-label filter and the SAQE head's uncertainty weighting
+    of the surface / IoU terms (dense_heads/saqe_head.py:590-607,631-641)."""
+
+    def __init__(self, backbone=None, bbox_head=None, **kw):
+        bbox_head = dict(bbox_head or nesie_head_cfg())
+        bbox_head.setdefault('uncertainty', 'saqe')
+        kw.setdefault('quality_poly', (0.8, 1.8))
+        super().__init__(backbone, bbox_head, **kw)

@@ -2,10 +2,6 @@
 REFERENCE's own NesieHead source (tests/golden/make_golden_head.py): targets exact, loss terms and
 gradients within fp32 rounding, forward outputs (module re-created from the seed: same construction
 order and state_dict names as the reference) within 1e-5."""
-import os
-import tempfile
-
-import numpy as np
 import pytest
 import torch
 
@@ -85,3 +81,33 @@ def test_forward_matches_reference():
             assert rel_err(res[k], G[f"fwd_{mode}_{k}"]) < 1e-5, (mode, k)
         assert torch.equal(res["aggregated_indices"].long(),
                            torch.from_numpy(G[f"fwd_{mode}_aggregated_indices"]).long())
+
+
+def test_saqe_uncertainty_weighting():
+    """uncertainty='saqe' (dense_heads/saqe_head.py:590-607,631-641): the surface and IoU terms are
+    weighted by exp(-sigma.detach()) with no alpha * sigma term, so side_scores receive no gradient
+    from them; every other term is the Nesie head's."""
+    torch.manual_seed(int(G["seed"]))
+    nesie = make_head(NesieHeadOracle, 16, 8)
+    saqe = make_head(NesieHeadOracle, 16, 8, uncertainty="saqe")
+    preds, points, boxes, labels, _ = loss_inputs(G, "lossA", torch.device("cpu"), grad=True)
+    a = nesie.loss({k: v.detach() for k, v in preds.items()}, points, boxes, labels)
+    b = saqe.loss(preds, points, boxes, labels)
+    for k in LOSS_KEYS:
+        if k not in ("surface_loss", "iou_loss"):
+            assert torch.equal(a[k], b[k]), k
+    # restatement of the two SAQE lines from the same targets
+    from nesie_b200.targets import pad_gt
+    t = saqe.get_targets_padded(points, *pad_gt(boxes, labels, torch.device("cpu")), preds)
+    C = 18
+    sem = preds["sem_scores"].reshape(-1, C)
+    side = preds["side_scores"].reshape(-1, 6, C)[torch.arange(sem.shape[0]), :, sem.argmax(-1)]
+    sigma = 0.8 * side * side - 1.8 * side + 1
+    w = t["box_loss_weights"].reshape(-1, 1).repeat(1, 6)
+    from oracle.restate import bbox2surface
+    L = 10.0 * ((preds["surface_pred"].reshape(-1, 6) - bbox2surface(t["bbox_targets"].reshape(-1, 7))) ** 2 * w)
+    want = (torch.exp(-sigma.detach()) * L).sum()
+    assert rel_err(b["surface_loss"], want.detach().numpy()) < 2e-6
+    (b["surface_loss"] + b["iou_loss"]).backward()
+    assert preds["side_scores"].grad is None or float(preds["side_scores"].grad.abs().sum()) == 0.0
+    assert float(preds["surface_pred"].grad.abs().sum()) > 0

@@ -203,7 +203,8 @@ def test_query_and_group_rows_layout_matches_channel_major(pad_to):
 
 
 # ---------------------------------------------------------------- three_nn / interpolate
-@pytest.mark.parametrize("B,n,m", [(2, 512, 256), (2, 1024, 512), (1, 7, 2), (1, 5, 1), (1, 3000, 2500)])
+@pytest.mark.parametrize("B,n,m", [(2, 512, 256), (2, 1024, 512), (1, 7, 2), (1, 5, 1), (1, 3000, 2500),
+                                   (8, 20001, 1000)])   # last: the 4-targets-per-thread path
 def test_three_nn(B, n, m):
     t = scene_xyz(B, n, 30)
     s = scene_xyz(B, m, 31)
