@@ -144,32 +144,45 @@ __global__ void __launch_bounds__(CH_THREADS) chamfer_assign_kernel(
 // ---- sort_vertices ---------------------------------------------------------------------------
 constexpr int SV_MAX_IDX = 9, SV_INTER_OFF = 8, SV_M = 24;
 
-__device__ __forceinline__ bool sv_less(float x1, float y1, float x2, float y2) {
-  const double EPS = 1e-8;
-  if ((double)fabsf(__fsub_rn(x1, x2)) < EPS && (double)fabsf(__fsub_rn(y2, y1)) < EPS) return false;
-  if (y1 > 0 && y2 < 0) return true;
-  if (y1 < 0 && y2 > 0) return false;
-  const float n1 = (float)((double)__fmaf_rn(x1, x1, __fmul_rn(y1, y1)) + EPS);
-  const float n2 = (float)((double)__fmaf_rn(x2, x2, __fmul_rn(y2, y2)) + EPS);
-  const float d = __fsub_rn(__fdiv_rn(__fmul_rn(fabsf(x1), x1), n1),
-                            __fdiv_rn(__fmul_rn(fabsf(x2), x2), n2));
-  if (y1 > 0 && y2 > 0) return (double)d > EPS;
-  if (y1 < 0 && y2 < 0) return (double)d < EPS;
+// The reference comparator (compare_vertices, sort_vert_kernel.cu:16-40) orders two vertices by
+// quadrant and by q = |x| x / n with n = x^2 + y^2 + EPSILON; EPSILON is the double literal 1e-8, so
+// its epsilon tests are double comparisons of float values.  q depends on one vertex only: it is
+// formed once per vertex (same operations: fma(x, x, y*y) in float, + 1e-8 in double, rounded to
+// float, float divide) instead of twice per comparison, and the double comparisons are replaced by
+// float comparisons against 1e-8 rounded up / down, which decide identically for every float.
+struct SvVertex { float x, y, q; };
+
+__device__ __forceinline__ float sv_q(float x, float y) {
+  const float n = (float)((double)__fmaf_rn(x, x, __fmul_rn(y, y)) + 1e-8);
+  return __fdiv_rn(__fmul_rn(fabsf(x), x), n);
+}
+
+__device__ __forceinline__ bool sv_less(const SvVertex &a, const SvVertex &b) {
+  const float eps_up = __double2float_ru(1e-8), eps_dn = __double2float_rd(1e-8);
+  if (fabsf(__fsub_rn(a.x, b.x)) < eps_up && fabsf(__fsub_rn(b.y, a.y)) < eps_up) return false;
+  if (a.y > 0 && b.y < 0) return true;
+  if (a.y < 0 && b.y > 0) return false;
+  const float d = __fsub_rn(a.q, b.q);
+  if (a.y > 0 && b.y > 0) return d > eps_dn;   // (double)d > 1e-8
+  if (a.y < 0 && b.y < 0) return d < eps_up;   // (double)d < 1e-8
   return false;
 }
 
-__global__ void __launch_bounds__(128) sort_vertices_kernel(
+// One thread per polygon, the 24 candidates (x, y, q) in registers (every loop over them is fully
+// unrolled), validity as a bit mask; the selection keeps the reference's single ascending scan per
+// round, because its comparator is not transitive across the epsilon tests.
+__global__ void __launch_bounds__(64) sort_vertices_kernel(
     long long polys, const float *__restrict__ vertices, const unsigned char *__restrict__ mask,
     const int *__restrict__ num_valid, int *__restrict__ idx) {
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= polys) return;
-  float vx[SV_M], vy[SV_M];
+  SvVertex v[SV_M];
   unsigned valid = 0u;
-  const float2 *v = reinterpret_cast<const float2 *>(vertices) + p * SV_M;
+  const float2 *vp = reinterpret_cast<const float2 *>(vertices) + p * SV_M;
 #pragma unroll
   for (int k = 0; k < SV_M; ++k) {
-    const float2 t = v[k];
-    vx[k] = t.x; vy[k] = t.y;
+    const float2 c = vp[k];
+    v[k].x = c.x; v[k].y = c.y; v[k].q = sv_q(c.x, c.y);
     valid |= (mask[p * SV_M + k] ? 1u : 0u) << k;
   }
   const int nv = num_valid[p];
@@ -182,31 +195,43 @@ __global__ void __launch_bounds__(128) sort_vertices_kernel(
 #pragma unroll
   for (int j = 0; j < SV_MAX_IDX; ++j) out[j] = pad;
   if (nv >= 3) {
-    float px = 0.f, py = 0.f;           // previously taken vertex
+    SvVertex first = {1.f, (float)(-1e-8), 0.f};       // the scan's initial "minimum" (:84-85)
+    first.q = sv_q(first.x, first.y);
+    SvVertex prev = first;
+#pragma unroll 1
     for (int j = 0; j < nv && j < SV_MAX_IDX - 1; ++j) {
-      float x_min = 1.f, y_min = (float)(-1e-8);
+      SvVertex best = first;
       int take = 0;
 #pragma unroll
       for (int k = 0; k < SV_M; ++k) {
-        if (!((valid >> k) & 1u)) continue;
-        if (!sv_less(vx[k], vy[k], x_min, y_min)) continue;
-        if (j > 0 && !sv_less(px, py, vx[k], vy[k])) continue;
-        x_min = vx[k]; y_min = vy[k]; take = k;
+        if (((valid >> k) & 1u) && sv_less(v[k], best) && (j == 0 || sv_less(prev, v[k]))) {
+          best = v[k];
+          take = k;
+        }
       }
-      out[j] = take;
-      px = 0.f; py = 0.f;
+      // the next round compares against vertices[idx[j]] -- vertex 0 when nothing was selected
+      // (the reference's i_take stays 0, :86)
+      prev = v[0];
 #pragma unroll
-      for (int k = 0; k < SV_M; ++k)
-        if (k == take) { px = vx[k]; py = vy[k]; }
+      for (int k = 1; k < SV_M; ++k)
+        if (k == take) prev = v[k];
+#pragma unroll
+      for (int jj = 0; jj < SV_MAX_IDX - 1; ++jj)
+        if (jj == j) out[jj] = take;
     }
-    if (nv < SV_MAX_IDX) out[nv] = out[0];
+#pragma unroll
+    for (int jj = 3; jj < SV_MAX_IDX; ++jj)
+      if (jj == nv) out[jj] = out[0];
     if (nv == 8) {                      // two identical boxes: every corner appears twice
       int counter = 0;
-      for (int j = 0; j < 4; ++j)
-        for (int k = 4; k < SV_INTER_OFF; ++k) counter += out[k] == out[j];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int k = 4; k < SV_INTER_OFF; ++k) counter += out[k] == out[a];
       if (counter == 4) {
         out[4] = out[0];
-        for (int j = 5; j < SV_MAX_IDX; ++j) out[j] = pad;
+#pragma unroll
+        for (int jj = 5; jj < SV_MAX_IDX; ++jj) out[jj] = pad;
       }
     }
   }
@@ -254,7 +279,7 @@ extern "C" int nesie_sort_vertices(int b, int n, int m, const float *vertices,
   const long long polys = (long long)b * n;
   if (polys == 0) return NESIE_OK;
   NESIE_REQUIRE(vertices && mask && num_valid && idx, "null pointer");
-  sort_vertices_kernel<<<(unsigned)((polys + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+  sort_vertices_kernel<<<(unsigned)((polys + 63) / 64), 64, 0, (cudaStream_t)stream>>>(
       polys, vertices, mask, num_valid, idx);
   return check_launch("nesie_sort_vertices");
 }
