@@ -380,6 +380,11 @@ int nesie_chamfer_assign(int b, int n, int m, const float *src, const float *dst
                          const int *nvalid, long long *idx1, long long *idx2, void *stream);
 int nesie_sort_vertices(int b, int n, int m, const float *vertices, const unsigned char *mask,
                         const int *num_valid, int *idx, void *stream);
+/* nesie_iou3d: cal_iou_3d (ops/rotated_iou/oriented_iou_loss.py:86-109) fused: box1, box2 (n, 7) =
+ *   x, y, z, w, h, l, alpha row-wise pairs -> iou (n) and, when jac_box1 != NULL, d iou / d box1 (n, 7)
+ *   (the reference differentiates through its tensor formulation; targets carry no gradient). */
+int nesie_iou3d(long long n, const float *box1, const float *box2, float *iou, float *jac_box1,
+                void *stream);
 
 #ifdef __cplusplus
 }

@@ -63,6 +63,7 @@ SIGNATURES = {
     "nesie_vote_targets": [_i, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p],
     "nesie_chamfer_assign": [_i, _i, _i, _p, _p, _p, _p, _p, _p],
     "nesie_sort_vertices": [_i, _i, _i, _p, _p, _p, _p, _p],
+    "nesie_iou3d": [_ll, _p, _p, _p, _p, _p],
     "nesie_sa_fused_forward": [_i] * 8 + [_p, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p],
 }
 

@@ -283,3 +283,291 @@ extern "C" int nesie_sort_vertices(int b, int n, int m, const float *vertices,
       polys, vertices, mask, num_valid, idx);
   return check_launch("nesie_sort_vertices");
 }
+
+// ---------------------------------------------------------------------------------------------
+// Fused rotated IoU (cal_iou_3d, ops/rotated_iou/oriented_iou_loss.py:86-109 with cal_iou :38-58 and
+// box_intersection_2d.py) forward + gradient with respect to the FIRST box, one thread per box pair.
+// The reference evaluates ~135 small tensor ops forward and ~200 backward per call (3 calls per train
+// step); here the candidate vertices (4 + 4 corners, 16 edge intersections), the vertex ordering
+// (the sort_vertices scan above), the shoelace area, the 3-D IoU and the reverse-mode gradient all
+// stay in registers.  Arithmetic follows the tensor formulation operator by operator (single-rounding
+// intrinsics, no contraction), so values agree with it to the last bits; the gradient is the exact
+// derivative of the same formulas (what autograd computes), including its conventions: no gradient
+// through the masks / ordering, `clamp_min` passes the gradient where its input is >= 0, a tie of
+// torch.min / torch.max splits it evenly.
+namespace nesie {
+namespace {
+
+struct F2 { float x, y; };
+
+__device__ __forceinline__ float fm(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fa(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fs(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fd(float a, float b) { return __fdiv_rn(a, b); }
+
+// corners of (x, y, w, h, alpha): lx = sx * w, ly = sy * h, (lx c - ly s + x, lx s + ly c + y)
+__device__ __forceinline__ void rect_corners(float x, float y, float w, float h, float c, float s,
+                                             F2 (&out)[4]) {
+  const float sx[4] = {0.5f, -0.5f, -0.5f, 0.5f}, sy[4] = {0.5f, 0.5f, -0.5f, -0.5f};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float lx = fm(sx[i], w), ly = fm(sy[i], h);
+    out[i].x = fa(fs(fm(lx, c), fm(ly, s)), x);
+    out[i].y = fa(fa(fm(lx, s), fm(ly, c)), y);
+  }
+}
+
+// corners of r1 inside (or on) rectangle r2 (box_intersection_2d.py:56-83)
+__device__ __forceinline__ unsigned corners_inside(const F2 (&r1)[4], const F2 (&r2)[4]) {
+  const float abx = fs(r2[1].x, r2[0].x), aby = fs(r2[1].y, r2[0].y);
+  const float adx = fs(r2[3].x, r2[0].x), ady = fs(r2[3].y, r2[0].y);
+  const float nab = fa(fm(abx, abx), fm(aby, aby)), nad = fa(fm(adx, adx), fm(ady, ady));
+  unsigned m = 0u;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float amx = fs(r1[i].x, r2[0].x), amy = fs(r1[i].y, r2[0].y);
+    const float pab = fd(fa(fm(abx, amx), fm(aby, amy)), nab);
+    const float pad = fd(fa(fm(adx, amx), fm(ady, amy)), nad);
+    const bool in = pab > -1e-6f && pab < 1.f + 1e-6f && pad > -1e-6f && pad < 1.f + 1e-6f;
+    m |= (in ? 1u : 0u) << i;
+  }
+  return m;
+}
+
+__global__ void __launch_bounds__(64) iou3d_kernel(long long n, const float *__restrict__ box1,
+                                                   const float *__restrict__ box2,
+                                                   float *__restrict__ iou_out,
+                                                   float *__restrict__ jac_out) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const float *a = box1 + r * 7, *b = box2 + r * 7;
+  const float x1 = a[0], y1 = a[1], z1 = a[2], w1 = a[3], h1 = a[4], l1 = a[5], al1 = a[6];
+  const float x2 = b[0], y2 = b[1], z2 = b[2], w2 = b[3], h2 = b[4], l2 = b[5], al2 = b[6];
+  const float c1 = cosf(al1), s1 = sinf(al1), c2 = cosf(al2), s2 = sinf(al2);
+  F2 r1[4], r2[4];
+  rect_corners(x1, y1, w1, h1, c1, s1, r1);
+  rect_corners(x2, y2, w2, h2, c2, s2, r2);
+
+  // ---- 24 candidate vertices -------------------------------------------------------------------
+  SvVertex v[SV_M];
+  float tt[16];                         // t of every edge pair (for the gradient)
+  unsigned valid = corners_inside(r1, r2) | (corners_inside(r2, r1) << 4);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { v[i].x = r1[i].x; v[i].y = r1[i].y; v[4 + i].x = r2[i].x; v[4 + i].y = r2[i].y; }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const F2 A = r1[i], B = r1[(i + 1) & 3];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const F2 C = r2[j], D = r2[(j + 1) & 3];
+      const float ya = fs(C.y, D.y), xb = fs(C.x, D.x);
+      const float num = fs(fm(fs(A.x, B.x), ya), fm(fs(A.y, B.y), xb));
+      const float den_t = fs(fm(fs(A.x, C.x), ya), fm(fs(A.y, C.y), xb));
+      const float den_u = fs(fm(fs(A.x, B.x), fs(A.y, C.y)), fm(fs(A.y, B.y), fs(A.x, C.x)));
+      const bool par = num == 0.f;
+      const float t0 = par ? -1.f : fd(den_t, num);
+      const float u0 = par ? -1.f : fd(-den_u, num);
+      const bool hit = t0 > 0.f && t0 < 1.f && u0 > 0.f && u0 < 1.f;
+      const float t = fd(den_t, fa(num, 1e-8f));
+      const int k = 8 + i * 4 + j;
+      tt[i * 4 + j] = t;
+      v[k].x = hit ? fa(A.x, fm(t, fs(B.x, A.x))) : 0.f;
+      v[k].y = hit ? fa(A.y, fm(t, fs(B.y, A.y))) : 0.f;
+      valid |= (hit ? 1u : 0u) << k;
+    }
+  }
+  // ---- ordering: mean-normalised copies through the sort_vertices scan ---------------------------
+  const int nv = __popc(valid);
+  float mx = 0.f, my = 0.f;
+#pragma unroll
+  for (int k = 0; k < SV_M; ++k) {      // torch.sum over the 24 slots in order, masked
+    mx = fa(mx, ((valid >> k) & 1u) ? v[k].x : fm(v[k].x, 0.f));
+    my = fa(my, ((valid >> k) & 1u) ? v[k].y : fm(v[k].y, 0.f));
+  }
+  mx = fd(mx, (float)nv);
+  my = fd(my, (float)nv);
+  int pad = 0;
+  {
+    const unsigned inv = ~valid & 0x00ffff00u;
+    if (inv) pad = __ffs(inv) - 1;
+  }
+  int order[SV_MAX_IDX];
+#pragma unroll
+  for (int j = 0; j < SV_MAX_IDX; ++j) order[j] = pad;
+  if (nv >= 3) {
+    SvVertex nrm[SV_M];
+#pragma unroll
+    for (int k = 0; k < SV_M; ++k) {
+      nrm[k].x = fs(v[k].x, mx); nrm[k].y = fs(v[k].y, my); nrm[k].q = sv_q(nrm[k].x, nrm[k].y);
+    }
+    SvVertex first = {1.f, (float)(-1e-8), 0.f};
+    first.q = sv_q(first.x, first.y);
+    SvVertex prev = first;
+#pragma unroll 1
+    for (int j = 0; j < nv && j < SV_MAX_IDX - 1; ++j) {
+      SvVertex best = first;
+      int take = 0;
+#pragma unroll
+      for (int k = 0; k < SV_M; ++k)
+        if (((valid >> k) & 1u) && sv_less(nrm[k], best) && (j == 0 || sv_less(prev, nrm[k]))) {
+          best = nrm[k]; take = k;
+        }
+      prev = nrm[0];
+#pragma unroll
+      for (int k = 1; k < SV_M; ++k)
+        if (k == take) prev = nrm[k];
+#pragma unroll
+      for (int jj = 0; jj < SV_MAX_IDX - 1; ++jj)
+        if (jj == j) order[jj] = take;
+    }
+#pragma unroll
+    for (int jj = 3; jj < SV_MAX_IDX; ++jj)
+      if (jj == nv) order[jj] = order[0];
+    if (nv == 8) {
+      int counter = 0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int k = 4; k < SV_INTER_OFF; ++k) counter += order[k] == order[q];
+      if (counter == 4) {
+        order[4] = order[0];
+#pragma unroll
+        for (int jj = 5; jj < SV_MAX_IDX; ++jj) order[jj] = pad;
+      }
+    }
+  }
+  // ---- shoelace area over the 9 selected vertices + its gradient per selected slot ---------------
+  float px[SV_MAX_IDX], py[SV_MAX_IDX];
+#pragma unroll
+  for (int j = 0; j < SV_MAX_IDX; ++j) {
+    px[j] = v[0].x; py[j] = v[0].y;
+#pragma unroll
+    for (int k = 1; k < SV_M; ++k)
+      if (k == order[j]) { px[j] = v[k].x; py[j] = v[k].y; }
+  }
+  float total = 0.f;
+#pragma unroll
+  for (int j = 0; j + 1 < SV_MAX_IDX; ++j)
+    total = fa(total, fs(fm(px[j], py[j + 1]), fm(py[j], px[j + 1])));
+  const float inter = fd(fabsf(total), 2.f);
+  const float sgn = total > 0.f ? 1.f : (total < 0.f ? -1.f : 0.f);
+  // 3-D part
+  const float zmax1 = fa(z1, fm(l1, 0.5f)), zmin1 = fs(z1, fm(l1, 0.5f));
+  const float zmax2 = fa(z2, fm(l2, 0.5f)), zmin2 = fs(z2, fm(l2, 0.5f));
+  const float ztop = fminf(zmax1, zmax2), zbot = fmaxf(zmin1, zmin2);
+  const float zraw = fs(ztop, zbot);
+  const float zov = fmaxf(zraw, 0.f);
+  const float area1 = fm(w1, h1), area2 = fm(w2, h2);
+  const float u = fs(fa(area1, area2), inter);
+  const float iou2d = fd(inter, u);
+  const float i3 = fm(fm(iou2d, u), zov);
+  const float vol1 = fm(fm(w1, h1), l1), vol2 = fm(fm(w2, h2), l2);
+  const float u3 = fs(fa(vol1, vol2), i3);
+  const float iou = fd(i3, u3);
+  iou_out[r] = iou;
+  if (!jac_out) return;
+
+  // ---- reverse mode: d iou / d (x1, y1, z1, w1, h1, l1, al1) ---------------------------------------
+  // iou = i3 / u3, u3 = vol1 + vol2 - i3
+  const float g_i3 = 1.f / u3 + i3 / (u3 * u3);            // d iou / d i3 (direct + through u3)
+  const float g_vol1 = -i3 / (u3 * u3);
+  // i3 = (iou2d * u) * zov
+  const float g_zov = g_i3 * (iou2d * u);
+  const float g_iou2d = g_i3 * zov * u;
+  float g_u = g_i3 * zov * iou2d;
+  // iou2d = inter / u ; u = area1 + area2 - inter
+  float g_inter = g_iou2d / u;
+  g_u += -g_iou2d * inter / (u * u);
+  g_inter += -g_u;
+  const float g_area1 = g_u;
+  float gw = g_area1 * h1 + g_vol1 * (h1 * l1);
+  float gh = g_area1 * w1 + g_vol1 * (w1 * l1);
+  float gl = g_vol1 * (w1 * h1);
+  // z overlap
+  float gz = 0.f;
+  {
+    const float g_zraw = zraw >= 0.f ? g_zov : 0.f;
+    const float top1 = zmax1 < zmax2 ? 1.f : (zmax1 == zmax2 ? 0.5f : 0.f);   // d min / d zmax1
+    const float bot1 = zmin1 > zmin2 ? 1.f : (zmin1 == zmin2 ? 0.5f : 0.f);   // d max / d zmin1
+    const float g_zmax1 = g_zraw * top1, g_zmin1 = -g_zraw * bot1;
+    gz = g_zmax1 + g_zmin1;
+    gl += 0.5f * g_zmax1 - 0.5f * g_zmin1;
+  }
+  // area = |total| / 2 -> gradient of every selected slot
+  const float g_total = g_inter * 0.5f * sgn;
+  float gcx[4] = {0.f, 0.f, 0.f, 0.f}, gcy[4] = {0.f, 0.f, 0.f, 0.f};       // wrt the corners of box 1
+#pragma unroll
+  for (int j = 0; j < SV_MAX_IDX; ++j) {
+    // total = sum_j px[j] py[j+1] - py[j] px[j+1]
+    float gx = 0.f, gy = 0.f;
+    if (j + 1 < SV_MAX_IDX) { gx += py[j + 1]; gy -= px[j + 1]; }
+    if (j > 0) { gx -= py[j - 1]; gy += px[j - 1]; }
+    gx *= g_total; gy *= g_total;
+    const int k = order[j];
+    if (!((valid >> k) & 1u)) continue;                   // padded slot: value 0, gradient 0
+    if (k < 4) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (q == k) { gcx[q] += gx; gcy[q] += gy; }
+    } else if (k >= 8) {
+      // P = A + t (B - A), t = den_t / (num + eps); A = r1[i], B = r1[i+1], C / D of box 2 constant
+      const int e = k - 8, i = e >> 2, jj2 = e & 3;
+      F2 A = r1[0], B = r1[1], C = r2[0], D = r2[1];
+      float t = tt[0];
+#pragma unroll
+      for (int q = 0; q < 16; ++q)
+        if (q == e) t = tt[q];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (q == i) { A = r1[q]; B = r1[(q + 1) & 3]; }
+        if (q == jj2) { C = r2[q]; D = r2[(q + 1) & 3]; }
+      }
+      const float ya = C.y - D.y, xb = C.x - D.x;
+      const float num = (A.x - B.x) * ya - (A.y - B.y) * xb + 1e-8f;
+      const float den_t = (A.x - C.x) * ya - (A.y - C.y) * xb;
+      // g_t = gx * (B.x - A.x) + gy * (B.y - A.y)
+      const float g_t = gx * (B.x - A.x) + gy * (B.y - A.y);
+      const float g_den = g_t / num, g_num = -g_t * den_t / (num * num);
+      // direct terms: P.x = A.x (1 - t) + t B.x
+      float gAx = gx * (1.f - t), gAy = gy * (1.f - t), gBx = gx * t, gBy = gy * t;
+      // num = (A.x - B.x) ya - (A.y - B.y) xb ; den_t = (A.x - C.x) ya - (A.y - C.y) xb
+      gAx += g_num * ya + g_den * ya;
+      gAy += -g_num * xb - g_den * xb;
+      gBx += -g_num * ya;
+      gBy += g_num * xb;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (q == i) { gcx[q] += gAx; gcy[q] += gAy; }
+        if (q == ((i + 1) & 3)) { gcx[q] += gBx; gcy[q] += gBy; }
+      }
+    }
+  }
+  // corners of box 1 -> (x, y, w, h, alpha)
+  float gx1 = 0.f, gy1 = 0.f, gal = 0.f;
+  {
+    const float sx[4] = {0.5f, -0.5f, -0.5f, 0.5f}, sy[4] = {0.5f, 0.5f, -0.5f, -0.5f};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float lx = sx[q] * w1, ly = sy[q] * h1;
+      gx1 += gcx[q];
+      gy1 += gcy[q];
+      gw += gcx[q] * (sx[q] * c1) + gcy[q] * (sx[q] * s1);
+      gh += gcx[q] * (-sy[q] * s1) + gcy[q] * (sy[q] * c1);
+      gal += gcx[q] * (-lx * s1 - ly * c1) + gcy[q] * (lx * c1 - ly * s1);
+    }
+  }
+  float *jo = jac_out + r * 7;
+  jo[0] = gx1; jo[1] = gy1; jo[2] = gz; jo[3] = gw; jo[4] = gh; jo[5] = gl; jo[6] = gal;
+}
+
+}  // namespace
+}  // namespace nesie
+
+extern "C" int nesie_iou3d(long long n, const float *box1, const float *box2, float *iou,
+                           float *jac_box1, void *stream) {
+  NESIE_REQUIRE(n >= 0, "negative size");
+  if (n == 0) return NESIE_OK;
+  NESIE_REQUIRE(box1 && box2 && iou, "null pointer");
+  nesie::iou3d_kernel<<<(unsigned)((n + 63) / 64), 64, 0, (cudaStream_t)stream>>>(n, box1, box2, iou, jac_box1);
+  return nesie::check_launch("nesie_iou3d");
+}

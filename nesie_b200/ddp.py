@@ -11,6 +11,10 @@ path is the gradient all-reduce (~12.4 MB fp32).  Here:
   * a post-accumulate hook per parameter counts the bucket's ready gradients; the last one launches
     the bucket's all-reduce on a communication stream, so the head / FP buckets are reduced while
     the backward pass still runs through the SA levels; `finish()` joins the stream;
+  * gradients are not accumulated tensor by tensor: before backward every .grad is None, so autograd
+    hands each parameter its gradient tensor as produced (no `grad += g` launch per parameter, ~190 of
+    them); when a bucket is complete its gradients are copied into the flat slice by ONE multi-tensor
+    copy and the .grad attributes are pointed back at the views for clipping and the optimizer;
   * everything is stream-ordered (no host sync), so a step that calls backward() + finish() can be
     captured in a CUDA graph together with the optimizer;
   * averaging: ReduceOp.AVG on NCCL, SUM then scale on backends without it (gloo in the CPU tests).
@@ -54,26 +58,25 @@ class FlatGradDDP:
         self.device = dev
         pad = lambda n: (n + 63) // 64 * 64      # noqa: E731  every gradient starts 256-byte aligned
         self.flat = torch.zeros(sum(pad(p.numel()) for p in self.params), dtype=torch.float32, device=dev)
-        self.slices, self._bucket_of, off = [], {}, 0
+        self.slices, self._bucket_of, self._view, off = [], {}, {}, 0
         for bi, bucket in enumerate(self.buckets):
             start = off
             for p in bucket:
-                p.grad = self.flat[off:off + p.numel()].view_as(p)
+                self._view[id(p)] = self.flat[off:off + p.numel()].view_as(p)
+                p.grad = self._view[id(p)]
                 self._bucket_of[id(p)] = bi
                 off += pad(p.numel())
             self.slices.append(self.flat[start:off])
+        self._ready = [[] for _ in self.buckets]
         self._pending = [len(b) for b in self.buckets]
         self._launched = [False] * len(self.buckets)
         self.overlap = overlap and dev.type == "cuda" and self.world > 1
         self.comm_stream = torch.cuda.Stream(device=dev) if self.overlap else None
         backend = dist.get_backend(process_group) if self.world > 1 else None
         self._avg = backend == "nccl"
-        self._hooks = []
-        if self.world > 1:
-            for p in self.params:
-                self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
-            if broadcast_parameters:
-                self.broadcast()
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
+        if self.world > 1 and broadcast_parameters:
+            self.broadcast()
 
     # ---- replica consistency --------------------------------------------------------------------
     def broadcast(self, src=0):
@@ -83,10 +86,24 @@ class FlatGradDDP:
 
     # ---- per step ---------------------------------------------------------------------------------
     def zero_grad(self):
-        """Clear the flat buffer (gradients accumulate into its views) and re-arm the buckets."""
+        """Clear the flat buffer, detach every .grad (autograd then assigns instead of adding) and
+        re-arm the buckets."""
         self.flat.zero_()
+        for p in self.params:
+            p.grad = None
         self._pending = [len(b) for b in self.buckets]
         self._launched = [False] * len(self.buckets)
+        self._ready = [[] for _ in self.buckets]
+
+    def _gather(self, bi):
+        """The bucket's fresh gradient tensors -> their views of the flat buffer (one multi-tensor
+        copy); .grad of every parameter of the bucket becomes its view (zeros where no gradient came)."""
+        ready = self._ready[bi]
+        if ready:
+            torch._foreach_copy_([self._view[id(p)] for p in ready], [p.grad for p in ready])
+        for p in self.buckets[bi]:
+            p.grad = self._view[id(p)]
+        self._ready[bi] = []
 
     def _reduce(self, bi):
         buf = self.slices[bi]
@@ -99,10 +116,20 @@ class FlatGradDDP:
 
     def _on_grad(self, p):
         bi = self._bucket_of[id(p)]
+        if p.grad is not self._view[id(p)]:
+            self._ready[bi].append(p)
         self._pending[bi] -= 1
         if self._pending[bi] != 0:
             return
-        if self.overlap:
+        self._flush(bi)
+
+    def _flush(self, bi):
+        """Bucket complete: gather on the producing stream (the fresh gradient tensors are released
+        right afterwards), then exchange on the communication stream."""
+        self._gather(bi)
+        if self.world == 1:
+            self._launched[bi] = True
+        elif self.overlap:
             self.comm_stream.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(self.comm_stream):
                 self._reduce(bi)
@@ -112,19 +139,11 @@ class FlatGradDDP:
     def finish(self):
         """Call after backward(): reduces the buckets whose last gradient never arrived (parameters
         without a gradient this step) and makes the current stream wait for the exchange."""
-        if self.world == 1:
-            return
-        late = [bi for bi, done in enumerate(self._launched) if not done]
+        for bi, done in enumerate(self._launched):
+            if not done:
+                self._flush(bi)
         if self.overlap:
-            if late:
-                self.comm_stream.wait_stream(torch.cuda.current_stream(self.device))
-                with torch.cuda.stream(self.comm_stream):
-                    for bi in late:
-                        self._reduce(bi)
             torch.cuda.current_stream(self.device).wait_stream(self.comm_stream)
-        else:
-            for bi in late:
-                self._reduce(bi)
 
     def remove_hooks(self):
         for h in self._hooks:

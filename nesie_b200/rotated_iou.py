@@ -111,8 +111,45 @@ def oriented_box_intersection_2d(c1, c2, sort_fn=sort_vertices):
     return cross.sum(dim=2).abs() / 2
 
 
+class _IoU3D(Function):
+    """cal_iou_3d as ONE kernel: forward value and d iou / d box1 in the same pass (nesie_iou3d)."""
+
+    @staticmethod
+    def forward(ctx, box1, box2):
+        _lib.need_cuda(box1, box2)
+        shape = box1.shape[:-1]
+        b1 = box1.detach().reshape(-1, 7).contiguous().float()
+        b2 = box2.detach().reshape(-1, 7).contiguous().float()
+        n = b1.shape[0]
+        iou = torch.empty((n,), dtype=torch.float32, device=b1.device)
+        jac = torch.empty((n, 7), dtype=torch.float32, device=b1.device) if box1.requires_grad else None
+        with torch.cuda.device(b1.device):
+            _lib.call("nesie_iou3d", n, _lib.ptr(b1), _lib.ptr(b2), _lib.ptr(iou), _lib.ptr(jac),
+                      _lib.stream())
+        ctx.save_for_backward(jac)
+        ctx.box_shape = box1.shape
+        return iou.view(shape)
+
+    @staticmethod
+    def backward(ctx, grad):
+        (jac,) = ctx.saved_tensors
+        if jac is None:
+            return None, None
+        return (grad.reshape(-1, 1) * jac).view(ctx.box_shape), None
+
+
 def cal_iou_3d(box3d1, box3d2, sort_fn=sort_vertices):
-    """(B, N, 7) x, y, z, w, h, l, alpha boxes -> (B, N) IoU (oriented_iou_loss.py:86-109)."""
+    """(B, N, 7) x, y, z, w, h, l, alpha boxes -> (B, N) IoU (oriented_iou_loss.py:86-109).  On CUDA
+    tensors with the default vertex ordering this is the fused kernel (gradient to box3d1 only: the
+    second box is a target in every loss of the path); `cal_iou_3d_tensor` is the tensor formulation."""
+    if (sort_fn is sort_vertices and box3d1.is_cuda and not box3d2.requires_grad
+            and box3d1.shape[-1] == 7 and box3d1.shape == box3d2.shape):
+        return _IoU3D.apply(box3d1, box3d2)
+    return cal_iou_3d_tensor(box3d1, box3d2, sort_fn)
+
+
+def cal_iou_3d_tensor(box3d1, box3d2, sort_fn=sort_vertices):
+    """The reference's tensor formulation (differentiable with respect to both boxes)."""
     bev = lambda b: torch.cat([b[..., 0:2], b[..., 3:5], b[..., 6:7]], dim=-1)   # noqa: E731  x, y, w, h, alpha
     b1, b2 = bev(box3d1), bev(box3d2)
     zmax1, zmin1 = box3d1[..., 2] + box3d1[..., 5] * 0.5, box3d1[..., 2] - box3d1[..., 5] * 0.5

@@ -62,10 +62,15 @@ def _worker(rank, world, port, out):
     ddp.zero_grad()
     torch.manual_seed(7)
     sum(model.forward_train(pts, gb, gl).values()).backward()
+    for p in ddp.params:                           # without hooks the gradients are plain tensors
+        if p.grad is not None:
+            ddp._view[id(p)].copy_(p.grad)
     local = ddp.flat.clone()
     both = [torch.zeros_like(local) for _ in range(world)]
     dist.all_gather(both, local)
     ddp.flat.copy_(reduced)
+    for p in ddp.params:
+        p.grad = ddp._view[id(p)]
     opt.step()
     flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
     gathered = [torch.zeros_like(flat) for _ in range(world)]
