@@ -68,6 +68,7 @@ class FlatGradDDP:
                 off += pad(p.numel())
             self.slices.append(self.flat[start:off])
         self._ready = [[] for _ in self.buckets]
+        self._events = [[] for _ in self.buckets]
         self._pending = [len(b) for b in self.buckets]
         self._launched = [False] * len(self.buckets)
         self.overlap = overlap and dev.type == "cuda" and self.world > 1
@@ -94,11 +95,15 @@ class FlatGradDDP:
         self._pending = [len(b) for b in self.buckets]
         self._launched = [False] * len(self.buckets)
         self._ready = [[] for _ in self.buckets]
+        self._events = [[] for _ in self.buckets]
 
     def _gather(self, bi):
         """The bucket's fresh gradient tensors -> their views of the flat buffer (one multi-tensor
         copy); .grad of every parameter of the bucket becomes its view (zeros where no gradient came)."""
         ready = self._ready[bi]
+        for ev in self._events[bi]:
+            torch.cuda.current_stream(self.device).wait_event(ev)
+        self._events[bi] = []
         if ready:
             torch._foreach_copy_([self._view[id(p)] for p in ready], [p.grad for p in ready])
         for p in self.buckets[bi]:
@@ -118,6 +123,12 @@ class FlatGradDDP:
         bi = self._bucket_of[id(p)]
         if p.grad is not self._view[id(p)]:
             self._ready[bi].append(p)
+            if self.device.type == "cuda":
+                # the gradient may have been produced on a forked stream (autograd runs a node's
+                # backward on its forward stream): the gather must wait for it
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(self.device))
+                self._events[bi].append(ev)
         self._pending[bi] -= 1
         if self._pending[bi] != 0:
             return

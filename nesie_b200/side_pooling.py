@@ -18,6 +18,8 @@ center / size / heading arrive detached (nesie_head.py:264) and the seeds are de
 (:83-86), so gradients only reach this module's own parameters.  There is no CPU path: the hooks
 `_grid_rows`, `_mini_pointnet`, `_head` are what oracle/side_pooling_ref.py overrides with a CPU
 restatement of the reference arithmetic."""
+import os
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -277,14 +279,46 @@ class SidePooling(nn.Module):
         bbox_rows = self._grid_rows(origin_xyz, origin_features, bbox_grid, center)
         dist_feature = self.dist_feature(end_points, prefix)
 
-        scores = []
-        for i in range(6):
-            feats = self._mini_pointnet(self.mlps_before[i], side_rows[i], g2)    # (B*K, 128)
-            feats = feats.view(B, K, -1).transpose(1, 2)
-            feats = torch.cat((feats, dist_feature[i]), dim=1)
-            scores.append(self._head(self.mlps_head[i], feats))
-        end_points[f"{prefix}side_scores"] = torch.stack(scores, 0)
-        bbox_feats = self._mini_pointnet(self.mlps_before[6], bbox_rows, g3)
-        bbox_feats = bbox_feats.view(B, K, -1).transpose(1, 2)
-        end_points[f"{prefix}iou_scores"] = self._head(self.mlps_head[6], bbox_feats).transpose(2, 1)
+        def branch(i):
+            if i < 6:
+                feats = self._mini_pointnet(self.mlps_before[i], side_rows[i], g2)    # (B*K, 128)
+                feats = feats.view(B, K, -1).transpose(1, 2)
+                feats = torch.cat((feats, dist_feature[i]), dim=1)
+                return self._head(self.mlps_head[i], feats)
+            bbox_feats = self._mini_pointnet(self.mlps_before[6], bbox_rows, g3)
+            bbox_feats = bbox_feats.view(B, K, -1).transpose(1, 2)
+            return self._head(self.mlps_head[6], bbox_feats).transpose(2, 1)
+
+        # tensors made on the caller's stream and read inside a branch (also by the branch's backward)
+        shared = [[side_rows[i], dist_feature] for i in range(6)] + [[bbox_rows]]
+        outs = self._run_branches(branch, 7, size, shared)
+        end_points[f"{prefix}side_scores"] = torch.stack(outs[:6], 0)
+        end_points[f"{prefix}iou_scores"] = outs[6]
         return end_points
+
+    def _run_branches(self, branch, n, like, shared=None):
+        """The seven MiniPointNet + head chains are independent: on CUDA they are issued round-robin
+        on a few forked streams (joined before the results are used), so the dozens of small kernels of
+        one chain overlap the large GEMMs of another, and autograd replays the same concurrency in the
+        backward pass.  Every stream is re-forked from the caller's stream before it is used, which
+        also orders any reuse of the allocator's blocks behind their last reader."""
+        nstreams = int(os.environ.get("NESIE_SIDEPOOL_STREAMS", "3"))
+        if not like.is_cuda or nstreams <= 1:
+            return [branch(i) for i in range(n)]
+        dev = like.device
+        if getattr(self, "_branch_streams", None) is None or len(self._branch_streams) != nstreams \
+                or self._branch_streams[0].device != dev:
+            self._branch_streams = [torch.cuda.Stream(device=dev) for _ in range(nstreams)]
+        main = torch.cuda.current_stream(dev)
+        for st in self._branch_streams:
+            st.wait_stream(main)
+        outs = []
+        for i in range(n):
+            st = self._branch_streams[i % nstreams]
+            for t in (shared[i] if shared else ()):
+                t.record_stream(st)          # the allocator must not recycle them under the branch
+            with torch.cuda.stream(st):
+                outs.append(branch(i))
+        for st in self._branch_streams:
+            main.wait_stream(st)
+        return outs

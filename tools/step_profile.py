@@ -65,3 +65,12 @@ if os.environ.get("NESIE_PROFILE_ATEN"):
     print("\n| aten op | input shapes | us/step | calls |\n|---|---|---:|---:|")
     for e in ev[:40]:
         print(f"| `{e.key}` | `{str(e.input_shapes)[:120]}` | {e.self_device_time_total:.0f} | {e.count} |")
+    tot_n = sum(e.count for e in ev)
+    tot_t = sum(e.self_device_time_total for e in ev)
+    print(f"\nATen ops with device time: {tot_n} calls, {tot_t / 1000:.2f} ms per step; by call count:")
+    by = {}
+    for e in ev:
+        k = (e.key, str(e.input_shapes)[:70])
+        by[k] = by.get(k, 0) + e.count
+    for (k, shp), n in sorted(by.items(), key=lambda kv: -kv[1])[:45]:
+        print(f"  {n:4d}  {k}  {shp}")
