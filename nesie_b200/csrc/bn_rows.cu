@@ -47,14 +47,17 @@ __global__ void __launch_bounds__(BN_THREADS) bn_colsum_kernel(
       is = *reinterpret_cast<const float4 *>(invstd + c);
     }
     for (long long r = (long long)blockIdx.x * rpi + ry; r < R; r += (long long)gridDim.x * rpi) {
-      const float4 y = __ldcs(reinterpret_cast<const float4 *>(Y + r * C + c));
+      // backward: plain loads (the apply kernel that follows walks the rows in reverse and finds the
+      // tail of this sweep still in the 126 MB L2); forward statistics: streaming loads
+      const float4 y = MODE == 0 ? __ldcs(reinterpret_cast<const float4 *>(Y + r * C + c))
+                                 : __ldg(reinterpret_cast<const float4 *>(Y + r * C + c));
       if (MODE == 0) {
         const float dx = y.x - p0.x, dy = y.y - p0.y, dz = y.z - p0.z, dw = y.w - p0.w;
         a1.x += dx; a1.y += dy; a1.z += dz; a1.w += dw;
         a2.x = fmaf(dx, dx, a2.x); a2.y = fmaf(dy, dy, a2.y);
         a2.z = fmaf(dz, dz, a2.z); a2.w = fmaf(dw, dw, a2.w);
       } else {
-        const float4 d = __ldcs(reinterpret_cast<const float4 *>(dA + r * C + c));
+        const float4 d = __ldg(reinterpret_cast<const float4 *>(dA + r * C + c));
         const float gx = fmaf(y.x, sc.x, sh.x) > 0.f ? d.x : 0.f;
         const float gy = fmaf(y.y, sc.y, sh.y) > 0.f ? d.y : 0.f;
         const float gz = fmaf(y.z, sc.z, sh.z) > 0.f ? d.z : 0.f;
@@ -254,8 +257,11 @@ __global__ void __launch_bounds__(BN_THREADS) bn_relu_bwd_apply_kernel(
   const float *mean = stats, *invstd = stats + C, *scale = stats + 2 * C, *shift = stats + 3 * C;
   const int tpr = C >> 2;
   const long long n4 = R * tpr;
-  for (long long i = (long long)blockIdx.x * BN_THREADS + threadIdx.x; i < n4;
-       i += (long long)gridDim.x * BN_THREADS) {
+  // rows from the last to the first: the statistics sweep that ran just before read them in
+  // ascending order, so its most recent ~100 MB are served from L2 here
+  for (long long j = (long long)blockIdx.x * BN_THREADS + threadIdx.x; j < n4;
+       j += (long long)gridDim.x * BN_THREADS) {
+    const long long i = n4 - 1 - j;
     const long long r = i / tpr;
     const int c = (int)(i - r * tpr) * 4;
     const float4 y = __ldcs(reinterpret_cast<const float4 *>(Y) + i);
