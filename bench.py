@@ -56,7 +56,8 @@ WORKLOADS = {
                    name="saqe_stress_fwd_bwd_adamw_b16_per_gpu_100kpts_4096seeds"),
 }
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of gemm_nt_tma_kernel at its largest
-# shape (SA1 layer 3, 524288 x 64 -> 128), ncu --set full capture summarised in profiles/r01_ncu_notes.md
+# HBM-bound shape (SA1 layer 3, 1048576 x 64 -> 128, 805.3 MB algorithmic), ncu --set full capture
+# summarised in profiles/r01_ncu_notes.md; the tensor-bound SidePooling shape is in r02_ncu_notes.md
 GEMM_DRAM_TRAFFIC = 749.8e6
 
 
@@ -247,9 +248,10 @@ def cpu_reference(workload, steps, warmup, scenes=None, forward_only_scene=False
 
 
 def cpu_sample_scenes(workload):
-    """Bounded CPU sample (10-30 s of host work for 1 warm-up + 3 timed steps): 4 scenes per step for
-    the 40k-point workloads, 2 for the 100k-point stress."""
-    return {"stress": 2, "pretrain_conv": 8}.get(workload, 4)
+    """Bounded CPU sample (10-30 s of host work for 1 warm-up + 3 timed steps on the GPU box's 16
+    cores): the full 8-scene batch for the pretrain step, 4 labeled + 4 unlabeled scenes for the
+    mean-teacher step, 2 scenes of the 100k-point stress."""
+    return {"stress": 2, "mean_teacher": 8}.get(workload, 8)
 
 
 def run_reference(args):
@@ -619,6 +621,7 @@ def main():
                     "gemm_wgrad": "gemm_wgrad_tma_kernel (3xTF32 tcgen05 weight gradient)"}[name]
             roofline = {"kernel": kern, "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"],
                         "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": GEMM_DRAM_TRAFFIC,
+                        "traffic_launch": "SA1 layer 3 (1048576 x 64 -> 128): 805.3 MB algorithmic per launch",
                         "peak_source": pk_kind, "weighting": "step-weighted: sum of algorithmic bytes "
                         "4*R*(K+N) of the family's launches in one step / sum of their live-timed durations",
                         "launches_per_step": c["launches"], "kernel_ms_per_step": c["ms"],
