@@ -39,6 +39,8 @@ def supported(x, layers):
             x.is_contiguous() and x.shape[0] >= 2):
         return False
     k = x.shape[1]
+    if k > 512:     # the weight-gradient kernel of the backward pass takes k <= 512 (gemm_3xtf32.cu)
+        return False
     for w, bn in layers:
         n = w.shape[0]
         if w.shape[1] != k or not (bn.training and bn.affine and bn.momentum is not None):

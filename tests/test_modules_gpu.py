@@ -82,6 +82,28 @@ def test_fp_module_forward_backward():
     assert rel_err(sg.grad.cpu(), sc.grad) < 1e-4
 
 
+def test_fp_module_with_more_than_512_input_channels():
+    """A 512 + 256 = 768-channel FP layer: wider than the weight-gradient kernel takes (k <= 512), so the
+    fused GEMM + BatchNorm pipeline must decline it up front and forward AND backward must still work."""
+    torch.manual_seed(5)
+    target, source = torch.rand(2, 256, 3), torch.rand(2, 128, 3)
+    tf, sf = torch.randn(2, 256, 256), torch.randn(2, 512, 128)
+    fp = nb.PointFPModule(mlp_channels=[768, 256, 256])
+    fp_cpu = copy.deepcopy(fp)
+    sc = sf.clone().requires_grad_(True)
+    want = om.fp_forward(fp_cpu, target, source, tf, sc)
+    fp = fp.cuda()
+    sg = sf.cuda().requires_grad_(True)
+    got = fp(target.cuda(), source.cuda(), tf.cuda(), sg)
+    assert rel_err(got.detach().cpu(), want.detach()) < 1e-5
+    g = torch.randn_like(want)
+    want.backward(g)
+    got.backward(g.cuda())
+    assert rel_err(sg.grad.cpu(), sc.grad) < 1e-4
+    for (n1, p1), (n2, p2) in zip(fp.named_parameters(), fp_cpu.named_parameters()):
+        assert n1 == n2 and rel_err(p1.grad.cpu(), p2.grad) < 1e-3, n1
+
+
 @pytest.mark.parametrize("overlap", [True, False])
 def test_backbone_votenet_shape(overlap):
     """PointNet2SASSG at a reduced ScanNet shape (8192 pts) end to end, train-mode BN."""
