@@ -307,6 +307,75 @@ class NesieHead(nn.Module):
         results['side_scores_jitter'], results['side_scores'] = side[:, P:], side[:, :P]
         return results
 
+    # ---- test-time decoding -----------------------------------------------------------------------
+    def _k_points_in_boxes_count(self, points, boxes):
+        """points (B, N, 3) depth frame, boxes (B, P, 7) bottom-centred -> (B, P) points per box
+        (DepthInstance3DBoxes.points_in_boxes: depth -> LiDAR flip + points_in_boxes_batch)."""
+        from .points_in_boxes import points_in_boxes_batch
+        pl = torch.stack([points[..., 1], -points[..., 0], points[..., 2]], dim=-1).contiguous()
+        bl = torch.stack([boxes[..., 1], -boxes[..., 0], boxes[..., 2], boxes[..., 4], boxes[..., 3],
+                          boxes[..., 5], boxes[..., 6]], dim=-1).contiguous()
+        return points_in_boxes_batch(pl, bl).sum(dim=1)
+
+    def _k_aligned_nms(self, boxes, scores, classes, thresh, counts):
+        from .box3d_nms import aligned_3d_nms_batched
+        return aligned_3d_nms_batched(boxes, scores, classes, thresh, counts)
+
+    def get_bboxes(self, points, bbox_preds, input_metas=None, rescale=False, use_nms=True,
+                   use_iou_for_nms=True):
+        """NesieHead.get_bboxes / multiclass_nms_single (nesie_head.py:681-788) for all scenes at once:
+        objectness x IoU score, axis-aligned extent of every (rotated) box, non-empty test (> 5 points
+        inside), class-aware aligned_3d_nms over the non-empty boxes (ONE launch for the batch), score
+        threshold, per-class expansion.  Returns [(boxes (k, 7) bottom-centred, scores (k,), labels (k,))]
+        per scene; the only host sync is the final split into variable-length lists."""
+        cfg = self.test_cfg
+        obj_scores = F.softmax(bbox_preds['obj_scores'], dim=-1)[..., -1]
+        sem_scores = F.softmax(bbox_preds['sem_scores'], dim=-1)
+        bbox3d = bbox_preds['bbox_preds']
+        if use_iou_for_nms:
+            indx = bbox_preds['sem_scores'].argmax(dim=-1, keepdim=True)
+            obj_scores = obj_scores * torch.gather(bbox_preds['iou_scores'], 2, indx).squeeze(-1)
+        if not use_nms:
+            return bbox3d
+        B, P = obj_scores.shape
+        # box_type_3d(bbox, origin=(0.5, 0.5, 0.5)): gravity centre -> bottom centre
+        boxes = bbox3d.clone()
+        boxes[..., 2] = boxes[..., 2] + boxes[..., 5] * (0.0 - 0.5)
+        nonempty = self._k_points_in_boxes_count(points[..., :3].contiguous(), boxes) > 5
+        # corners (depth_box3d.py:51-89) -> axis-aligned min / max
+        dims = boxes[..., 3:6]
+        norm = boxes.new_tensor([[0, 0, 0], [0, 0, 1], [0, 1, 1], [0, 1, 0], [1, 0, 0], [1, 0, 1],
+                                 [1, 1, 1], [1, 1, 0]]) - boxes.new_tensor([0.5, 0.5, 0])
+        corners = dims.unsqueeze(2) * norm.view(1, 1, 8, 3)
+        sin, cos = torch.sin(boxes[..., 6]).unsqueeze(-1), torch.cos(boxes[..., 6]).unsqueeze(-1)
+        cx = corners[..., 0] * cos + corners[..., 1] * sin
+        cy = corners[..., 0] * (-sin) + corners[..., 1] * cos
+        corners = torch.stack([cx, cy, corners[..., 2]], dim=-1) + boxes[..., None, :3]
+        minmax = torch.cat([corners.min(dim=2)[0], corners.max(dim=2)[0]], dim=-1)
+        classes = torch.argmax(sem_scores, -1)
+        # aligned_3d_nms over the non-empty boxes only: compact them to the front (stable)
+        order = torch.argsort((~nonempty).to(torch.int8), dim=1, stable=True)
+        g = lambda t: torch.gather(t, 1, order if t.dim() == 2 else order.unsqueeze(-1).expand(-1, -1, t.shape[-1]))  # noqa: E731
+        keep, keep_cnt = self._k_aligned_nms(g(minmax), g(obj_scores), g(classes), cfg['nms_thr'],
+                                             nonempty.sum(dim=1))
+        valid = torch.arange(P, device=keep.device).unsqueeze(0) < keep_cnt.unsqueeze(1)
+        picked = torch.zeros((B, P + 1), dtype=torch.bool, device=keep.device)
+        src = torch.where(valid, torch.gather(order, 1, keep.clamp(min=0)), torch.full_like(keep, P))
+        picked.scatter_(1, src, True)
+        selected = picked[:, :P] & (obj_scores > cfg['score_thr'])
+        results = []
+        for b in range(B):
+            sel = selected[b]
+            bs, sc, cl = boxes[b][sel], obj_scores[b][sel], classes[b][sel]
+            if cfg.get('per_class_proposal', False):
+                C = sem_scores.shape[-1]
+                sem = sem_scores[b][sel]
+                results.append((bs.repeat(C, 1), (sc.unsqueeze(0) * sem.t()).reshape(-1),
+                                torch.arange(C, device=cl.device).repeat_interleave(bs.shape[0])))
+            else:
+                results.append((bs, sc, cl))
+        return results
+
     # ---- targets --------------------------------------------------------------------------------
     def get_targets_padded(self, points, boxes, labels, valid, bbox_preds, at_seeds=True):
         """points (B, N, >=3); boxes (B, G, 7) bottom-centred, valid rows first; labels (B, G);

@@ -91,6 +91,26 @@ class NesieHeadOracle(NesieHead):
 
     _k_sort_vertices = staticmethod(cpu.sort_vertices)
 
+    def _k_points_in_boxes_count(self, points, boxes):
+        pl = torch.stack([points[..., 1], -points[..., 0], points[..., 2]], dim=-1)
+        bl = torch.stack([boxes[..., 1], -boxes[..., 0], boxes[..., 2], boxes[..., 4], boxes[..., 3],
+                          boxes[..., 5], boxes[..., 6]], dim=-1)
+        return cpu.points_in_boxes_batch(pl, bl).to(points.device).sum(dim=1)
+
+    def _k_aligned_nms(self, boxes, scores, classes, thresh, counts):
+        """aligned_3d_nms per scene (core/post_processing/box3d_nms.py:129-176), numpy restatement."""
+        B, P = scores.shape
+        keep = torch.full((B, P), -1, dtype=torch.long)
+        cnt = torch.zeros((B,), dtype=torch.int32)
+        for b in range(B):
+            n = int(counts[b])
+            if n:
+                k = restate.aligned_3d_nms(boxes[b, :n].detach().cpu().numpy(), scores[b, :n].detach().cpu().numpy(),
+                                           classes[b, :n].cpu().numpy(), thresh)
+                keep[b, :len(k)] = torch.from_numpy(k)
+                cnt[b] = len(k)
+        return keep.to(scores.device), cnt.to(scores.device)
+
     def _k_side_loss(self, surface_pred, box_targets, side_scores, sem_scores, weight):
         lw = self.loss_cfg['surface'].get('loss_weight', 1.0)
         if self.uncertainty == 'saqe':

@@ -206,6 +206,36 @@ def main():
             res = head(feat, "vote", "ScanNet")
         for k in keys:
             out[f"fwd_{mode}_{k}"] = res[k].numpy()
+    # ---- test-time decoding: get_bboxes / multiclass_nms_single (:681-788) ------------------------
+    import types
+    ref_lift.lift(os.path.join(ref_lift.REF, "core/post_processing/box3d_nms.py"), ns, names={"aligned_3d_nms"})
+    g = torch.Generator().manual_seed(SEED + 20)
+    B, N, P = 2, 3000, 48
+    pts = torch.rand(B, N, 3, generator=g) * torch.tensor([4.0, 4.0, 2.0])
+    nclu = 5
+    clu = torch.rand(B, nclu, 3, generator=g) * torch.tensor([3.0, 3.0, 1.0]) + 0.5
+    which = torch.randint(0, nclu, (B, P), generator=g)
+    ctr = torch.gather(clu, 1, which.unsqueeze(-1).expand(-1, -1, 3)) + torch.randn(B, P, 3, generator=g) * 0.1
+    size = torch.rand(B, P, 3, generator=g) * 0.8 + 0.3
+    size[:, ::7] = 0.02                                     # boxes that hold no points
+    yaw = torch.randn(B, P, 1, generator=g) * 0.3
+    preds = dict(bbox_preds=torch.cat([ctr, size, yaw], -1),
+                 obj_scores=torch.randn(B, P, 2, generator=g) * 2,
+                 sem_scores=torch.randn(B, P, NUM_CLASSES, generator=g) * 2,
+                 iou_scores=torch.rand(B, P, NUM_CLASSES, generator=g))
+    for per_class in (True, False):
+        head.test_cfg = types.SimpleNamespace(nms_thr=0.25, score_thr=0.05, per_class_proposal=per_class)
+        metas = [dict(box_type_3d=ns["DepthInstance3DBoxes"]) for _ in range(B)]
+        res = head.get_bboxes(pts, {k: v.clone() for k, v in preds.items()}, metas)
+        tag = f"dec{int(per_class)}"
+        out[f"{tag}_counts"] = np.array([r[1].shape[0] for r in res], dtype=np.int64)
+        out[f"{tag}_boxes"] = torch.cat([r[0].tensor for r in res]).numpy()
+        out[f"{tag}_scores"] = torch.cat([r[1] for r in res]).numpy()
+        out[f"{tag}_labels"] = torch.cat([r[2] for r in res]).numpy()
+        print(tag, "boxes per scene:", out[f"{tag}_counts"])
+    out["dec_points"] = pts.numpy()
+    for k, v in preds.items():
+        out[f"dec_in_{k}"] = v.numpy()
     np.savez_compressed(OUT, **out)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
 

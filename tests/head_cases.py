@@ -96,3 +96,21 @@ def rel_err(a, b):
     a = a.detach().double().cpu() if torch.is_tensor(a) else torch.as_tensor(a).double()
     b = torch.as_tensor(np.asarray(b)).double()
     return float((a - b).abs().max() / max(float(b.abs().max()), 1e-12))
+
+
+def decode_inputs(G, device):
+    preds = {k[len("dec_in_"):]: torch.from_numpy(G[k]).to(device) for k in G.files if k.startswith("dec_in_")}
+    return torch.from_numpy(G["dec_points"]).to(device), preds
+
+
+def check_decoded(G, per_class, results):
+    """get_bboxes results against the reference's: same boxes in the same order, scores to 1e-6."""
+    tag = f"dec{int(per_class)}"
+    counts = [int(c) for c in G[f"{tag}_counts"]]
+    assert [r[1].shape[0] for r in results] == counts
+    o = 0
+    for (b, s, l), n in zip(results, counts):
+        assert torch.equal(l.cpu().long(), torch.from_numpy(G[f"{tag}_labels"][o:o + n]).long())
+        assert torch.allclose(b.cpu(), torch.from_numpy(G[f"{tag}_boxes"][o:o + n]), rtol=1e-6, atol=1e-6)
+        assert torch.allclose(s.cpu(), torch.from_numpy(G[f"{tag}_scores"][o:o + n]), rtol=2e-6, atol=1e-7)
+        o += n

@@ -111,3 +111,16 @@ def test_saqe_uncertainty_weighting():
     (b["surface_loss"] + b["iou_loss"]).backward()
     assert preds["side_scores"].grad is None or float(preds["side_scores"].grad.abs().sum()) == 0.0
     assert float(preds["surface_pred"].grad.abs().sum()) > 0
+
+
+@pytest.mark.parametrize("per_class", [True, False])
+def test_get_bboxes_matches_reference(per_class):
+    """Test-time decoding (get_bboxes / multiclass_nms_single, nesie_head.py:681-788) against the
+    reference's own source: objectness x IoU score, non-empty test, aligned_3d_nms over the non-empty
+    boxes, score threshold, per-class expansion."""
+    from head_cases import check_decoded, decode_inputs
+    torch.manual_seed(0)
+    head = make_head(NesieHeadOracle, 16, 8, test_cfg=dict(nms_thr=0.25, score_thr=0.05, per_class_proposal=per_class))
+    head = head.to(torch.device("cpu"))
+    points, preds = decode_inputs(G, torch.device("cpu"))
+    check_decoded(G, per_class, head.get_bboxes(points, preds))

@@ -157,3 +157,17 @@ def test_fused_iou3d_matches_tensor_formulation():
     assert float((a1.grad - a2.grad).abs().max()) < 2e-5 * scale
     # no gradient requested: forward only
     assert torch.equal(cal_iou_3d(a, b), got.detach())
+
+
+@pytest.mark.parametrize("per_class", [True, False])
+def test_get_bboxes_matches_reference(per_class):
+    """Test-time decoding (get_bboxes / multiclass_nms_single, nesie_head.py:681-788) against the
+    reference's own source: objectness x IoU score, non-empty test, aligned_3d_nms over the non-empty
+    boxes, score threshold, per-class expansion."""
+    from head_cases import check_decoded, decode_inputs
+    from nesie_b200.nesie_head import NesieHead
+    torch.manual_seed(0)
+    head = make_head(NesieHead, 16, 8, test_cfg=dict(nms_thr=0.25, score_thr=0.05, per_class_proposal=per_class))
+    head = head.to(DEV)
+    points, preds = decode_inputs(G, DEV)
+    check_decoded(G, per_class, head.get_bboxes(points, preds))
