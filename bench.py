@@ -439,6 +439,8 @@ def main():
         remaining levels of `nxt` and the first level of `nxt2` on two branches)."""
         cur = torch.cuda.current_stream()
         hook = None
+        if os.environ.get("NESIE_BENCH_SKIP_FPS") == "1":     # diagnostic: the step without any FPS work
+            nxt = nxt2 = None
         if nxt is not None:
             def hook(i):
                 if i == fork_level:

@@ -28,8 +28,18 @@ class FurthestPointSampling(Function):
         if _lib.lib().nesie_fps_needs_temp(B, N, num_points):
             temp = torch.full((B, N), 1e10, dtype=torch.float32, device=points_xyz.device)
         with torch.cuda.device(points_xyz.device):
-            _lib.call("nesie_fps", B, N, num_points, _lib.ptr(points_xyz), _lib.ptr(temp),
-                      _lib.ptr(output), _lib.stream())
+            try:
+                _lib.call("nesie_fps", B, N, num_points, _lib.ptr(points_xyz), _lib.ptr(temp),
+                          _lib.ptr(output), _lib.stream())
+            except RuntimeError:
+                if temp is not None:
+                    raise
+                # the register-resident cluster kernel could not be scheduled (e.g. a cluster of 16 is
+                # refused on this device / MIG slice): the global-memory kernel needs the reference's
+                # `temp` buffer (furthest_point_sample.py:29-30)
+                temp = torch.full((B, N), 1e10, dtype=torch.float32, device=points_xyz.device)
+                _lib.call("nesie_fps", B, N, num_points, _lib.ptr(points_xyz), _lib.ptr(temp),
+                          _lib.ptr(output), _lib.stream())
         ctx.mark_non_differentiable(output)
         return output
 
