@@ -91,6 +91,9 @@ class VoteNet(nn.Module):
             return self.bbox_head(x, self.train_cfg.get('sample_mod', 'vote'),
                                   self.train_cfg.get('dataset_name', 'ScanNet'), jitter_noise=jitter_noise)
 
+    def forward(self, points, **kw):
+        return self.predict(points, **kw)
+
     def forward_train(self, points, gt_bboxes_3d, gt_labels_3d, **kw):
         """points (B, N, 4) or list; per-scene GT lists -> loss dict (list interface)."""
         pts = torch.stack(list(points)) if isinstance(points, (list, tuple)) else points
@@ -225,8 +228,17 @@ class VoteNetNesie(VoteNet):
     unlabeled scene tables the reference's runner attaches (lb_map / ulb_map)."""
 
     def __init__(self, backbone=None, bbox_head=None, train_cfg=None, n_lb=120, n_ulb=1081,
-                 ema=dict(momentum=0.001, interval=1, warm_up=10), quality_poly=(5 / 3, 8 / 3)):
+                 ema=dict(momentum=0.001, interval=1, warm_up=10), quality_poly=(5 / 3, 8 / 3),
+                 teacher_mode='overlap'):
+        """teacher_mode: 'swap' -- the reference's schedule (student forward, swap EMA weights in,
+        teacher forward, swap back); 'overlap' -- the teacher pass reads the EMA copies directly and
+        runs on its own stream BESIDE the student forward (same results: the BatchNorm running
+        statistics, the only state both passes write, are merged afterwards in the reference's
+        student-then-teacher order)."""
         super().__init__(backbone, bbox_head, train_cfg)
+        assert teacher_mode in ('swap', 'overlap')
+        self.teacher_mode = teacher_mode
+        self._overlap = None
         self.n_lb, self.n_ulb = n_lb, n_ulb
         self.quality_poly = quality_poly
         self.ema_cfg = dict(ema)
@@ -240,6 +252,70 @@ class VoteNetNesie(VoteNet):
         """SimiTeacherHook.hooks_before_run: EMA copies of every parameter (call after .to(device))."""
         self.teacher = TeacherEMA(self, **self.ema_cfg)
         return self.teacher
+
+    def _filter_teacher(self, preds_t, aug_t, aug_s):
+        packed = get_pseudo_labels(
+            preds_t, self.ulb_list, self.ulb_flag, self.n_lb, self.n_ulb,
+            num_classes=self.bbox_head.num_classes,
+            thresh_warmup=self.train_cfg.get('thresh_warmup', True),
+            use_cbl=self.train_cfg.get('use_cbl', True), quality_poly=self.quality_poly,
+            as_lists=False)
+        boxes, labels, valid, quality = compact_pseudo_labels(packed)
+        return transformation_bbox_preds(boxes, aug_t, aug_s), labels, valid, quality
+
+    # ---- teacher pass beside the student pass -------------------------------------------------------
+    def _overlap_state(self, dev):
+        if self._overlap is None:
+            bns = [(n, m) for n, m in self.named_modules()
+                   if isinstance(m, nn.modules.batchnorm._BatchNorm) and m.track_running_stats]
+            real, names, mom = [], [], []
+            for n, m in bns:
+                for b in ('running_mean', 'running_var'):
+                    real.append(getattr(m, b))
+                    names.append(f'{n}.{b}')
+                    mom.append(m.momentum)
+            nbt = [m.num_batches_tracked for _, m in bns]
+            self._overlap = dict(
+                stream=torch.cuda.Stream(device=dev), real=real, names=names, keep=[1.0 - x for x in mom],
+                neg_keep=[-(1.0 - x) for x in mom], snap=[t.clone() for t in real],
+                clone=[t.clone() for t in real], nbt=nbt, nbt_names=[f'{n}.num_batches_tracked' for n, _ in bns],
+                nbt_clone=[t.clone() for t in nbt])
+        return self._overlap
+
+    def _teacher_begin(self, points_t, aug_t, aug_s, **kw):
+        """Fork: the teacher forward + pseudo-label filter on the teacher stream, reading the EMA copies
+        through torch.func.functional_call and writing BatchNorm statistics into private clones."""
+        from torch.func import functional_call
+        dev = points_t.device
+        st = self._overlap_state(dev)
+        main = torch.cuda.current_stream(dev)
+        torch._foreach_copy_(st['snap'], st['real'])
+        torch._foreach_copy_(st['clone'], st['real'])
+        torch._foreach_copy_(st['nbt_clone'], st['nbt'])
+        tensors = dict(self.teacher.ema_named_views())
+        tensors.update(zip(st['names'], st['clone']))
+        tensors.update(zip(st['nbt_names'], st['nbt_clone']))
+        st['stream'].wait_stream(main)
+        cross = [points_t] + [t for a in (aug_t, aug_s) if a is not None
+                              for t in (a.hf, a.vf, a.rot, a.scale, a.trans)]
+        cross += [t for v in kw.values() if isinstance(v, (list, tuple)) for t in v if torch.is_tensor(t)]
+        for t in cross:
+            t.record_stream(st['stream'])
+        with torch.cuda.stream(st['stream']), torch.no_grad():
+            preds_t = functional_call(self, tensors, (points_t,), kw)
+            out = self._filter_teacher(preds_t, aug_t, aug_s)
+        return out
+
+    def _teacher_end(self, dev):
+        """Join, then merge the running statistics as if the teacher pass had run after the student
+        pass: r <- (1 - m) r_student + (r_teacher_clone - (1 - m) r_before)."""
+        st = self._overlap
+        torch.cuda.current_stream(dev).wait_stream(st['stream'])
+        torch._foreach_mul_(st['real'], st['keep'])
+        torch._foreach_add_(st['real'], st['clone'])
+        torch._foreach_mul_(st['snap'], st['neg_keep'])
+        torch._foreach_add_(st['real'], st['snap'])
+        torch._foreach_add_(st['nbt'], 1)
 
     def teacher_pseudo_labels(self, points_t, aug_t=None, aug_s=None, **kw):
         """no_grad teacher pass -> padded pseudo boxes in the student frame."""
@@ -264,9 +340,15 @@ class VoteNetNesie(VoteNet):
         labeled rows (len(sup_index), G, .); sup_index / unsup_index: int64 row indices of the labeled /
         unlabeled scenes; ulb_positions (len(unsup_index),) int64 rows of the unlabeled scenes in the
         class-count table."""
-        preds_s = self.predict(points_s, **(student_kw or {}))
-        pl_boxes, pl_labels, pl_valid, pl_quality = self.teacher_pseudo_labels(
-            points_t, aug_t, aug_s, **(teacher_kw or {}))
+        if self.teacher_mode == 'overlap' and points_t.is_cuda:
+            pl_boxes, pl_labels, pl_valid, pl_quality = self._teacher_begin(
+                points_t, aug_t, aug_s, **(teacher_kw or {}))
+            preds_s = self.predict(points_s, **(student_kw or {}))
+            self._teacher_end(points_t.device)
+        else:
+            preds_s = self.predict(points_s, **(student_kw or {}))
+            pl_boxes, pl_labels, pl_valid, pl_quality = self.teacher_pseudo_labels(
+                points_t, aug_t, aug_s, **(teacher_kw or {}))
         head = self.bbox_head
         sup = head.loss_padded(choose_items(preds_s, sup_index), points_s.index_select(0, sup_index),
                                gt_boxes, gt_labels, gt_valid)

@@ -306,19 +306,23 @@ class SidePooling(nn.Module):
         if not like.is_cuda or nstreams <= 1:
             return [branch(i) for i in range(n)]
         dev = like.device
-        if getattr(self, "_branch_streams", None) is None or len(self._branch_streams) != nstreams \
-                or self._branch_streams[0].device != dev:
-            self._branch_streams = [torch.cuda.Stream(device=dev) for _ in range(nstreams)]
         main = torch.cuda.current_stream(dev)
-        for st in self._branch_streams:
+        # one set of branch streams per calling stream (the teacher pass of the mean-teacher step runs
+        # on its own stream beside the student pass)
+        pool = self.__dict__.setdefault("_branch_pool", {})
+        key = (dev.index, main.cuda_stream, nstreams)
+        if key not in pool:
+            pool[key] = [torch.cuda.Stream(device=dev) for _ in range(nstreams)]
+        streams = pool[key]
+        for st in streams:
             st.wait_stream(main)
         outs = []
         for i in range(n):
-            st = self._branch_streams[i % nstreams]
+            st = streams[i % nstreams]
             for t in (shared[i] if shared else ()):
                 t.record_stream(st)          # the allocator must not recycle them under the branch
             with torch.cuda.stream(st):
                 outs.append(branch(i))
-        for st in self._branch_streams:
+        for st in streams:
             main.wait_stream(st)
         return outs

@@ -53,6 +53,12 @@ class TeacherEMA:
             out[f"ema_{name.replace('.', '_')}"] = self.flat_ema[off:off + p.numel()].view_as(p.data)
         return out
 
+    def ema_named_views(self):
+        """{parameter name: EMA copy (a view of the flat buffer, shaped like the parameter)}: what
+        torch.func.functional_call needs to run the module as the teacher without swapping."""
+        return {name: self.flat_ema[off:off + p.numel()].view_as(p.data)
+                for name, p, off in zip(self.names, self.params, self.offsets)}
+
     def load_ema_state_dict(self, state, strict=True):
         """Fill the EMA copies from `ema_*` entries of a reference checkpoint (the hook registers them
         as model buffers, simi_teacher_hook.py:47-51, so `epoch_N.pth` / `epoch_N_ema.pth` carry

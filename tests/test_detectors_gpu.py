@@ -68,7 +68,8 @@ def test_votenet_pretrain_step_matches_cpu_twin():
     assert cos > 0.9999, float(cos)
 
 
-def test_mean_teacher_step_matches_cpu_twin():
+@pytest.mark.parametrize("teacher_mode", ["overlap", "swap"])
+def test_mean_teacher_step_matches_cpu_twin(teacher_mode):
     from nesie_b200 import targets as T
     from nesie_b200.detectors import BoxAug, VoteNetNesie, transform_boxes
     from nesie_b200.synthetic import make_batch
@@ -77,7 +78,7 @@ def test_mean_teacher_step_matches_cpu_twin():
     torch.manual_seed(4)
     kw = dict(n_lb=6, n_ulb=20)
     ref = tiny_votenet(lambda **k: VoteNetNesieRef(**k, **kw))
-    gpu = tiny_votenet(lambda **k: VoteNetNesie(**k, **kw))
+    gpu = tiny_votenet(lambda **k: VoteNetNesie(**k, teacher_mode=teacher_mode, **kw))
     for m in (ref, gpu):
         _liven(m)
         m.train_cfg.update(use_cbl=False)
@@ -109,6 +110,13 @@ def test_mean_teacher_step_matches_cpu_twin():
     for k in want:
         assert abs(float(got[k]) - float(want[k])) < 1e-5 * max(scale, 1.0), (k, float(got[k]), float(want[k]))
     assert torch.equal(gpu.ulb_list.cpu(), ref.ulb_list) and torch.equal(gpu.ulb_flag.cpu(), ref.ulb_flag)
+    # BatchNorm running statistics: written by the student AND the teacher pass (in that order)
+    for (n1, b1), (n2, b2) in zip(gpu.named_buffers(), ref.named_buffers()):
+        assert n1 == n2
+        if n1.endswith("num_batches_tracked"):
+            assert int(b1) == int(b2) == 2, n1
+        elif "running_" in n1:
+            assert float((b1.cpu() - b2).abs().max()) < 1e-5 * max(float(b2.abs().max()), 1.0), n1
     # optimizer + EMA: weights and teacher copies stay together
     for m, losses in ((ref, want), (gpu, got)):
         opt = torch.optim.AdamW(m.parameters(), lr=0.008, weight_decay=0.01)
