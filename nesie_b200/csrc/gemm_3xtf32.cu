@@ -805,10 +805,20 @@ extern "C" int nesie_gemm_nt_3xtf32_fused(long long r, int n, int k, const float
   return gemm_nt_impl(r, n, k, a, lda, b_image, c, ldc, pro_scale, pro_shift, col_stats, stream);
 }
 
+// B channels per CTA: the whole (padded) K up to 128 channels, 128-channel parts beyond
+// (NESIE_WGRAD_KSPLIT=0 keeps K whole)
+static int wgrad_kpart(int k) {
+  static int ksplit = -1;
+  if (ksplit < 0) { const char *e = getenv("NESIE_WGRAD_KSPLIT"); ksplit = e ? atoi(e) : 1; }
+  const int kp = (k + 31) & ~31;
+  return (ksplit && kp > 128) ? 128 : kp;
+}
+
 // row chunks (one TMEM accumulation each) and CTAs along x (one partial block each)
-static void wgrad_plan(long long r, int n, int *chunk, int *nchunks, int *gx) {
+static void wgrad_plan(long long r, int n, int k, int *chunk, int *nchunks, int *gx) {
   const long long nslab = (r + 31) / 32;
-  const int mblocks = (n + 127) / 128;
+  const int kp = (k + 31) & ~31, kpart = wgrad_kpart(k);
+  const int mblocks = ((n + 127) / 128) * ((kp + kpart - 1) / kpart);   // CTAs per row chunk
   *chunk = wgrad_chunk(nslab, mblocks);
   *nchunks = (int)((nslab + *chunk - 1) / *chunk);
   int g = gemm_grid_sms() / mblocks;
@@ -818,10 +828,9 @@ static void wgrad_plan(long long r, int n, int *chunk, int *nchunks, int *gx) {
 }
 
 extern "C" int nesie_gemm_wgrad_splits(long long r, int n, int k) {
-  (void)k;
   if (r <= 0 || n <= 0) return 0;
   int chunk, nchunks, gx;
-  wgrad_plan(r, n, &chunk, &nchunks, &gx);
+  wgrad_plan(r, n, k, &chunk, &nchunks, &gx);
   return gx;  // one partial block per CTA
 }
 
@@ -838,9 +847,10 @@ static int gemm_wgrad_impl(long long r, int n, int k, const float *a, long long 
         make_tmap(&tb, b, r, k, ldb, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) {
       WgradTmaParams q;
       q.R = (int)r; q.N = n; q.K = k; q.kp = (k + 31) & ~31; q.P = partials;
+      q.kpart = wgrad_kpart(k);
       q.pro_scale = pro_scale; q.pro_shift = pro_shift;
       { const char *e = getenv("NESIE_GEMM_DBG"); q.dbg = e ? atoi(e) : 0; }
-      const size_t stage = 2 * (size_t)(4 * 4096) + 2 * (size_t)(q.kp >> 5) * 4096;
+      const size_t stage = 2 * (size_t)(4 * 4096) + 2 * (size_t)(q.kpart >> 5) * 4096;
       q.nstages = (int)((gemm_smem_budget()) / stage);
       if (q.nstages > G_MAXSTAGES) q.nstages = G_MAXSTAGES;
       NESIE_REQUIRE(q.nstages >= 1, "k too large for shared memory");
@@ -849,9 +859,9 @@ static int gemm_wgrad_impl(long long r, int n, int k, const float *a, long long 
       auto kern = regs == 64 ? gemm_wgrad_tma_kernel<64> : (regs == 88 ? gemm_wgrad_tma_kernel<88> : gemm_wgrad_tma_kernel<96>);
       NESIE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G_MAX_DYN_SMEM));
       int gx;
-      wgrad_plan(r, n, &q.chunk, &q.nchunks, &gx);
-      const int mblocks = (n + 127) / 128;
-      kern<<<dim3(gx, mblocks), T_THREADS, smem, (cudaStream_t)stream>>>(ta, tb, q);
+      wgrad_plan(r, n, k, &q.chunk, &q.nchunks, &gx);
+      const int mblocks = (n + 127) / 128, kblocks = (q.kp + q.kpart - 1) / q.kpart;
+      kern<<<dim3(gx, mblocks, kblocks), T_THREADS, smem, (cudaStream_t)stream>>>(ta, tb, q);
       return check_launch("nesie_gemm_wgrad_3xtf32");
     }
   }
@@ -869,7 +879,7 @@ static int gemm_wgrad_impl(long long r, int n, int k, const float *a, long long 
   NESIE_CUDA(cudaFuncSetAttribute(gemm_wgrad_3xtf32_kernel,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, G_MAX_DYN_SMEM));
   int gx;
-  wgrad_plan(r, n, &p.chunk, &p.nchunks, &gx);
+  wgrad_plan(r, n, k, &p.chunk, &p.nchunks, &gx);
   p.vec = ((lda & 3) == 0) && ((ldb & 3) == 0) && ((n & 3) == 0) && ((k & 3) == 0) &&
           (((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0);
   p.mn = p.vec ? 3 : 0;

@@ -331,6 +331,7 @@ gemm_nt_tma_kernel(const __grid_constant__ CUtensorMap tmA, GemmTmaParams p) {
 struct WgradTmaParams {
   int R, N, K;
   int kp;            // K rounded up to 32
+  int kpart;         // B channels per CTA along gridDim.z (= kp when the K dimension is not split)
   int nstages;
   float *P;          // [gridDim.x][N][K] partial sums, one block per CTA
   int nchunks, chunk;
@@ -350,12 +351,18 @@ gemm_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   __shared__ unsigned s_tmem;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nacc = p.kp <= 256 ? 2 : 1;     // TMEM accumulators (double-buffered when they fit)
+  // K split (gridDim.z > 1): a CTA owns `kpart` of the B channels.  Wide B tiles leave room for only two
+  // pipeline stages next to the raw + lo copies (96 KB per stage at K = 256) and the TMA round trip is
+  // then exposed; 128-channel parts fit three stages and two TMEM accumulators, at the price of loading
+  // the A tile once per part.
+  const int k0 = blockIdx.z * p.kpart;      // first channel of B handled by this CTA
+  const int kpl = min(p.kpart, p.kp - k0);  // its (padded) channel count
+  const int nacc = p.kpart <= 256 ? 2 : 1;  // TMEM accumulators (double-buffered when they fit)
   const int m0 = blockIdx.y * 128;          // first channel of A handled by this CTA
   const int ma = min(4, (p.N - m0 + 31) >> 5);  // 32-channel blocks of A that exist
-  const int nb = p.kp >> 5;                 // 32-channel blocks of B
+  const int nb = kpl >> 5;                  // 32-channel blocks of B
   const int a_part = 128 * 128;             // A tile: 4 blocks x (32 rows x 128 B)
-  const int b_part = p.kp * 128;
+  const int b_part = p.kpart * 128;
   const int stage_bytes = 2 * a_part + 2 * b_part;   // A raw, A lo, B raw, B lo
   const int nslab = (p.R + 31) >> 5;        // reduction slabs of 32 rows
   const unsigned smem_base = g_smem_u32(smem);
@@ -403,7 +410,7 @@ gemm_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           // box = 32 channels x 32 rows = one 4 KB column of SW128_32B atoms; rows >= R and
           // channels beyond the tensor arrive as zeros
           for (int m = 0; m < ma; ++m) g_tma_2d(sa + (unsigned)m * 4096u, &tmA, m0 + 32 * m, slab * 32, bar);
-          for (int c = 0; c < nb; ++c) g_tma_2d(sb + (unsigned)c * 4096u, &tmB, 32 * c, slab * 32, bar);
+          for (int c = 0; c < nb; ++c) g_tma_2d(sb + (unsigned)c * 4096u, &tmB, k0 + 32 * c, slab * 32, bar);
         }
       }
     }
@@ -443,7 +450,7 @@ gemm_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll
             for (int i = 0; i < 4; ++i)
               if (c + i < nb) {
-                const int ch = (c + i) * 32 + bch;
+                const int ch = k0 + (c + i) * 32 + bch;
                 float4 hi, lo;
                 bn_relu_split4(v[i], ldg4_guard(p.pro_scale, ch, p.K), ldg4_guard(p.pro_shift, ch, p.K), hi, lo);
                 g_sts128(sb + (c + i) * 4096, hi);
@@ -469,7 +476,7 @@ gemm_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     unsigned it = 0, ccount = 0;
     long long w_acce = 0, w_full = 0, w_issue = 0, t_begin = clock64();
     const unsigned major_bits = (1u << 15) | (1u << 16);  // A and B MN-major
-    const unsigned idesc0 = g_idesc(128, p.kp <= 256 ? p.kp : 256) | major_bits;
+    const unsigned idesc0 = g_idesc(128, kpl <= 256 ? kpl : 256) | major_bits;
     for (int chunk = blockIdx.x; chunk < p.nchunks; chunk += gridDim.x, ++ccount) {
       const int acc = nacc == 2 ? (int)(ccount & 1) : 0;
       const unsigned dbase = tmem + (unsigned)(acc * 256);
@@ -498,13 +505,13 @@ gemm_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           for (int ks = 0; ks < 4; ++ks) {  // 8 reduction rows = two 512-byte K atoms = 64 units
             const unsigned long long o = (unsigned long long)(ks * 64);
             const unsigned accum = (first && ks == 0) ? 0u : 1u;
-            if (p.kp <= 256) {
+            if (kpl <= 256) {
               g_mma(dbase, ah0 + o, bh0 + o, idesc0, accum);
               g_mma(dbase, ah0 + o, bl0 + o, idesc0, 1u);
               g_mma(dbase, al0 + o, bh0 + o, idesc0, 1u);
             } else {
-              for (int n0 = 0; n0 < p.kp; n0 += 256) {
-                const int nn = min(256, p.kp - n0);
+              for (int n0 = 0; n0 < kpl; n0 += 256) {
+                const int nn = min(256, kpl - n0);
                 const unsigned idesc = g_idesc(128, nn) | major_bits;
                 const unsigned long long bn = o + (unsigned long long)(n0 * 8);  // n0 * 128 bytes >> 4
                 const unsigned d = dbase + (unsigned)n0;
@@ -539,9 +546,10 @@ gemm_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       // One partial block per CTA: the chunks a CTA processes are added (round-to-nearest fp32,
       // fixed order) into its own block, which stays in L2 between chunks; the thread that owns
       // an element is the only one that ever touches it.
-      float *prow = p.P + ((size_t)blockIdx.x * p.N + n) * p.K;
+      float *prow = p.P + ((size_t)blockIdx.x * p.N + n) * p.K + k0;   // this CTA's column range
+      const int kleft = p.K - k0;                                        // columns that exist from k0 on
       const bool addto = ccount > 0;
-      for (int c0 = 0; c0 < p.kp; c0 += 32) {
+      for (int c0 = 0; c0 < kpl; c0 += 32) {
         unsigned v[32];
         g_tmem_ld32(tmem + (unsigned)(acc * 256 + c0) + ((unsigned)(warp * 32) << 16), v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -550,18 +558,18 @@ gemm_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             float4 old[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              old[j] = (addto && c0 + 4 * j < p.K) ? *reinterpret_cast<const float4 *>(prow + c0 + 4 * j)
-                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+              old[j] = (addto && c0 + 4 * j < kleft) ? *reinterpret_cast<const float4 *>(prow + c0 + 4 * j)
+                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              if (c0 + 4 * j < p.K)
+              if (c0 + 4 * j < kleft)
                 *reinterpret_cast<float4 *>(prow + c0 + 4 * j) =
                     make_float4(old[j].x + __uint_as_float(v[4 * j]), old[j].y + __uint_as_float(v[4 * j + 1]),
                                 old[j].z + __uint_as_float(v[4 * j + 2]), old[j].w + __uint_as_float(v[4 * j + 3]));
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (c0 + j < p.K) prow[c0 + j] = (addto ? prow[c0 + j] : 0.f) + __uint_as_float(v[j]);
+              if (c0 + j < kleft) prow[c0 + j] = (addto ? prow[c0 + j] : 0.f) + __uint_as_float(v[j]);
           }
         }
       }
