@@ -805,19 +805,24 @@ extern "C" int nesie_gemm_nt_3xtf32_fused(long long r, int n, int k, const float
   return gemm_nt_impl(r, n, k, a, lda, b_image, c, ldc, pro_scale, pro_shift, col_stats, stream);
 }
 
-// B channels per CTA: the whole (padded) K up to 128 channels, 128-channel parts beyond
-// (NESIE_WGRAD_KSPLIT=0 keeps K whole)
-static int wgrad_kpart(int k) {
+// B channels per CTA along gridDim.z.  The kernel is bound by shared-memory traffic (TMA fill + the
+// hi / lo transform's read and write + the operand reads of 12 MMAs per slab: profiles/r02_ncu_notes.md),
+// so splitting K only pays where it buys parallelism or a third pipeline stage without multiplying
+// whole CTAs on a sliver of channels: K a multiple of 128, and either two A blocks (N > 128) or few
+// rows (measured per shape; NESIE_WGRAD_KSPLIT=0 keeps K whole, =2 always splits beyond 128).
+static int wgrad_kpart(long long r, int n, int k) {
   static int ksplit = -1;
   if (ksplit < 0) { const char *e = getenv("NESIE_WGRAD_KSPLIT"); ksplit = e ? atoi(e) : 1; }
   const int kp = (k + 31) & ~31;
-  return (ksplit && kp > 128) ? 128 : kp;
+  if (!ksplit || kp <= 128) return kp;
+  if (ksplit == 2) return 128;
+  return (kp % 128 == 0 && (n > 128 || r <= 16384)) ? 128 : kp;
 }
 
 // row chunks (one TMEM accumulation each) and CTAs along x (one partial block each)
 static void wgrad_plan(long long r, int n, int k, int *chunk, int *nchunks, int *gx) {
   const long long nslab = (r + 31) / 32;
-  const int kp = (k + 31) & ~31, kpart = wgrad_kpart(k);
+  const int kp = (k + 31) & ~31, kpart = wgrad_kpart(r, n, k);
   const int mblocks = ((n + 127) / 128) * ((kp + kpart - 1) / kpart);   // CTAs per row chunk
   *chunk = wgrad_chunk(nslab, mblocks);
   *nchunks = (int)((nslab + *chunk - 1) / *chunk);
@@ -847,7 +852,7 @@ static int gemm_wgrad_impl(long long r, int n, int k, const float *a, long long 
         make_tmap(&tb, b, r, k, ldb, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) {
       WgradTmaParams q;
       q.R = (int)r; q.N = n; q.K = k; q.kp = (k + 31) & ~31; q.P = partials;
-      q.kpart = wgrad_kpart(k);
+      q.kpart = wgrad_kpart(r, n, k);
       q.pro_scale = pro_scale; q.pro_shift = pro_shift;
       { const char *e = getenv("NESIE_GEMM_DBG"); q.dbg = e ? atoi(e) : 0; }
       const size_t stage = 2 * (size_t)(4 * 4096) + 2 * (size_t)(q.kpart >> 5) * 4096;
