@@ -280,7 +280,7 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # per-shape census of the GEMM kernels of one step (roofline)
 # ------------------------------------------------------------------------------------------------
-def gemm_census(trace, dev, min_reps=5):
+def gemm_census(trace, dev, min_reps=5, hbm_gbs=6459.6, bf16_tflops=1684.1):
     """trace: [(entry point, args)] of one eager step.  Times every distinct GEMM launch shape live
     (back to back, CUDA events) and returns per-family step-weighted numbers."""
     from nesie_b200 import _lib
@@ -334,7 +334,10 @@ def gemm_census(trace, dev, min_reps=5):
         if os.environ.get("NESIE_BENCH_CENSUS_DUMP"):
             sys.stderr.write(f"[census] {family} R={R} K={K} N={N} x{count}: {ms * 1e3:.1f} us, "
                              f"{per / (ms * 1e-3) / 1e9:.0f} GB/s, {2.0 * R * N * K / (ms * 1e-3) / 1e12:.1f} TF/s fp32-equiv\n")
-        f = out.setdefault(family, dict(bytes=0.0, ms=0.0, launches=0, flops=0.0, best=None))
+        f = out.setdefault(family, dict(bytes=0.0, ms=0.0, launches=0, flops=0.0, best=None, bound_ms=0.0))
+        # per-launch lower bound: HBM time of the algorithmic bytes vs tensor time of the 3 TF32 MMAs per
+        # fp32 product at half the measured bf16 rate
+        f["bound_ms"] += count * max(per / (hbm_gbs * 1e9), 3 * 2.0 * R * N * K / (bf16_tflops / 2 * 1e12)) * 1e3
         f["bytes"] += count * per
         f["ms"] += count * ms
         f["launches"] += count
@@ -614,7 +617,7 @@ def main():
     pk, pk_kind = peaks()
     roofline = None
     if rank == 0 and not args.no_census:
-        census = gemm_census(trace, dev)
+        census = gemm_census(trace, dev, hbm_gbs=pk["hbm_gbs"], bf16_tflops=pk["bf16_tflops"])
         if census:
             name = max(census, key=lambda k: census[k]["ms"])
             c = census[name]
@@ -629,11 +632,13 @@ def main():
                         "launches_per_step": c["launches"], "kernel_ms_per_step": c["ms"],
                         "algorithmic_bytes_per_step": c["bytes"],
                         "tensor_tflops_fp32_equiv": c["flops"] / (c["ms"] * 1e-3) / 1e12,
+                        "frac_of_max_hbm_tensor_bound": c["bound_ms"] / c["ms"],
                         "best_shape": c["best"],
                         "best_shape_frac": (c["best"]["gbs"] / pk["hbm_gbs"]) if c["best"] else None,
                         "families": {k: dict(ms_per_step=v["ms"], launches=v["launches"],
                                              gbs=v["bytes"] / (v["ms"] * 1e-3) / 1e9,
-                                             frac=v["bytes"] / (v["ms"] * 1e-3) / 1e9 / pk["hbm_gbs"])
+                                             frac=v["bytes"] / (v["ms"] * 1e-3) / 1e9 / pk["hbm_gbs"],
+                                             frac_of_max_hbm_tensor_bound=v["bound_ms"] / v["ms"])
                                      for k, v in census.items()}}
 
     line = {"metric": "train_scenes_per_s", "value": value, "unit": "scenes/s", "n_gpus": world,
