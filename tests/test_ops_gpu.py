@@ -67,6 +67,30 @@ def test_fps_stress_shape_100k():
     assert torch.equal(got[:1].cpu(), cpu.furthest_point_sample(xyz[:1], 512))
 
 
+def test_stress_shape_op_chain_vs_reference_kernels():
+    """BASELINE configs[4] (SAQE stress): 100 000-point scenes, 4096 SA1 centres, 64 samples.  The whole
+    SA1 operator chain -- FPS, centre gather, ball query, grouping -- bit-exact against the reference's
+    own kernels on the same GPU, plus size-independent properties."""
+    pts = make_batch(2, 100000, seed0=70)[0]
+    xyz = dev(pts[..., :3].contiguous())
+    feats = dev(pts[..., 3:].transpose(1, 2).contiguous())
+    idx = nb.furthest_point_sample(xyz, 4096)
+    assert (idx[:, 0] == 0).all()
+    assert all(idx[b].unique().numel() >= 4096 - 40 for b in range(2))     # duplicates only at exact ties
+    centres = nb.gather_points(xyz.transpose(1, 2).contiguous(), idx).transpose(1, 2).contiguous()
+    bq = nb.ball_query(0.0, 0.2, 64, xyz, centres)
+    d2 = ((torch.gather(xyz, 1, bq.long().reshape(2, -1, 1).expand(-1, -1, 3)).view(2, 4096, 64, 3)
+           - centres.unsqueeze(2)) ** 2).sum(-1)
+    assert float(d2.max()) < 0.2 ** 2 * (1 + 1e-6)                          # every hit inside the ball
+    assert (bq[..., 1:] >= bq[..., :1]).all()                              # slots start from the first hit
+    g = nb.grouping_operation(feats, bq)
+    assert torch.equal(g, torch.gather(feats, 2, bq.long().reshape(2, 1, -1)).view(2, 1, 4096, 64))
+    if ref_cuda.available():
+        assert torch.equal(idx, ref_cuda.furthest_point_sample(xyz, 4096))
+        assert torch.equal(bq, ref_cuda.ball_query(0.0, 0.2, 64, xyz, centres))
+        assert torch.equal(g, ref_cuda.grouping_operation(feats, bq))
+
+
 def test_fps_generic_fallback_large_n():
     xyz = torch.rand(1, 140000, 3)
     got = nb.furthest_point_sample(dev(xyz), 40)

@@ -67,3 +67,27 @@ def test_teacher_ema_matches_reference_hook():
     ema.load_ema_state_dict(state)
     for k, v in ema.ema_state_dict().items():
         assert torch.equal(v, state[k])
+
+
+def test_scene_batcher_and_views_on_the_device(tmp_path):
+    """SURVEY 8f-4 on the GPU: `.bin` scenes -> pinned host -> device sampling -> the two augmented
+    views of a mean-teacher batch; a box centre moves like the point at its centre."""
+    import numpy as np
+    from nesie_b200 import data
+    from nesie_b200.detectors import transform_boxes
+    files = []
+    rng = np.random.default_rng(0)
+    for i in range(4):
+        f = str(tmp_path / f"s{i}.bin")
+        data.save_points(f, rng.normal(size=(60000 if i % 2 else 30000, 6)).astype(np.float32))
+        files.append(f)
+    pts, choices = next(iter(data.SceneBatcher(files, num_points=40000, batch_size=4, device=DEV)))
+    assert pts.shape == (4, 40000, 4) and pts.is_cuda
+    assert choices[1].unique().numel() == 40000 and choices[0].unique().numel() < 40000
+    ref = torch.from_numpy(data.load_points(files[1])).to(DEV)
+    assert torch.equal(pts[1], ref[choices[1]])
+    boxes = torch.rand(4, 6, 7, device=DEV)
+    v = data.mean_teacher_views(pts, boxes, torch.Generator().manual_seed(2))
+    assert torch.allclose(transform_boxes(boxes, v["aug_s"])[..., :3],
+                          v["aug_s"].apply_points(boxes[..., :3]), atol=1e-6)
+    assert torch.equal(v["points_s"][..., 3], pts[..., 3])
