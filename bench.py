@@ -386,11 +386,12 @@ def main():
 
     torch.manual_seed(0)
     model = build_model(wl).to(dev)
+    # flat gradient AND parameter buffers (bucketed all-reduce, broadcast of rank 0): AdamW, clipping and
+    # the teacher EMA are one elementwise launch each over the flat buffers
+    ddp = FlatGradDDP(model, flatten_parameters=True)
     if wl == "mean_teacher":
-        model.init_teacher()             # re-homes the parameters into one flat buffer
-    ddp = FlatGradDDP(model)             # flat gradient buffer, bucketed all-reduce, broadcast of rank 0
-    params = ddp.params
-    opt = torch.optim.AdamW(params, lr=0.008, weight_decay=0.01, fused=True, capturable=True)
+        model.init_teacher(flat=ddp)
+    opt = torch.optim.AdamW([ddp.flat_parameter()], lr=0.008, weight_decay=0.01, fused=True, capturable=True)
     backbone = model.backbone
     static = None
     if wl == "mean_teacher":
@@ -461,7 +462,7 @@ def main():
         loss = step_loss(wl, model, slot["inp"], slot["fps"], hook, static)
         loss.backward()
         ddp.finish()
-        torch.nn.utils.clip_grad_norm_(params, 10.0)
+        ddp.clip_grad_norm_(10.0)
         opt.step()
         if wl == "mean_teacher":
             model.after_train_iter(10 + step_no["n"])   # past the warm-up: constant momentum 0.001

@@ -46,7 +46,11 @@ def default_buckets(model, bucket_bytes=4 << 20):
 class FlatGradDDP:
 
     def __init__(self, model, process_group=None, bucket_bytes=4 << 20, buckets=None,
-                 broadcast_parameters=True, overlap=True):
+                 broadcast_parameters=True, overlap=True, flatten_parameters=False):
+        """flatten_parameters: also re-home every parameter into ONE flat buffer with the layout of the
+        gradient buffer (`flat_params`; the modules keep working on views).  AdamW, gradient clipping
+        and the teacher EMA are elementwise over all parameters, so with `flat_parameter()` they
+        become one launch each instead of a multi-tensor sweep over ~190 tensors."""
         self.model = model
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
@@ -67,6 +71,15 @@ class FlatGradDDP:
                 self._bucket_of[id(p)] = bi
                 off += pad(p.numel())
             self.slices.append(self.flat[start:off])
+        self.flat_params = None
+        if flatten_parameters:
+            self.flat_params = torch.zeros_like(self.flat)
+            for p in self.params:
+                view = self._view[id(p)]
+                off = view.storage_offset() - self.flat.storage_offset()
+                dst = self.flat_params[off:off + p.numel()].view_as(p)
+                dst.copy_(p.data)
+                p.data = dst
         self._ready = [[] for _ in self.buckets]
         self._events = [[] for _ in self.buckets]
         self._pending = [len(b) for b in self.buckets]
@@ -78,6 +91,27 @@ class FlatGradDDP:
         self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
         if self.world > 1 and broadcast_parameters:
             self.broadcast()
+
+    # ---- flat optimizer view -----------------------------------------------------------------------
+    def flat_parameter(self):
+        """One nn.Parameter over `flat_params` whose .grad is the flat gradient buffer: hand it to the
+        optimizer instead of the ~190 parameter tensors (same elementwise update; the padding between
+        tensors stays 0: zero value, zero gradient)."""
+        assert self.flat_params is not None, "construct with flatten_parameters=True"
+        fp = torch.nn.Parameter(self.flat_params, requires_grad=True)
+        fp.grad = self.flat
+        return fp
+
+    def offsets(self):
+        """{id(parameter): offset in the flat buffers} (for TeacherEMA(flat=...))."""
+        return {id(p): self._view[id(p)].storage_offset() - self.flat.storage_offset() for p in self.params}
+
+    def clip_grad_norm_(self, max_norm):
+        """torch.nn.utils.clip_grad_norm_ over the flat gradient buffer (call after finish()): the
+        2-norm of all gradients is the 2-norm of the buffer."""
+        total = torch.linalg.vector_norm(self.flat)
+        self.flat.mul_(torch.clamp(max_norm / (total + 1e-6), max=1.0))
+        return total
 
     # ---- replica consistency --------------------------------------------------------------------
     def broadcast(self, src=0):

@@ -248,9 +248,10 @@ class VoteNetNesie(VoteNet):
         self.register_buffer('ulb_flag', torch.ones(n_ulb))
         self.teacher = None
 
-    def init_teacher(self):
-        """SimiTeacherHook.hooks_before_run: EMA copies of every parameter (call after .to(device))."""
-        self.teacher = TeacherEMA(self, **self.ema_cfg)
+    def init_teacher(self, flat=None):
+        """SimiTeacherHook.hooks_before_run: EMA copies of every parameter (call after .to(device)).
+        flat: a FlatGradDDP(flatten_parameters=True) whose flat parameter buffer is shared."""
+        self.teacher = TeacherEMA(self, flat=flat, **self.ema_cfg)
         return self.teacher
 
     def _filter_teacher(self, preds_t, aug_t, aug_s):

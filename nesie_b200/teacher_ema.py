@@ -18,7 +18,9 @@ ALIGN = 64   # floats
 
 class TeacherEMA:
 
-    def __init__(self, model, momentum=0.001, interval=1, warm_up=10):
+    def __init__(self, model, momentum=0.001, interval=1, warm_up=10, flat=None):
+        """flat: a FlatGradDDP built with flatten_parameters=True; its flat parameter buffer (and layout)
+        is then used as is instead of re-homing the parameters a second time."""
         assert isinstance(interval, int) and interval > 0
         assert 0 < momentum < 1
         self.momentum = momentum ** interval
@@ -26,13 +28,19 @@ class TeacherEMA:
         self.warm_up = warm_up
         self.params = [p for _, p in model.named_parameters(recurse=True)]
         self.names = [n for n, _ in model.named_parameters(recurse=True)]
+        dev = self.params[0].device
+        if flat is not None:
+            off = flat.offsets()
+            self.offsets = [off[id(p)] for p in self.params]
+            self.flat_param = flat.flat_params
+            self.flat_ema = self.flat_param.clone()
+            return
         # every parameter starts on a 256-byte boundary of the flat buffer: the kernels read weights and
         # BatchNorm vectors with 16-byte accesses / TMA (the padding floats are zero in both buffers)
         self.offsets, total = [], 0
         for p in self.params:
             self.offsets.append(total)
             total += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
-        dev = self.params[0].device
         _lib.need_cuda(self.params[0])
         for n, p in zip(self.names, self.params):
             assert p.dtype == torch.float32 and p.device == dev and p.layout == torch.strided, \
