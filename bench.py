@@ -579,6 +579,14 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     value = world * S * K / (ms / 1e3)
 
+    if os.environ.get("NESIE_BENCH_TRACE") and rank == 0:
+        # diagnostic: kernel timeline (name, stream, start, duration) of 3 pipelined steps
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            run_pipeline(3, resident)
+            torch.cuda.synchronize()
+        prof.export_chrome_trace(os.environ["NESIE_BENCH_TRACE"])
+
     # ---- end to end: pinned host -> device every step, loss read back every step ---------------
     # The loss of every step is copied to pinned host memory right behind the step; the host waits
     # for it one step later (the way a training loop logs), so the copy does not drain the pipeline.

@@ -27,11 +27,14 @@ One deliberate difference: IoU3DLoss returns early through a host-side `torch.an
 Hooks prefixed `_k_` are the kernels; oracle/nesie_head_ref.py overrides exactly those with CPU
 restatements (test infrastructure).
 """
+import os
+
 import torch
 from torch import nn as nn
 from torch.nn import functional as F
 
 from . import targets as T
+from .branches import run_branches
 from .conv_rows import conv1d_rows
 from .furthest_point_sample import furthest_point_sample
 from .pointnet_modules import ConvModule, build_sa_module, _rows_linear
@@ -452,42 +455,67 @@ class NesieHead(nn.Module):
         return (torch.exp(-sigma_mean) * per_row + self.alpha * sigma_mean * iou_weight).sum(), iou
 
     # ---- supervised loss ------------------------------------------------------------------------
+    def _loss_streams(self):
+        return int(os.environ.get("NESIE_LOSS_STREAMS", "4"))
+
     def loss_padded(self, bbox_preds, points, boxes, labels, valid, ret_target=False):
+        """All eight loss terms.  After the (sequential) target assignment the terms are independent
+        chains of small kernels: on CUDA they run as forked branches (branches.py)."""
         t = self.get_targets_padded(points, boxes, labels, valid, bbox_preds)
         C = self.num_classes
-        vote_loss = self.vote_module.get_loss(bbox_preds['seed_points'], bbox_preds['vote_points'],
-                                              bbox_preds['seed_indices'], t['vote_target_masks'],
-                                              t['vote_targets'], at_seeds=t['at_seeds'])
-        ocfg = self.loss_cfg['objectness']
-        cw = self._obj_class_weight
-        objectness_loss = ocfg.get('loss_weight', 1.0) * (F.cross_entropy(
-            bbox_preds['obj_scores'].transpose(2, 1), t['objectness_targets'], weight=cw,
-            reduction='none') * t['objectness_weights']).sum()
-        center_loss = self._center_loss(bbox_preds, t)
         box_w = t['box_loss_weights'].reshape(-1)
         surface_weight = box_w.unsqueeze(-1).repeat(1, 6)
-        surface_loss, sigma = self._sigma_terms(bbox_preds, t, surface_weight)
-        semantic_loss = self._semantic_loss(bbox_preds, t)
-        iou_loss, iou = self._iou_loss(bbox_preds, t, sigma, box_w)
-        # IoU-score regression (quality focal loss) on the proposals and their jittered copies
-        label_iou = iou.detach()
-        label_iou_jitter = cal_iou_3d(bbox_preds['jitter_bbox_preds'].detach(), t['bbox_targets'],
-                                      self._k_sort_vertices).reshape(-1)
         label_cls = t['mask_targets'].reshape(-1)
         qcfg = self.loss_cfg['iou_pred']
-        iou_pred_loss = sum(quality_focal_loss(bbox_preds[k].reshape(-1, C), label_cls, s, box_w,
-                                               qcfg.get('beta', 2.0), qcfg.get('loss_weight', 1.0))
-                            for k, s in (('iou_scores', label_iou), ('iou_scores_jitter', label_iou_jitter)))
-        # side-score regression: label = min(4 |surface - target|, 1) (SidePredLoss)
-        side_pred = torch.gather(bbox_preds['side_scores'].reshape(-1, 6, C), 2,
-                                 label_cls.view(-1, 1, 1).expand(-1, 6, 1)).squeeze(-1)
-        label_side = (4.0 * (bbox_preds['surface_pred'].reshape(-1, 6)
-                             - bbox2surface(t['bbox_targets'].reshape(-1, 7))).abs()).detach().clamp(max=1.0)
-        side_loss = self.loss_cfg['side'].get('loss_weight', 1.0) * \
-            (F.mse_loss(side_pred, label_side, reduction='none') * surface_weight).sum()
-        losses = dict(vote_loss=vote_loss, objectness_loss=objectness_loss,
-                      semantic_loss=semantic_loss, center_loss=center_loss, surface_loss=surface_loss,
-                      iou_loss=iou_loss, iou_pred_loss=iou_pred_loss, side_loss=side_loss)
+
+        def vote():
+            return dict(vote_loss=self.vote_module.get_loss(
+                bbox_preds['seed_points'], bbox_preds['vote_points'], bbox_preds['seed_indices'],
+                t['vote_target_masks'], t['vote_targets'], at_seeds=t['at_seeds']))
+
+        def objectness():
+            ocfg = self.loss_cfg['objectness']
+            ce = F.cross_entropy(bbox_preds['obj_scores'].transpose(2, 1), t['objectness_targets'],
+                                 weight=self._obj_class_weight, reduction='none')
+            return dict(objectness_loss=ocfg.get('loss_weight', 1.0) * (ce * t['objectness_weights']).sum())
+
+        def center_semantic():
+            return dict(center_loss=self._center_loss(bbox_preds, t),
+                        semantic_loss=self._semantic_loss(bbox_preds, t))
+
+        def surface_iou():
+            # surface loss with per-side uncertainty (fused kernel), IoU loss with its mean, and the
+            # IoU-score regression (quality focal loss) that needs the same IoU
+            surface_loss, sigma = self._sigma_terms(bbox_preds, t, surface_weight)
+            iou_loss, iou = self._iou_loss(bbox_preds, t, sigma, box_w)
+            qfl = quality_focal_loss(bbox_preds['iou_scores'].reshape(-1, C), label_cls, iou.detach(), box_w,
+                                     qcfg.get('beta', 2.0), qcfg.get('loss_weight', 1.0))
+            return dict(surface_loss=surface_loss, iou_loss=iou_loss, _qfl=qfl)
+
+        def jitter_side():
+            label_iou_jitter = cal_iou_3d(bbox_preds['jitter_bbox_preds'].detach(), t['bbox_targets'],
+                                          self._k_sort_vertices).reshape(-1)
+            qfl = quality_focal_loss(bbox_preds['iou_scores_jitter'].reshape(-1, C), label_cls,
+                                     label_iou_jitter, box_w, qcfg.get('beta', 2.0),
+                                     qcfg.get('loss_weight', 1.0))
+            # side-score regression: label = min(4 |surface - target|, 1) (SidePredLoss)
+            side_pred = torch.gather(bbox_preds['side_scores'].reshape(-1, 6, C), 2,
+                                     label_cls.view(-1, 1, 1).expand(-1, 6, 1)).squeeze(-1)
+            label_side = (4.0 * (bbox_preds['surface_pred'].reshape(-1, 6)
+                                 - bbox2surface(t['bbox_targets'].reshape(-1, 7))).abs()).detach().clamp(max=1.0)
+            side_loss = self.loss_cfg['side'].get('loss_weight', 1.0) * \
+                (F.mse_loss(side_pred, label_side, reduction='none') * surface_weight).sum()
+            return dict(_qfl_jitter=qfl, side_loss=side_loss)
+
+        shared = [v for v in list(bbox_preds.values()) + list(t.values()) if torch.is_tensor(v)]
+        shared += [box_w, surface_weight, label_cls]
+        parts = run_branches([surface_iou, jitter_side, center_semantic, vote, objectness],
+                             bbox_preds['aggregated_points'], shared, self._loss_streams())
+        r = {k: v for d in parts for k, v in d.items()}
+        losses = dict(vote_loss=r['vote_loss'], objectness_loss=r['objectness_loss'],
+                      semantic_loss=r['semantic_loss'], center_loss=r['center_loss'],
+                      surface_loss=r['surface_loss'], iou_loss=r['iou_loss'],
+                      iou_pred_loss=r['_qfl'] + r['_qfl_jitter'], side_loss=r['side_loss'])
         if ret_target:
             losses['targets'] = t['bbox_targets']
         return losses
@@ -508,12 +536,19 @@ class NesieHead(nn.Module):
         quality = quality * valid.unsqueeze(-1).to(quality.dtype)
         q_side = torch.gather(quality, 1, a.unsqueeze(-1).expand(-1, -1, 6))
         q_mean = q_side.mean(dim=-1)
-        center_loss = self._center_loss(bbox_preds, t)
-        semantic_loss = self._semantic_loss(bbox_preds, t)
         box_w = t['box_loss_weights']
         surface_weight = box_w.reshape(-1).unsqueeze(-1).repeat(1, 6) * q_side.reshape(-1, 6)
-        surface_loss, sigma = self._sigma_terms(bbox_preds, t, surface_weight)
-        iou_loss, _ = self._iou_loss(bbox_preds, t, sigma, (box_w * q_mean).reshape(-1))
+        iou_weight = (box_w * q_mean).reshape(-1)
+
+        def surface_iou():
+            surface_loss, sigma = self._sigma_terms(bbox_preds, t, surface_weight)
+            return surface_loss, self._iou_loss(bbox_preds, t, sigma, iou_weight)[0]
+
+        shared = [v for v in list(bbox_preds.values()) + list(t.values()) if torch.is_tensor(v)]
+        shared += [surface_weight, iou_weight]
+        (surface_loss, iou_loss), center_loss, semantic_loss = run_branches(
+            [surface_iou, lambda: self._center_loss(bbox_preds, t), lambda: self._semantic_loss(bbox_preds, t)],
+            bbox_preds['aggregated_points'], shared, self._loss_streams())
         return dict(unsup_semantic_loss=un_label_weight * semantic_loss,
                     unsup_center_loss=un_label_weight * center_loss,
                     unsup_iou_loss=un_label_weight * iou_loss,

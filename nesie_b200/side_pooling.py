@@ -297,32 +297,8 @@ class SidePooling(nn.Module):
         return end_points
 
     def _run_branches(self, branch, n, like, shared=None):
-        """The seven MiniPointNet + head chains are independent: on CUDA they are issued round-robin
-        on a few forked streams (joined before the results are used), so the dozens of small kernels of
-        one chain overlap the large GEMMs of another, and autograd replays the same concurrency in the
-        backward pass.  Every stream is re-forked from the caller's stream before it is used, which
-        also orders any reuse of the allocator's blocks behind their last reader."""
-        nstreams = int(os.environ.get("NESIE_SIDEPOOL_STREAMS", "3"))
-        if not like.is_cuda or nstreams <= 1:
-            return [branch(i) for i in range(n)]
-        dev = like.device
-        main = torch.cuda.current_stream(dev)
-        # one set of branch streams per calling stream (the teacher pass of the mean-teacher step runs
-        # on its own stream beside the student pass)
-        pool = self.__dict__.setdefault("_branch_pool", {})
-        key = (dev.index, main.cuda_stream, nstreams)
-        if key not in pool:
-            pool[key] = [torch.cuda.Stream(device=dev) for _ in range(nstreams)]
-        streams = pool[key]
-        for st in streams:
-            st.wait_stream(main)
-        outs = []
-        for i in range(n):
-            st = streams[i % nstreams]
-            for t in (shared[i] if shared else ()):
-                t.record_stream(st)          # the allocator must not recycle them under the branch
-            with torch.cuda.stream(st):
-                outs.append(branch(i))
-        for st in streams:
-            main.wait_stream(st)
-        return outs
+        """The seven MiniPointNet + head chains are independent: on CUDA they run as forked branches
+        (branches.py), so the dozens of small kernels of one chain overlap the large GEMMs of another."""
+        from .branches import run_branches
+        width = int(os.environ.get("NESIE_SIDEPOOL_STREAMS", "3"))
+        return run_branches([lambda i=i: branch(i) for i in range(n)], like, shared, width)
