@@ -320,6 +320,14 @@ int nesie_gemm_wgrad_3xtf32(long long r, int n, int k, const float *a, long long
 /* out[count] = sum of the nparts partial blocks (ascending order: deterministic); count % 4 == 0. */
 int nesie_gemm_sum_partials(int nparts, long long count, const float *partials, float *out,
                             void *stream);
+/* Data gradient dA_prev = dY W with the BatchNorm-backward statistics of the PREVIOUS layer taken in the
+ * epilogue: bn_y (r x n, row stride ldy) is that layer's pre-activation, bn_stats its 4 x n statistics
+ * (mean | invstd | scale | shift from the forward); col_stats (nesie_gemm_stats_parts(r) blocks of
+ * [2][n]) receives the column sums of g * [relu active] and g * [relu active] * xhat for
+ * nesie_bn_relu_rows_backward_fused, which then only finalizes and applies. */
+int nesie_gemm_nt_3xtf32_bnbwd(long long r, int n, int k, const float *a, long long lda,
+                               const void *b_image, float *c, long long ldc, const float *bn_y,
+                               long long ldy, const float *bn_stats, float *col_stats, void *stream);
 /* ... with B = relu(b * scale + shift) applied on the fly (k floats each; TMA path only). */
 int nesie_gemm_wgrad_3xtf32_fused(long long r, int n, int k, const float *a, long long lda,
                                   const float *b, long long ldb, const float *pro_scale,
@@ -351,6 +359,10 @@ int nesie_bn_rows_forward_fused(long long r, int c, int k, const float *y, const
                                 float *running_var, const float *col_partials, int nparts,
                                 float *stats, float *a_or_pooled, unsigned char *arg,
                                 void *workspace, void *stream);
+int nesie_bn_relu_rows_backward_fused(long long r, int c, const float *y, const float *d_a,
+                                      const float *stats, const float *col_partials, int nparts,
+                                      float *d_y, float *d_gamma, float *d_beta, void *workspace,
+                                      void *stream);
 int nesie_bn_relu_rows_backward(long long r, int c, int k, const float *y, const float *d_a,
                                 const unsigned char *arg, const float *stats, float *d_y,
                                 float *d_gamma, float *d_beta, void *workspace, void *stream);

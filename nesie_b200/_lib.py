@@ -50,6 +50,8 @@ SIGNATURES = {
     "nesie_gemm_fused_supported": [_ll, _i, _i, _p, _ll, _ll],
     "nesie_gemm_stats_parts": [_ll],
     "nesie_gemm_nt_3xtf32_fused": [_ll, _i, _i, _p, _ll, _p, _p, _ll, _p, _p, _p, _p],
+    "nesie_gemm_nt_3xtf32_bnbwd": [_ll, _i, _i, _p, _ll, _p, _p, _ll, _p, _ll, _p, _p, _p],
+    "nesie_bn_relu_rows_backward_fused": [_ll, _i, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p],
     "nesie_gemm_wgrad_3xtf32_fused": [_ll, _i, _i, _p, _ll, _p, _ll, _p, _p, _p, _i, _p],
     "nesie_bn_rows_forward_fused": [_ll, _i, _i, _p, _p, _p, _f, _f, _p, _p, _p, _i, _p, _p, _p, _p, _p],
     "nesie_gemm_sum_partials": [_i, _ll, _p, _p, _p],

@@ -377,6 +377,24 @@ extern "C" int nesie_bn_rows_forward_fused(long long r, int c, int k, const floa
                          col_partials, nparts, stats, a_or_pooled, arg, workspace, stream);
 }
 
+// Backward of a dense (un-pooled) layer whose statistics sweep already happened in the epilogue of the
+// data-gradient GEMM that produced d_a (nesie_gemm_nt_3xtf32_bnbwd): finalize + apply only.
+extern "C" int nesie_bn_relu_rows_backward_fused(long long r, int c, const float *y, const float *d_a,
+                                                 const float *stats, const float *col_partials,
+                                                 int nparts, float *d_y, float *d_gamma, float *d_beta,
+                                                 void *workspace, void *stream) {
+  NESIE_REQUIRE(shape_ok(r, c), "need R >= 1 and C a multiple of 4 in [4, 1024]");
+  NESIE_REQUIRE(y && d_a && stats && col_partials && d_y && d_gamma && d_beta && workspace, "null pointer");
+  NESIE_REQUIRE(nparts >= 1, "need nparts >= 1");
+  cudaStream_t st = (cudaStream_t)stream;
+  float *coef = reinterpret_cast<float *>(workspace) + (size_t)(BN_MAXPART - 1) * 2 * c;
+  bn_bwd_finalize_kernel<<<ceil_div(c, FIN_CH), dim3(FIN_CH, FIN_SLICES), 0, st>>>(r, c, nparts, col_partials,
+                                                                                 d_gamma, d_beta, coef);
+  const long long n4 = r * (c >> 2);
+  bn_relu_bwd_apply_kernel<false><<<grid_for(n4), BN_THREADS, 0, st>>>(r, 1, c, y, d_a, nullptr, stats, coef, d_y);
+  return check_launch("nesie_bn_relu_rows_backward_fused");
+}
+
 // Backward.  K == 0: d_a is (R, C).  K > 0: d_a is the pooled gradient (R/K, C) and arg the forward's.
 extern "C" int nesie_bn_relu_rows_backward(long long r, int c, int k, const float *y,
                                            const float *d_a, const unsigned char *arg,

@@ -723,7 +723,8 @@ extern "C" int nesie_gemm_debug_profile(long long *out16) {
 
 static int gemm_nt_impl(long long r, int n, int k, const float *a, long long lda,
                         const void *b_image, float *c, long long ldc, const float *pro_scale,
-                        const float *pro_shift, float *col_stats, void *stream) {
+                        const float *pro_shift, float *col_stats, void *stream,
+                        const float *bn_y = nullptr, long long ldy = 0, const float *bn_stats = nullptr) {
   NESIE_REQUIRE(r >= 0 && n >= 1 && n <= 256 && k >= 1, "need r >= 0, 1 <= n <= 256, k >= 1");
   NESIE_REQUIRE(r < (1LL << 31) - 256, "too many rows");
   if (r == 0) return NESIE_OK;
@@ -743,6 +744,7 @@ static int gemm_nt_impl(long long r, int n, int k, const float *a, long long lda
       q.R = p.R; q.N = n; q.K = k; q.npad = p.npad; q.nslab = p.nslab; q.ldc = ldc;
       q.Bimg = p.Bimg; q.C = c;
       q.pro_scale = pro_scale; q.pro_shift = pro_shift; q.col_stats = col_stats;
+      q.bn_y = bn_y; q.ldy = ldy; q.bn_stats = bn_stats;
       { const char *e = getenv("NESIE_GEMM_DBG"); q.dbg = e ? atoi(e) : 0; }
       const size_t stage = 2 * G_ASLAB + 2 * (size_t)p.npad * 128;
       const size_t epi = (size_t)T_EPIW * 4096;
@@ -759,7 +761,7 @@ static int gemm_nt_impl(long long r, int n, int k, const float *a, long long lda
       return check_launch("nesie_gemm_nt_3xtf32");
     }
   }
-  NESIE_REQUIRE(!pro_scale && !col_stats,
+  NESIE_REQUIRE(!pro_scale && !col_stats && !bn_y,
                 "the fused prologue / statistics need the TMA path (16-byte aligned rows)");
   p.fast = ((lda & 3) == 0) && ((k & 3) == 0) && ((reinterpret_cast<uintptr_t>(a) & 15) == 0);
   { const char *e = getenv("NESIE_GEMM_DBG"); p.dbg = e ? atoi(e) : 0; }
@@ -817,6 +819,18 @@ static int wgrad_kpart(long long r, int n, int k) {
   if (!ksplit || kp <= 128) return kp;
   if (ksplit == 2) return 128;
   return (kp % 128 == 0 && (n > 128 || r <= 16384)) ? 128 : kp;
+}
+
+extern "C" int nesie_gemm_nt_3xtf32_bnbwd(long long r, int n, int k, const float *a, long long lda,
+                                          const void *b_image, float *c, long long ldc,
+                                          const float *bn_y, long long ldy, const float *bn_stats,
+                                          float *col_stats, void *stream) {
+  NESIE_REQUIRE(r >= 1, "need r >= 1");
+  NESIE_REQUIRE(bn_y && bn_stats && col_stats, "null pointer");
+  NESIE_REQUIRE(nesie_gemm_fused_supported(r, n, k, a, lda, ldc), "shape / alignment not supported");
+  NESIE_REQUIRE((reinterpret_cast<uintptr_t>(c) & 15) == 0, "c must be 16-byte aligned");
+  return gemm_nt_impl(r, n, k, a, lda, b_image, c, ldc, nullptr, nullptr, col_stats, stream, bn_y, ldy,
+                      bn_stats);
 }
 
 // row chunks (one TMEM accumulation each) and CTAs along x (one partial block each)

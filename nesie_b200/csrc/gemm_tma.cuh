@@ -80,6 +80,14 @@ struct GemmTmaParams {
   float *C;
   const float *pro_scale, *pro_shift;  // optional [K]: A operand = relu(a * scale + shift)
   float *col_stats;                    // optional [gridDim.x * 4][2][N]: column sums of C and C^2
+  // optional BatchNorm-backward statistics of the OUTPUT (this GEMM is the data gradient that
+  // produces g = dL/dA of the previous layer): with y = bn_y[row, col] the previous layer's
+  // pre-activation and bn_stats = mean | invstd | scale | shift (4 x N), col_stats receives the
+  // column sums of g * [y*scale+shift > 0] and of that times xhat = (y - mean) * invstd -- what
+  // bn_colsum_kernel<1> computes in a separate sweep over g and y
+  const float *bn_y;
+  long long ldy;
+  const float *bn_stats;
   int dbg;
 };
 
@@ -271,13 +279,34 @@ gemm_nt_tma_kernel(const __grid_constant__ CUtensorMap tmA, GemmTmaParams p) {
             // rows >= R exist only in the last tile; with an operand prologue they are not zero
             const long long left = (long long)p.R - ((long long)tile * G_TILE + q * 32);
             const int nvalid = left >= 32 ? 32 : (left > 0 ? (int)left : 0);
+            if (p.bn_y) {
+              // lane = column c0 + lane of the block; the 32 lanes read 128 contiguous bytes of a y row
+              const int col = c0 + lane;
+              const bool cok = col < p.N;
+              const float mu = cok ? __ldg(p.bn_stats + col) : 0.f;
+              const float is = cok ? __ldg(p.bn_stats + p.N + col) : 0.f;
+              const float sc = cok ? __ldg(p.bn_stats + 2 * p.N + col) : 0.f;
+              const float sh = cok ? __ldg(p.bn_stats + 3 * p.N + col) : 0.f;
+              const float *yp = p.bn_y + ((long long)tile * G_TILE + q * 32) * p.ldy + col;
+#pragma unroll 8
+              for (int rr = 0; rr < 32; ++rr) {
+                float g;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(g) : "r"(stg + (unsigned)(rr * 128 + ((ch ^ (rr & 7)) << 4)) + wo) : "memory");
+                const bool ok = cok && rr < nvalid;
+                const float yv = ok ? __ldg(yp + (long long)rr * p.ldy) : 0.f;
+                const float gm = (ok && fmaf(yv, sc, sh) > 0.f) ? g : 0.f;
+                a1 += gm;
+                a2 = fmaf(gm, (yv - mu) * is, a2);
+              }
+            } else {
 #pragma unroll
-            for (int rr = 0; rr < 32; ++rr) {
-              float y;
-              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(y) : "r"(stg + (unsigned)(rr * 128 + ((ch ^ (rr & 7)) << 4)) + wo) : "memory");
-              y = rr < nvalid ? y : 0.f;
-              a1 += y;
-              a2 = fmaf(y, y, a2);
+              for (int rr = 0; rr < 32; ++rr) {
+                float y;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(y) : "r"(stg + (unsigned)(rr * 128 + ((ch ^ (rr & 7)) << 4)) + wo) : "memory");
+                y = rr < nvalid ? y : 0.f;
+                a1 += y;
+                a2 = fmaf(y, y, a2);
+              }
             }
             cs1[blk] += a1;
             cs2[blk] += a2;

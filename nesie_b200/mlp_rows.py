@@ -90,6 +90,36 @@ def _wgrad_fused(gy, x, scale, shift):
     return sum_partials(parts)
 
 
+def bnbwd_fused_enabled():
+    return os.environ.get("NESIE_BNBWD_FUSE", "1") != "0"
+
+
+def _dgrad_bn_backward(gy, w, y_prev, stats):
+    """d_y_prev of  y = relu(bn(y_prev)) @ w.T : the data-gradient GEMM g = gy @ w takes the BatchNorm
+    backward statistics (column sums of g * [relu active] and of that times xhat) in its epilogue, so
+    the backward needs no statistics sweep over (g, y_prev): finalize + apply only.
+    Returns (d_y_prev, d_gamma, d_beta)."""
+    R, N = gy.shape
+    C = y_prev.shape[1]
+    dev = gy.device
+    g_act = torch.empty((R, C), dtype=torch.float32, device=dev)
+    nparts = _lib.lib().nesie_gemm_stats_parts(R)
+    parts = torch.empty((nparts, 2, C), dtype=torch.float32, device=dev)
+    d_y = torch.empty_like(y_prev)
+    d_gamma = torch.empty((C,), dtype=torch.float32, device=dev)
+    d_beta = torch.empty((C,), dtype=torch.float32, device=dev)
+    ws = torch.empty((_lib.lib().nesie_bn_rows_workspace_bytes(C),), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        img = _pack(w, C, N, 1, C)        # B = w^T (C x N): element (c, n) at w[n, c]
+        _lib.call("nesie_gemm_nt_3xtf32_bnbwd", R, C, N, _lib.ptr(gy), N, _lib.ptr(img), _lib.ptr(g_act), C,
+                  _lib.ptr(y_prev), C, _lib.ptr(stats), _lib.ptr(parts), _lib.stream())
+        _lib.call("nesie_bn_relu_rows_backward_fused", R, C, _lib.ptr(y_prev), _lib.ptr(g_act),
+                  _lib.ptr(stats), _lib.ptr(parts), nparts, _lib.ptr(d_y), _lib.ptr(d_gamma),
+                  _lib.ptr(d_beta), _lib.ptr(ws), _lib.stream())
+        _lib.LAUNCHES += 1
+    return d_y, d_gamma, d_beta
+
+
 def _bn_stats(y, parts, gamma, beta, rm, rv, eps, momentum):
     """[4, C] mean | invstd | scale | shift of y from the GEMM's column sums; updates rm / rv."""
     R, C = y.shape
@@ -144,6 +174,10 @@ class _BNReLULinear(Function):
         R, C = y_prev.shape
         dev = y_prev.device
         gw = _wgrad_fused(gy, y_prev, stats[2], stats[3]) if ctx.needs_input_grad[8] else None
+        if (bnbwd_fused_enabled() and C <= 256 and C % 4 == 0 and gy.shape[1] % 4 == 0 and
+                _gemm_supported(gy, C, gy.shape[1])):
+            d_y, d_gamma, d_beta = _dgrad_bn_backward(gy, w.contiguous(), y_prev, stats)
+            return d_y, None, d_gamma, d_beta, None, None, None, None, gw
         g_act = gemm_nt(gy, w, transpose_w=True)          # gradient w.r.t. relu(bn(y_prev))
         d_y = torch.empty_like(y_prev)
         d_gamma = torch.empty((C,), dtype=torch.float32, device=dev)
