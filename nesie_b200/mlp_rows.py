@@ -91,7 +91,11 @@ def _wgrad_fused(gy, x, scale, shift):
 
 
 def bnbwd_fused_enabled():
-    return os.environ.get("NESIE_BNBWD_FUSE", "1") != "0"
+    """Off by default: measured on the pretrain step (B200) the statistics in the data-gradient GEMM's
+    epilogue cost more than the sweep they replace (17.65 vs 16.19 ms per step) -- the epilogue reads
+    the y tile with 4-byte loads per lane and stops hiding behind the next tile's MMAs.  Kept as an
+    option (NESIE_BNBWD_FUSE=1) with its parity test; it needs a TMA-staged y tile to pay."""
+    return os.environ.get("NESIE_BNBWD_FUSE", "0") == "1"
 
 
 def _dgrad_bn_backward(gy, w, y_prev, stats):

@@ -66,6 +66,25 @@ def test_fused_mlp_matches_float64(R, chs, pool_k):
         assert int(bn.num_batches_tracked) == 1
 
 
+def test_bn_backward_statistics_in_the_dgrad_epilogue(monkeypatch):
+    """NESIE_BNBWD_FUSE=1: the BatchNorm-backward column sums come from the data-gradient GEMM's
+    epilogue (nesie_gemm_nt_3xtf32_bnbwd) instead of a sweep over (g, y): same gradients as the
+    default path (only the order of the fp32 column sums differs)."""
+    chs, R = (132, 128, 128, 256), 3000
+    torch.manual_seed(7)
+    x0 = torch.randn(R, chs[0], device="cuda")
+    g = torch.randn(R, chs[-1], device="cuda")
+    grads = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("NESIE_BNBWD_FUSE", mode)
+        layers = _layers(chs, torch.float32, 1)
+        x = x0.clone().requires_grad_(True)
+        mlp_rows.mlp_rows(x, layers).backward(g)
+        grads[mode] = [x.grad] + [t.grad for w, bn in layers for t in (w, bn.weight, bn.bias)]
+    for a, b in zip(grads["0"], grads["1"]):
+        assert float((a - b).abs().max()) < 1e-4 * float(a.abs().max())
+
+
 def test_fused_mlp_with_large_mean_keeps_variance():
     """The GEMM epilogue sums y and y^2 without a pivot: a mean ten times the spread must still give
     the variance to 1e-4."""
