@@ -279,26 +279,7 @@ gemm_nt_tma_kernel(const __grid_constant__ CUtensorMap tmA, GemmTmaParams p) {
             // rows >= R exist only in the last tile; with an operand prologue they are not zero
             const long long left = (long long)p.R - ((long long)tile * G_TILE + q * 32);
             const int nvalid = left >= 32 ? 32 : (left > 0 ? (int)left : 0);
-            if (p.bn_y) {
-              // lane = column c0 + lane of the block; the 32 lanes read 128 contiguous bytes of a y row
-              const int col = c0 + lane;
-              const bool cok = col < p.N;
-              const float mu = cok ? __ldg(p.bn_stats + col) : 0.f;
-              const float is = cok ? __ldg(p.bn_stats + p.N + col) : 0.f;
-              const float sc = cok ? __ldg(p.bn_stats + 2 * p.N + col) : 0.f;
-              const float sh = cok ? __ldg(p.bn_stats + 3 * p.N + col) : 0.f;
-              const float *yp = p.bn_y + ((long long)tile * G_TILE + q * 32) * p.ldy + col;
-#pragma unroll 8
-              for (int rr = 0; rr < 32; ++rr) {
-                float g;
-                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(g) : "r"(stg + (unsigned)(rr * 128 + ((ch ^ (rr & 7)) << 4)) + wo) : "memory");
-                const bool ok = cok && rr < nvalid;
-                const float yv = ok ? __ldg(yp + (long long)rr * p.ldy) : 0.f;
-                const float gm = (ok && fmaf(yv, sc, sh) > 0.f) ? g : 0.f;
-                a1 += gm;
-                a2 = fmaf(gm, (yv - mu) * is, a2);
-              }
-            } else {
+            if (!p.bn_y) {
 #pragma unroll
               for (int rr = 0; rr < 32; ++rr) {
                 float y;
@@ -314,11 +295,46 @@ gemm_nt_tma_kernel(const __grid_constant__ CUtensorMap tmA, GemmTmaParams p) {
           const int cc = c0 + qc * 4;
           const long long grow = (long long)tile * G_TILE + q * 32 + qr;
           float *dst = p.C + grow * p.ldc + cc;
+          if (p.bn_y) {
+            // BatchNorm-backward statistics of the output g (see GemmTmaParams): the y tile is read in
+            // the layout of the stores below (a quarter-warp covers 128 contiguous bytes of a row), a
+            // lane sums its 8 rows of 4 columns, the 4 lanes that share those columns are combined by
+            // two shuffles, and lane l keeps column c0 + 4 (l & 7) + (l >> 3)
+            float4 b1 = make_float4(0.f, 0.f, 0.f, 0.f), b2 = b1;
+            const bool cok = cc < p.N;
+            const float4 mu = ldg4_guard(p.bn_stats, cc, p.N), is = ldg4_guard(p.bn_stats + p.N, cc, p.N);
+            const float4 sc = ldg4_guard(p.bn_stats + 2 * p.N, cc, p.N), sh = ldg4_guard(p.bn_stats + 3 * p.N, cc, p.N);
+            const float *yb = p.bn_y + grow * p.ldy + cc;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rr = qr + 4 * i;
-            const float4 o = g_lds128(stg + (unsigned)(rr * 128 + ((qc ^ (rr & 7)) << 4)));
-            if (grow + 4 * i < p.R && cc < p.N) *reinterpret_cast<float4 *>(dst + (long long)(4 * i) * p.ldc) = o;
+            for (int i = 0; i < 8; ++i) {
+              const int rr = qr + 4 * i;
+              const float4 o = g_lds128(stg + (unsigned)(rr * 128 + ((qc ^ (rr & 7)) << 4)));
+              if (grow + 4 * i < p.R && cok) {
+                const float4 yv = __ldg(reinterpret_cast<const float4 *>(yb + (long long)(4 * i) * p.ldy));
+                *reinterpret_cast<float4 *>(dst + (long long)(4 * i) * p.ldc) = o;
+                const float gx = fmaf(yv.x, sc.x, sh.x) > 0.f ? o.x : 0.f, gy = fmaf(yv.y, sc.y, sh.y) > 0.f ? o.y : 0.f;
+                const float gz = fmaf(yv.z, sc.z, sh.z) > 0.f ? o.z : 0.f, gw = fmaf(yv.w, sc.w, sh.w) > 0.f ? o.w : 0.f;
+                b1.x += gx; b1.y += gy; b1.z += gz; b1.w += gw;
+                b2.x = fmaf(gx, (yv.x - mu.x) * is.x, b2.x); b2.y = fmaf(gy, (yv.y - mu.y) * is.y, b2.y);
+                b2.z = fmaf(gz, (yv.z - mu.z) * is.z, b2.z); b2.w = fmaf(gw, (yv.w - mu.w) * is.w, b2.w);
+              }
+            }
+#pragma unroll
+            for (int o = 8; o <= 16; o <<= 1) {
+              b1.x += __shfl_xor_sync(0xffffffffu, b1.x, o); b1.y += __shfl_xor_sync(0xffffffffu, b1.y, o);
+              b1.z += __shfl_xor_sync(0xffffffffu, b1.z, o); b1.w += __shfl_xor_sync(0xffffffffu, b1.w, o);
+              b2.x += __shfl_xor_sync(0xffffffffu, b2.x, o); b2.y += __shfl_xor_sync(0xffffffffu, b2.y, o);
+              b2.z += __shfl_xor_sync(0xffffffffu, b2.z, o); b2.w += __shfl_xor_sync(0xffffffffu, b2.w, o);
+            }
+            cs1[blk] += qr == 0 ? b1.x : (qr == 1 ? b1.y : (qr == 2 ? b1.z : b1.w));
+            cs2[blk] += qr == 0 ? b2.x : (qr == 1 ? b2.y : (qr == 2 ? b2.z : b2.w));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rr = qr + 4 * i;
+              const float4 o = g_lds128(stg + (unsigned)(rr * 128 + ((qc ^ (rr & 7)) << 4)));
+              if (grow + 4 * i < p.R && cc < p.N) *reinterpret_cast<float4 *>(dst + (long long)(4 * i) * p.ldc) = o;
+            }
           }
           __syncwarp();
         } else if (gr < p.R) {
@@ -338,7 +354,8 @@ gemm_nt_tma_kernel(const __grid_constant__ CUtensorMap tmA, GemmTmaParams p) {
       float *dst = p.col_stats + (size_t)(blockIdx.x * 4 + q) * 2 * p.N;
 #pragma unroll
       for (int blk = 0; blk < 4; ++blk) {
-        const int c = half * 32 + blk * 32 * (T_EPIW / 4) + lane;
+        // column owned by this lane: c0 + lane, or c0 + 4 (lane & 7) + (lane >> 3) in the bn_y mode
+        const int c = half * 32 + blk * 32 * (T_EPIW / 4) + (p.bn_y ? 4 * (lane & 7) + (lane >> 3) : lane);
         if (c < p.N) {
           dst[c] = cs1[blk];
           dst[p.N + c] = cs2[blk];
