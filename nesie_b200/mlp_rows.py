@@ -92,9 +92,10 @@ def _wgrad_fused(gy, x, scale, shift):
 
 def bnbwd_fused_enabled():
     """Off by default: measured on the pretrain step (B200) the statistics in the data-gradient GEMM's
-    epilogue cost more than the sweep they replace (17.65 vs 16.19 ms per step) -- the epilogue reads
-    the y tile with 4-byte loads per lane and stops hiding behind the next tile's MMAs.  Kept as an
-    option (NESIE_BNBWD_FUSE=1) with its parity test; it needs a TMA-staged y tile to pay."""
+    epilogue cost more than the 0.9 ms sweep they replace (17.19 vs 16.23 ms per step, y tile read with
+    coalesced 16-byte loads in the store layout; 17.65 with 4-byte loads): the epilogue of these GEMMs
+    does not hide behind the next tile's MMAs, so every byte it touches is on the critical path.  Kept as
+    an option (NESIE_BNBWD_FUSE=1) with its parity test."""
     return os.environ.get("NESIE_BNBWD_FUSE", "0") == "1"
 
 
