@@ -328,6 +328,40 @@ int nesie_gemm_sum_partials(int nparts, long long count, const float *partials, 
 int nesie_gemm_nt_3xtf32_bnbwd(long long r, int n, int k, const float *a, long long lda,
                                const void *b_image, float *c, long long ldc, const float *bn_y,
                                long long ldy, const float *bn_stats, float *col_stats, void *stream);
+/* Row GEMM of a MAX-POOLED or GROUP-BIASED layer (MiniPointNet, side_pooling_module.py:343-370; SA
+ * pooling, point_sa_module.py:136-158), nesie_gemm_nt_3xtf32_fused plus, taken from the accumulator tile:
+ *   pool_max / pool_amax [r / pool_u][n]  per-column maximum over every unit of pool_u (16 or 32, | r)
+ *                                          consecutive rows and the first row of the unit that attains
+ *                                          it; pool_min / pool_amin (nullable) the minimum likewise.
+ *                                          With c == NULL the output itself is not written at all.
+ *   grp_bias [r / grp_k][n] (nullable)     added to row i of the output as grp_bias[i / grp_k] (and seen by
+ *                                          col_stats and the pooling): the part of the layer's input that
+ *                                          is constant over a group's rows (torch.cat([global.expand, x])),
+ *                                          pushed through the weights once per group; grp_k a power of
+ *                                          two >= 16 that divides r. */
+int nesie_gemm_nt_3xtf32_pool(long long r, int n, int k, const float *a, long long lda,
+                              const void *b_image, float *c, long long ldc, const float *pro_scale,
+                              const float *pro_shift, float *col_stats, int pool_u, float *pool_max,
+                              unsigned char *pool_amax, float *pool_min, unsigned char *pool_amin,
+                              const float *grp_bias, int grp_k, void *stream);
+/* Unit maxima of nesie_gemm_nt_3xtf32_pool (u rows each) -> maxima over groups of k rows (u | k) plus
+ * bias (n, nullable): out (groups, n), arg (groups, n) = first maximising row within the group. */
+int nesie_pool_finalize(long long groups, int k, int u, int n, const float *pmax,
+                        const unsigned char *amax, const float *bias, float *out, unsigned char *arg,
+                        void *stream);
+/* Weight gradient of a max-pooled convolution out[g, c] = max_j (a[g k + j, :] . w[c, :]):
+ * d_w[c, :] = sum_g d_out[g, c] * a[g k + arg[g, c], :] with a = relu(y_prev * scale + shift) (or y_prev
+ * itself when scale / shift are NULL), y_prev (groups * k, k_in) row-major, k_in % 4 == 0, k_in <= 256.
+ * dw_part receives nesie_pool_wgrad_parts(groups) partial blocks of (n, k_in) for nesie_gemm_sum_partials. */
+int nesie_pool_wgrad_parts(long long groups);
+int nesie_pool_wgrad(long long groups, int k, int n, int k_in, const float *d_out,
+                     const unsigned char *arg, const float *y_prev, const float *scale,
+                     const float *shift, float *dw_part, void *stream);
+/* out[g, :] = sum of rows g k .. g k + k - 1 of x (groups * k, n); n % 4 == 0. */
+int nesie_group_sum_rows(long long groups, int k, int n, const float *x, float *out, void *stream);
+/* d_x[g k + arg[g, c], c] += d[g, c]: the gradient of a group maximum added in place. */
+int nesie_scatter_rows_add(long long groups, int k, int n, const float *d, const unsigned char *arg,
+                           float *d_x, void *stream);
 /* ... with B = relu(b * scale + shift) applied on the fly (k floats each; TMA path only). */
 int nesie_gemm_wgrad_3xtf32_fused(long long r, int n, int k, const float *a, long long lda,
                                   const float *b, long long ldb, const float *pro_scale,

@@ -51,6 +51,12 @@ SIGNATURES = {
     "nesie_gemm_stats_parts": [_ll],
     "nesie_gemm_nt_3xtf32_fused": [_ll, _i, _i, _p, _ll, _p, _p, _ll, _p, _p, _p, _p],
     "nesie_gemm_nt_3xtf32_bnbwd": [_ll, _i, _i, _p, _ll, _p, _p, _ll, _p, _ll, _p, _p, _p],
+    "nesie_gemm_nt_3xtf32_pool": [_ll, _i, _i, _p, _ll, _p, _p, _ll, _p, _p, _p, _i, _p, _p, _p, _p, _p, _i, _p],
+    "nesie_pool_finalize": [_ll, _i, _i, _i, _p, _p, _p, _p, _p, _p],
+    "nesie_pool_wgrad_parts": [_ll],
+    "nesie_pool_wgrad": [_ll, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p],
+    "nesie_group_sum_rows": [_ll, _i, _i, _p, _p, _p],
+    "nesie_scatter_rows_add": [_ll, _i, _i, _p, _p, _p, _p],
     "nesie_bn_relu_rows_backward_fused": [_ll, _i, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p],
     "nesie_gemm_wgrad_3xtf32_fused": [_ll, _i, _i, _p, _ll, _p, _ll, _p, _p, _p, _i, _p],
     "nesie_bn_rows_forward_fused": [_ll, _i, _i, _p, _p, _p, _f, _f, _p, _p, _p, _i, _p, _p, _p, _p, _p],

@@ -721,14 +721,24 @@ extern "C" int nesie_gemm_debug_profile(long long *out16) {
   return NESIE_OK;
 }
 
+// row-group extras of the TMA kernel's epilogue (GemmTmaParams)
+struct GemmRowGroups {
+  float *pool_max, *pool_min;
+  unsigned char *pool_amax, *pool_amin;
+  int pool_u, store_c;
+  const float *grp_bias;
+  int grp_shift;
+};
+
 static int gemm_nt_impl(long long r, int n, int k, const float *a, long long lda,
                         const void *b_image, float *c, long long ldc, const float *pro_scale,
                         const float *pro_shift, float *col_stats, void *stream,
-                        const float *bn_y = nullptr, long long ldy = 0, const float *bn_stats = nullptr) {
+                        const float *bn_y = nullptr, long long ldy = 0, const float *bn_stats = nullptr,
+                        const GemmRowGroups *rg = nullptr) {
   NESIE_REQUIRE(r >= 0 && n >= 1 && n <= 256 && k >= 1, "need r >= 0, 1 <= n <= 256, k >= 1");
   NESIE_REQUIRE(r < (1LL << 31) - 256, "too many rows");
   if (r == 0) return NESIE_OK;
-  NESIE_REQUIRE(a && b_image && c, "null pointer");
+  NESIE_REQUIRE(a && b_image && (c || (rg && !rg->store_c)), "null pointer");
   NESIE_REQUIRE((reinterpret_cast<uintptr_t>(b_image) & 15) == 0, "b_image must be 16-byte aligned");
   GemmParams p;
   p.R = (int)r; p.N = n; p.K = k;
@@ -745,6 +755,14 @@ static int gemm_nt_impl(long long r, int n, int k, const float *a, long long lda
       q.Bimg = p.Bimg; q.C = c;
       q.pro_scale = pro_scale; q.pro_shift = pro_shift; q.col_stats = col_stats;
       q.bn_y = bn_y; q.ldy = ldy; q.bn_stats = bn_stats;
+      q.pool_max = q.pool_min = nullptr; q.pool_amax = q.pool_amin = nullptr;
+      q.pool_u = 32; q.store_c = 1; q.grp_bias = nullptr; q.grp_shift = 4;
+      if (rg) {
+        q.pool_max = rg->pool_max; q.pool_amax = rg->pool_amax;
+        q.pool_min = rg->pool_min; q.pool_amin = rg->pool_amin;
+        q.pool_u = rg->pool_u; q.store_c = rg->store_c;
+        q.grp_bias = rg->grp_bias; q.grp_shift = rg->grp_shift;
+      }
       { const char *e = getenv("NESIE_GEMM_DBG"); q.dbg = e ? atoi(e) : 0; }
       const size_t stage = 2 * G_ASLAB + 2 * (size_t)p.npad * 128;
       const size_t epi = (size_t)T_EPIW * 4096;
@@ -761,8 +779,8 @@ static int gemm_nt_impl(long long r, int n, int k, const float *a, long long lda
       return check_launch("nesie_gemm_nt_3xtf32");
     }
   }
-  NESIE_REQUIRE(!pro_scale && !col_stats && !bn_y,
-                "the fused prologue / statistics need the TMA path (16-byte aligned rows)");
+  NESIE_REQUIRE(!pro_scale && !col_stats && !bn_y && !rg,
+                "the fused prologue / statistics / pooling need the TMA path (16-byte aligned rows)");
   p.fast = ((lda & 3) == 0) && ((k & 3) == 0) && ((reinterpret_cast<uintptr_t>(a) & 15) == 0);
   { const char *e = getenv("NESIE_GEMM_DBG"); p.dbg = e ? atoi(e) : 0; }
   const size_t stage = 2 * G_ASLAB + 2 * (size_t)p.npad * 128;
@@ -805,6 +823,43 @@ extern "C" int nesie_gemm_nt_3xtf32_fused(long long r, int n, int k, const float
   NESIE_REQUIRE(nesie_gemm_fused_supported(r, n, k, a, lda, ldc), "shape / alignment not supported");
   NESIE_REQUIRE((reinterpret_cast<uintptr_t>(c) & 15) == 0, "c must be 16-byte aligned");
   return gemm_nt_impl(r, n, k, a, lda, b_image, c, ldc, pro_scale, pro_shift, col_stats, stream);
+}
+
+// Pooled / group-biased variant (see GemmTmaParams): c may be null (the output itself is not stored)
+// when pool_max is given; pool_u is 16 or 32 and divides r; pool_min / pool_amin are optional;
+// grp_bias (nullable) is [r / grp_k][n] with grp_k a power of two >= 16 that divides r.
+extern "C" int nesie_gemm_nt_3xtf32_pool(long long r, int n, int k, const float *a, long long lda,
+                                         const void *b_image, float *c, long long ldc,
+                                         const float *pro_scale, const float *pro_shift,
+                                         float *col_stats, int pool_u, float *pool_max,
+                                         unsigned char *pool_amax, float *pool_min,
+                                         unsigned char *pool_amin, const float *grp_bias, int grp_k,
+                                         void *stream) {
+  NESIE_REQUIRE((pro_scale == nullptr) == (pro_shift == nullptr), "scale and shift go together");
+  NESIE_REQUIRE(r >= 1, "need r >= 1");
+  NESIE_REQUIRE(nesie_gemm_fused_supported(r, n, k, a, lda, c ? ldc : 4), "shape / alignment not supported");
+  NESIE_REQUIRE((reinterpret_cast<uintptr_t>(c) & 15) == 0, "c must be 16-byte aligned");
+  NESIE_REQUIRE(c || pool_max, "nothing to compute: no output and no pooling");
+  NESIE_REQUIRE((pool_max == nullptr) == (pool_amax == nullptr) && (pool_min == nullptr) == (pool_amin == nullptr),
+                "value and index arrays go together");
+  NESIE_REQUIRE(!pool_min || pool_max, "the minimum comes with the maximum");
+  GemmRowGroups rg;
+  rg.pool_max = pool_max; rg.pool_amax = pool_amax; rg.pool_min = pool_min; rg.pool_amin = pool_amin;
+  rg.pool_u = 32; rg.store_c = c ? 1 : 0; rg.grp_bias = grp_bias; rg.grp_shift = 4;
+  if (pool_max) {
+    NESIE_REQUIRE((pool_u == 16 || pool_u == 32) && r % pool_u == 0, "pool_u must be 16 or 32 and divide r");
+    rg.pool_u = pool_u;
+  }
+  if (grp_bias) {
+    NESIE_REQUIRE(grp_k >= 16 && (grp_k & (grp_k - 1)) == 0 && r % grp_k == 0,
+                  "grp_k must be a power of two >= 16 that divides r");
+    NESIE_REQUIRE((reinterpret_cast<uintptr_t>(grp_bias) & 15) == 0, "grp_bias must be 16-byte aligned");
+    int sh = 0;
+    while ((1 << sh) < grp_k) ++sh;
+    rg.grp_shift = sh;
+  }
+  return gemm_nt_impl(r, n, k, a, lda, b_image, c, c ? ldc : n, pro_scale, pro_shift, col_stats, stream,
+                      nullptr, 0, nullptr, &rg);
 }
 
 // B channels per CTA along gridDim.z.  The kernel is bound by shared-memory traffic (TMA fill + the

@@ -88,6 +88,21 @@ struct GemmTmaParams {
   const float *bn_y;
   long long ldy;
   const float *bn_stats;
+  // optional row-group extras of the OUTPUT (pooled layers of the MiniPointNets / SA modules):
+  //  pool_max / pool_amax [R / pool_u][N]: per-column maximum over every unit of pool_u (16 or 32)
+  //      consecutive rows and the first row within the unit that attains it (the way torch.max /
+  //      F.max_pool2d route their gradient); pool_min / pool_amin likewise for the minimum (a
+  //      BatchNorm that follows may have a negative scale).  Taken from the accumulator tile, so a
+  //      max-pooled layer's pre-activation need not exist in HBM at all (store_c = 0).
+  //  grp_bias [R >> grp_shift][N]: added to row r of C (and seen by the statistics and the pooling):
+  //      the part of a layer's input that is constant over the rows of a group, multiplied through
+  //      the weights once per group instead of once per row
+  float *pool_max, *pool_min;
+  unsigned char *pool_amax, *pool_amin;
+  int pool_u;
+  int store_c;
+  const float *grp_bias;
+  int grp_shift;
   int dbg;
 };
 
@@ -272,25 +287,61 @@ gemm_nt_tma_kernel(const __grid_constant__ CUtensorMap tmA, GemmTmaParams p) {
                      make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
                                  __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
           __syncwarp();
-          if (p.col_stats) {
+          // rows >= R exist only in the last tile; with an operand prologue they are not zero
+          const long long row0 = (long long)tile * G_TILE + q * 32;
+          const long long left = (long long)p.R - row0;
+          const int nvalid = left >= 32 ? 32 : (left > 0 ? (int)left : 0);
+          if ((p.col_stats && !p.bn_y) || p.pool_max) {
             float a1 = 0.f, a2 = 0.f;
             const unsigned wo = (unsigned)((lane & 3) << 2);
             const int ch = lane >> 2;
-            // rows >= R exist only in the last tile; with an operand prologue they are not zero
-            const long long left = (long long)p.R - ((long long)tile * G_TILE + q * 32);
-            const int nvalid = left >= 32 ? 32 : (left > 0 ? (int)left : 0);
-            if (!p.bn_y) {
+            const int col = c0 + lane;
+            // group constants of this lane's column for rows 0-15 / 16-31 of the block (grp_shift >= 4)
+            float e0 = 0.f, e1 = 0.f;
+            if (p.grp_bias && col < p.N) {
+              if (nvalid > 0) e0 = __ldg(p.grp_bias + (row0 >> p.grp_shift) * p.N + col);
+              if (nvalid > 16) e1 = __ldg(p.grp_bias + ((row0 + 16) >> p.grp_shift) * p.N + col);
+            }
+            float mx0 = -INFINITY, mx1 = -INFINITY, mn0 = INFINITY, mn1 = INFINITY;
+            int ix0 = 0, ix1 = 0, in0 = 0, in1 = 0;
+            const bool want_min = p.pool_min != nullptr;
 #pragma unroll
-              for (int rr = 0; rr < 32; ++rr) {
-                float y;
-                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(y) : "r"(stg + (unsigned)(rr * 128 + ((ch ^ (rr & 7)) << 4)) + wo) : "memory");
-                y = rr < nvalid ? y : 0.f;
-                a1 += y;
-                a2 = fmaf(y, y, a2);
+            for (int rr = 0; rr < 32; ++rr) {
+              float y;
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(y) : "r"(stg + (unsigned)(rr * 128 + ((ch ^ (rr & 7)) << 4)) + wo) : "memory");
+              y += rr < 16 ? e0 : e1;
+              if (rr < 16) {
+                if (y > mx0) { mx0 = y; ix0 = rr; }
+                if (want_min && y < mn0) { mn0 = y; in0 = rr; }
+              } else {
+                if (y > mx1) { mx1 = y; ix1 = rr - 16; }
+                if (want_min && y < mn1) { mn1 = y; in1 = rr - 16; }
               }
+              y = rr < nvalid ? y : 0.f;
+              a1 += y;
+              a2 = fmaf(y, y, a2);
             }
             cs1[blk] += a1;
             cs2[blk] += a2;
+            if (p.pool_max && col < p.N) {
+              if (p.pool_u == 16) {
+                const long long u0 = (row0 >> 4) * p.N + col;
+                if (nvalid >= 16) { p.pool_max[u0] = mx0; p.pool_amax[u0] = (unsigned char)ix0; }
+                if (nvalid >= 32) { p.pool_max[u0 + p.N] = mx1; p.pool_amax[u0 + p.N] = (unsigned char)ix1; }
+                if (want_min) {
+                  if (nvalid >= 16) { p.pool_min[u0] = mn0; p.pool_amin[u0] = (unsigned char)in0; }
+                  if (nvalid >= 32) { p.pool_min[u0 + p.N] = mn1; p.pool_amin[u0 + p.N] = (unsigned char)in1; }
+                }
+              } else if (nvalid >= 32) {   // one unit of 32 rows: strict comparisons keep the first row
+                const long long u0 = (row0 >> 5) * p.N + col;
+                if (mx1 > mx0) { mx0 = mx1; ix0 = ix1 + 16; }
+                p.pool_max[u0] = mx0; p.pool_amax[u0] = (unsigned char)ix0;
+                if (want_min) {
+                  if (mn1 < mn0) { mn0 = mn1; in0 = in1 + 16; }
+                  p.pool_min[u0] = mn0; p.pool_amin[u0] = (unsigned char)in0;
+                }
+              }
+            }
           }
           const int cc = c0 + qc * 4;
           const long long grow = (long long)tile * G_TILE + q * 32 + qr;
@@ -328,12 +379,19 @@ gemm_nt_tma_kernel(const __grid_constant__ CUtensorMap tmA, GemmTmaParams p) {
             }
             cs1[blk] += qr == 0 ? b1.x : (qr == 1 ? b1.y : (qr == 2 ? b1.z : b1.w));
             cs2[blk] += qr == 0 ? b2.x : (qr == 1 ? b2.y : (qr == 2 ? b2.z : b2.w));
-          } else {
+          } else if (p.store_c) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int rr = qr + 4 * i;
-              const float4 o = g_lds128(stg + (unsigned)(rr * 128 + ((qc ^ (rr & 7)) << 4)));
-              if (grow + 4 * i < p.R && cc < p.N) *reinterpret_cast<float4 *>(dst + (long long)(4 * i) * p.ldc) = o;
+              float4 o = g_lds128(stg + (unsigned)(rr * 128 + ((qc ^ (rr & 7)) << 4)));
+              if (grow + 4 * i < p.R && cc < p.N) {
+                if (p.grp_bias) {
+                  const float4 e = __ldg(reinterpret_cast<const float4 *>(
+                      p.grp_bias + ((grow + 4 * i) >> p.grp_shift) * p.N + cc));
+                  o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w;
+                }
+                *reinterpret_cast<float4 *>(dst + (long long)(4 * i) * p.ldc) = o;
+              }
             }
           }
           __syncwarp();

@@ -1,0 +1,222 @@
+"""The MiniPointNet's two pooled stages (models/dense_heads/side_pooling_module.py:343-370) with the
+max over a box's grid points taken in the row GEMM's epilogue (training mode).
+
+    feature        = conv_b(relu(bn(conv_a(rows))))              (R, C)   first_conv
+    feature_global = max over the k rows of a box                (R/k, C)
+    feature        = second_conv(cat([feature_global.expand, feature]))
+    out            = max over the k rows of a box                (R/k, F)
+
+Reference formulation: max -> expand -> cat -> conv over 2C channels -> ... -> conv -> max, every
+intermediate in HBM.  Here
+
+  * `bn_relu_linear_max(..., store=True)`: conv_b's GEMM also emits the per-box maximum and its row
+    from the accumulator tile (no second sweep over its output);
+  * `concat_global_linear`: cat([g.expand, f]) @ W^T = f @ W_f^T + (g @ W_g^T)[box]: the global half is
+    multiplied through the weights once per BOX and enters the GEMM over f as a per-group bias, so the
+    (R, 2C) concatenation never exists and the contraction is half as long; backward: the group sums of
+    the output gradient give the box term's gradient, the max's gradient is added in place;
+  * `bn_relu_linear_max(..., store=False)`: the last conv's output is only ever max-pooled, so it is
+    not written at all; its weight gradient is a gather of one input row per (box, channel)
+    (`nesie_pool_wgrad`) instead of a contraction over a dense (R, F) gradient.
+"""
+import os
+
+import torch
+from torch.autograd import Function
+
+from . import _lib
+from . import mlp_rows
+from .linear_rows import _pack, gemm_nt, sum_partials, wgrad
+
+
+def enabled():
+    return os.environ.get("NESIE_POOL_FUSE", "1") != "0"
+
+
+def pool_unit(k):
+    """Rows per epilogue unit for groups of k rows, or 0 when the epilogue cannot pool them."""
+    if k == 16:
+        return 16
+    return 32 if (k % 32 == 0 and 32 <= k <= 224) else 0
+
+
+def supported(x, w_a, bn, w_b, k):
+    """rows x -> conv_a -> bn -> relu -> conv_b (-> max over k rows) on the pooled GEMM path."""
+    return (enabled() and pool_unit(k) > 0 and x.shape[0] % k == 0 and (k & (k - 1)) == 0 and
+            mlp_rows.supported(x, [(w_a, bn)]) and w_b.shape[0] % 4 == 0 and 4 <= w_b.shape[0] <= 256 and
+            w_b.shape[1] % 4 == 0 and w_b.shape[1] <= 256)
+
+
+def _gemm_pool(x, img, N, scale, shift, want_stats, store, pool_k, grp_bias=None, grp_k=0):
+    """x (R, K) [relu(x * scale + shift)] @ W^T with W's packed image `img` -> (y | None, column-sum
+    partials | None, unit maxima | None, their rows | None)."""
+    R, K = x.shape
+    dev = x.device
+    y = torch.empty((R, N), dtype=torch.float32, device=dev) if store else None
+    parts = None
+    if want_stats:
+        parts = torch.empty((_lib.lib().nesie_gemm_stats_parts(R), 2, N), dtype=torch.float32, device=dev)
+    u = pool_unit(pool_k) if pool_k else 0
+    pmax = torch.empty((R // u, N), dtype=torch.float32, device=dev) if u else None
+    amax = torch.empty((R // u, N), dtype=torch.uint8, device=dev) if u else None
+    with torch.cuda.device(dev):
+        _lib.call("nesie_gemm_nt_3xtf32_pool", R, N, K, _lib.ptr(x), K, _lib.ptr(img), _lib.ptr(y), N,
+                  _lib.ptr(scale), _lib.ptr(shift), _lib.ptr(parts), u, _lib.ptr(pmax), _lib.ptr(amax),
+                  None, None, _lib.ptr(grp_bias), grp_k, _lib.stream())
+    return y, parts, pmax, amax
+
+
+def _finalize(pmax, amax, bias, k):
+    u = pool_unit(k)
+    U, N = pmax.shape
+    G = U * u // k
+    out = torch.empty((G, N), dtype=torch.float32, device=pmax.device)
+    arg = torch.empty((G, N), dtype=torch.uint8, device=pmax.device)
+    with torch.cuda.device(pmax.device):
+        _lib.call("nesie_pool_finalize", G, k, u, N, _lib.ptr(pmax), _lib.ptr(amax), _lib.ptr(bias),
+                  _lib.ptr(out), _lib.ptr(arg), _lib.stream())
+    return out, arg
+
+
+def _bn_relu_backward(y_prev, g_act, stats):
+    """Gradient of relu(bn(y_prev)) w.r.t. y_prev / gamma / beta given g_act = dL/d(relu(bn(y_prev)))."""
+    R, C = y_prev.shape
+    dev = y_prev.device
+    d_y = torch.empty_like(y_prev)
+    d_gamma = torch.empty((C,), dtype=torch.float32, device=dev)
+    d_beta = torch.empty((C,), dtype=torch.float32, device=dev)
+    ws = torch.empty((_lib.lib().nesie_bn_rows_workspace_bytes(C),), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.call("nesie_bn_relu_rows_backward", R, C, 0, _lib.ptr(y_prev), _lib.ptr(g_act), None,
+                  _lib.ptr(stats), _lib.ptr(d_y), _lib.ptr(d_gamma), _lib.ptr(d_beta),
+                  _lib.ptr(ws), _lib.stream())
+        _lib.LAUNCHES += 2
+    return d_y, d_gamma, d_beta
+
+
+class _BNReLULinearMax(Function):
+    """relu(bn(y_prev)) @ w.T with the maximum over every k rows (+ bias) from the epilogue.
+
+    store=True : -> (y (R, N) WITHOUT the bias, max + bias (R/k, N), arg); only y carries a gradient
+                 (the caller owns the bias and the maximum's gradient: concat_global_linear).
+    store=False: -> max + bias (R/k, N); y is never written."""
+
+    @staticmethod
+    def forward(ctx, y_prev, parts_prev, gamma, beta, rm, rv, eps, momentum, w, bias, k, store):
+        stats = mlp_rows._bn_stats(y_prev, parts_prev, gamma, beta, rm, rv, eps, momentum)
+        N, K = w.shape
+        with torch.cuda.device(y_prev.device):
+            img = _pack(w, N, K, K, 1)
+        y, _, pmax, amax = _gemm_pool(y_prev, img, N, stats[2], stats[3], False, store, k)
+        bias_c = bias.contiguous() if bias is not None else None
+        out, arg = _finalize(pmax, amax, bias_c, k)
+        ctx.k, ctx.store, ctx.has_bias = k, store, bias is not None
+        ctx.set_materialize_grads(False)
+        if store:
+            ctx.save_for_backward(y_prev, stats, w)
+            ctx.mark_non_differentiable(out, arg)
+            return y, out, arg
+        ctx.save_for_backward(y_prev, stats, w, arg)
+        return out
+
+    @staticmethod
+    def backward(ctx, *grads):
+        none = (None,) * 12
+        if ctx.store:
+            y_prev, stats, w = ctx.saved_tensors
+            gy = grads[0]
+            if gy is None:
+                return none
+            gy = gy.contiguous()
+            gw = mlp_rows._wgrad_fused(gy, y_prev, stats[2], stats[3]) if ctx.needs_input_grad[8] else None
+            g_act = gemm_nt(gy, w, transpose_w=True)
+            d_bias = None
+        else:
+            y_prev, stats, w, arg = ctx.saved_tensors
+            d_out = grads[0]
+            if d_out is None:
+                return none
+            d_out = d_out.contiguous()
+            G, N = d_out.shape
+            R, K = y_prev.shape
+            dev = d_out.device
+            gw = None
+            with torch.cuda.device(dev):
+                if ctx.needs_input_grad[8]:
+                    parts = torch.empty((_lib.lib().nesie_pool_wgrad_parts(G), N, K), dtype=torch.float32,
+                                        device=dev)
+                    _lib.call("nesie_pool_wgrad", G, ctx.k, N, K, _lib.ptr(d_out), _lib.ptr(arg),
+                              _lib.ptr(y_prev), _lib.ptr(stats[2]), _lib.ptr(stats[3]), _lib.ptr(parts),
+                              _lib.stream())
+                    gw = sum_partials(parts)
+                gy = torch.empty((R, N), dtype=torch.float32, device=dev)
+                _lib.call("nesie_group_max_rows_backward", G, ctx.k, N, _lib.ptr(d_out), _lib.ptr(arg),
+                          _lib.ptr(gy), 0, None, _lib.stream())
+            g_act = gemm_nt(gy, w, transpose_w=True)
+            d_bias = d_out.sum(dim=0) if (ctx.has_bias and ctx.needs_input_grad[9]) else None
+        d_y, d_gamma, d_beta = _bn_relu_backward(y_prev, g_act, stats)
+        return d_y, None, d_gamma, d_beta, None, None, None, None, gw, d_bias, None, None
+
+
+class _ConcatGlobalLinear(Function):
+    """cat([gmax.expand over the group's rows, y + bias]) @ w.T plus the column sums of the result;
+    y (R, C) is conv_b's output WITHOUT its bias, gmax (R/k, C) = max over the group's rows of y + bias,
+    arg its row, w (N, 2C) = [W_g | W_f].  Gradients: y (including the maximum's), bias, w."""
+
+    @staticmethod
+    def forward(ctx, y, gmax, arg, bias, w, k):
+        R, C = y.shape
+        N = w.shape[0]
+        dev = y.device
+        with torch.cuda.device(dev):
+            img_g = _pack(w, N, C, 2 * C, 1)              # columns 0 .. C-1 of w
+            img_f = _pack(w[:, C:], N, C, 2 * C, 1)       # columns C .. 2C-1
+            G = gmax.shape[0]
+            e = torch.empty((G, N), dtype=torch.float32, device=dev)
+            _lib.call("nesie_gemm_nt_3xtf32", G, N, C, _lib.ptr(gmax), C, _lib.ptr(img_g), _lib.ptr(e), N,
+                      _lib.stream())
+        e += torch.mv(w[:, C:], bias)                     # the bias of `y` through W_f: same for every row
+        out, parts, _, _ = _gemm_pool(y, img_f, N, None, None, True, True, 0, grp_bias=e, grp_k=k)
+        ctx.save_for_backward(y, gmax, arg, bias, w)
+        ctx.k = k
+        ctx.mark_non_differentiable(parts)
+        ctx.set_materialize_grads(False)
+        return out, parts
+
+    @staticmethod
+    def backward(ctx, g_out, _gparts):
+        y, gmax, arg, bias, w = ctx.saved_tensors
+        if g_out is None:
+            return (None,) * 6
+        g_out = g_out.contiguous()
+        R, C = y.shape
+        N = w.shape[0]
+        G = gmax.shape[0]
+        dev = y.device
+        w_g, w_f = w[:, :C].contiguous(), w[:, C:].contiguous()
+        d_e = torch.empty((G, N), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.call("nesie_group_sum_rows", G, ctx.k, N, _lib.ptr(g_out), _lib.ptr(d_e), _lib.stream())
+        colsum = d_e.sum(dim=0)                                   # = column sums of g_out
+        d_y = gemm_nt(g_out, w_f, transpose_w=True)               # (R, C)
+        d_g = gemm_nt(d_e, w_g, transpose_w=True)                 # (G, C) gradient of the group maximum
+        with torch.cuda.device(dev):
+            _lib.call("nesie_scatter_rows_add", G, ctx.k, C, _lib.ptr(d_g), _lib.ptr(arg), _lib.ptr(d_y),
+                      _lib.stream())
+        d_w = d_bias = None
+        if ctx.needs_input_grad[4]:
+            d_wf = wgrad(g_out, y) + torch.outer(colsum, bias)    # rows are y + bias
+            d_w = torch.cat([wgrad(d_e, gmax), d_wf], dim=1)
+        if ctx.needs_input_grad[3]:
+            d_bias = d_g.sum(dim=0) + torch.mv(w_f.t(), colsum)   # sum over rows of d(y + bias)
+        return d_y, None, None, d_bias, d_w, None
+
+
+def bn_relu_linear_max(y_prev, parts_prev, bn, w, bias, k, store):
+    rm, rv = mlp_rows._bn_buffers(bn)
+    return _BNReLULinearMax.apply(y_prev, parts_prev, bn.weight, bn.bias, rm, rv, bn.eps, bn.momentum,
+                                  w, bias, k, store)
+
+
+def concat_global_linear(y, gmax, arg, bias, w, k):
+    return _ConcatGlobalLinear.apply(y, gmax, arg, bias, w, k)

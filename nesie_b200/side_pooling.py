@@ -29,6 +29,7 @@ from . import _lib
 from . import bn_rows
 from . import group_max
 from . import mlp_rows
+from . import pool_rows
 from .interpolate import three_nn
 from .linear_rows import linear_rows
 
@@ -222,6 +223,9 @@ class SidePooling(nn.Module):
 
     def _mini_pointnet(self, mpn, rows, G):
         """rows (R, ld) with every G consecutive rows one box -> (R / G, feature_dim)."""
+        fused = self._mini_pointnet_pooled(mpn, rows, G)
+        if fused is not None:
+            return fused
         feat = _conv_bn_relu_conv(rows, mpn.first_conv[0], mpn.first_conv[1], mpn.first_conv[3],
                                   add_bias=False)
         # [max over the box's grid points, broadcast | feature] with the conv bias folded in
@@ -229,6 +233,28 @@ class SidePooling(nn.Module):
         feat = _conv_bn_relu_conv(feat, mpn.second_conv[0], mpn.second_conv[1], mpn.second_conv[3],
                                   add_bias=False)
         return group_max.group_max_rows(feat, mpn.second_conv[3].bias, G)
+
+    @staticmethod
+    def _mini_pointnet_pooled(mpn, rows, G):
+        """Training path with both maxima taken in the GEMM epilogues (pool_rows.py); None when the
+        shapes / modes are not covered (the caller then runs the step-by-step formulation)."""
+        (ca, bna, _, cb), (cc, bnc, _, cd) = mpn.first_conv, mpn.second_conv
+        wa, wb = ca.weight.flatten(1), cb.weight.flatten(1)
+        wc, wd = cc.weight.flatten(1), cd.weight.flatten(1)
+        if rows.shape[1] != wa.shape[1]:           # zero-padded input columns
+            wa = F.pad(wa, (0, rows.shape[1] - wa.shape[1]))
+        C = wb.shape[0]
+        if not (torch.is_grad_enabled() and bna.training and bnc.training and
+                pool_rows.supported(rows, wa, bna, wb, G) and wc.shape[1] == 2 * C and
+                cb.bias is not None and cd.bias is not None and
+                bnc.affine and bnc.momentum is not None and C % 4 == 0 and
+                wc.shape[0] % 4 == 0 and wc.shape[0] <= 256 and wd.shape[1] == wc.shape[0] and
+                wd.shape[0] % 4 == 0 and wd.shape[0] <= 256):
+            return None
+        y1, parts1 = mlp_rows._LinearStats.apply(rows, wa)
+        ya, gmax, arg = pool_rows.bn_relu_linear_max(y1, parts1, bna, wb, cb.bias, G, True)
+        yc, partsc = pool_rows.concat_global_linear(ya, gmax, arg, cb.bias, wc, G)
+        return pool_rows.bn_relu_linear_max(yc, partsc, bnc, wd, cd.bias, G, False)
 
     def _head(self, seq, x):
         """Conv1d / BatchNorm1d / ReLU stack on x (B, C, K) -> (B, C_out, K), as row GEMMs."""

@@ -1,0 +1,118 @@
+"""Row GEMMs with the group maximum / a per-group bias in the epilogue (nesie_gemm_nt_3xtf32_pool) and the
+MiniPointNet built on them (pool_rows.py) against plain torch fp32 formulations of
+models/dense_heads/side_pooling_module.py:343-370 and against the step-by-step kernels."""
+import pytest
+import torch
+
+from nesie_b200 import _lib
+from nesie_b200 import pool_rows
+from nesie_b200.linear_rows import _pack
+from nesie_b200.side_pooling import MiniPointNet, SidePooling
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("R,K,N,k", [(4096, 256, 128, 16), (4096 + 64, 128, 256, 32), (2048, 64, 128, 64),
+                                     (1600, 260, 132, 16)])
+def test_gemm_pool_epilogue(R, K, N, k):
+    """Unit maxima + first maximising row, with and without storing the output; integers so that the
+    3xTF32 product is exact and ties are real ties."""
+    torch.manual_seed(R + k)
+    x = torch.randint(-3, 4, (R, K), device="cuda").float()
+    w = torch.randint(-2, 3, (N, K), device="cuda").float()
+    img = _pack(w, N, K, K, 1)
+    want = x @ w.t()
+    for store in (True, False):
+        y, _, pmax, amax = pool_rows._gemm_pool(x, img, N, None, None, False, store, k)
+        if store:
+            assert torch.equal(y, want)
+        else:
+            assert y is None
+        out, arg = pool_rows._finalize(pmax, amax, None, k)
+        wmax, warg = want.view(R // k, k, N).max(dim=1)
+        assert torch.equal(out, wmax)
+        # first maximising row (torch.max's index on CUDA is not specified for ties: compare by value
+        # and check minimality separately)
+        rows = want.view(R // k, k, N)
+        assert torch.equal(rows.gather(1, arg.long().unsqueeze(1)).squeeze(1), wmax)
+        first = (rows == wmax.unsqueeze(1)).float().argmax(dim=1)
+        assert torch.equal(arg.long(), first)
+
+
+def test_gemm_group_bias_and_stats():
+    torch.manual_seed(3)
+    R, K, N, k = 4096, 128, 256, 16
+    x = torch.randn(R, K, device="cuda")
+    w = torch.randn(N, K, device="cuda") * 0.1
+    e = torch.randn(R // k, N, device="cuda")
+    img = _pack(w, N, K, K, 1)
+    y, parts, _, _ = pool_rows._gemm_pool(x, img, N, None, None, True, True, 0, grp_bias=e, grp_k=k)
+    want = (x.double() @ w.double().t() + e.double().repeat_interleave(k, dim=0))
+    assert (y.double() - want).abs().max() < 2e-5
+    sums = parts.double().sum(dim=0)
+    assert torch.allclose(sums[0], want.sum(0), rtol=1e-5, atol=1e-3)
+    assert torch.allclose(sums[1], (want * want).sum(0), rtol=1e-5, atol=1e-3)
+
+
+@pytest.mark.parametrize("G,boxes,cin", [(16, 96, 259), (64, 40, 131)])
+def test_mini_pointnet_pooled_matches_tensor_formulation(G, boxes, cin, monkeypatch):
+    """Outputs, input-free parameter gradients and running statistics of the pooled path against the
+    module's own nn.Conv2d / BatchNorm2d / max / cat forward (the reference formulation) in fp32."""
+    torch.manual_seed(G)
+    monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)     # the twin's convolutions in fp32
+    monkeypatch.setattr(torch.backends.cuda.matmul, "allow_tf32", False)
+    mpn = MiniPointNet(cin, 128).cuda()
+    twin = MiniPointNet(cin, 128).cuda()
+    twin.load_state_dict(mpn.state_dict())
+    ld = -(-cin // 4) * 4
+    rows = torch.randn(boxes * G, ld, device="cuda")
+    rows[:, cin:] = 0
+    got = SidePooling._mini_pointnet_pooled(mpn, rows, G)
+    assert got is not None
+    x4 = rows[:, :cin].view(1, boxes, G, cin).permute(0, 3, 1, 2).contiguous()     # (1, C, boxes, G)
+    want = twin(x4)[0].t()                                                          # (boxes, 128)
+    assert (got - want).abs().max() < 2e-5 * want.abs().max().clamp_min(1.0)
+    g = torch.randn_like(want)
+    (got * g).sum().backward()
+    (want * g).sum().backward()
+    gmax = max(float(p.grad.norm()) for p in twin.parameters())
+    for (name, p), q in zip(twin.named_parameters(), mpn.parameters()):
+        err = float((q.grad - p.grad).norm())
+        assert err < 5e-3 * float(p.grad.norm()) or err < 1e-5 * gmax, (name, err, float(p.grad.norm()))
+    for (name, b1), b2 in zip(twin.named_buffers(), mpn.buffers()):
+        assert torch.allclose(b1.float(), b2.float(), rtol=1e-4, atol=1e-5), name
+
+
+def test_pooled_path_equals_stepwise_kernels(monkeypatch):
+    """Same weights through the pooled path and through the step-by-step kernels (NESIE_POOL_FUSE=0)."""
+    torch.manual_seed(9)
+    sp = SidePooling(18, 1, 18, None, 8, "vote", seed_feat_dim=256).cuda()
+    mpn = sp.mlps_before[0]
+    rows = torch.randn(128 * 16, 260, device="cuda")
+    rows[:, 259:] = 0
+    a = sp._mini_pointnet(mpn, rows, 16)
+    ga = torch.autograd.grad((a * a).sum(), list(mpn.parameters()))
+    monkeypatch.setenv("NESIE_POOL_FUSE", "0")
+    b = sp._mini_pointnet(mpn, rows, 16)
+    gb = torch.autograd.grad((b * b).sum(), list(mpn.parameters()))
+    assert (a - b).abs().max() < 1e-5 * b.abs().max()
+    top = max(float(g.norm()) for g in gb)
+    for (name, _), x, y in zip(mpn.named_parameters(), ga, gb):
+        err = float((x - y).norm())
+        assert err < 2e-3 * float(y.norm()) or err < 1e-5 * top, (name, err, float(y.norm()))
+
+
+def test_pool_wgrad_kernel_is_a_row_gather():
+    torch.manual_seed(1)
+    G, k, N, K = 300, 16, 128, 256
+    y = torch.randn(G * k, K, device="cuda")
+    sc, sh = torch.rand(K, device="cuda") + 0.5, torch.randn(K, device="cuda") * 0.3
+    d = torch.randn(G, N, device="cuda")
+    arg = torch.randint(0, k, (G, N), device="cuda", dtype=torch.uint8)
+    parts = torch.empty((_lib.lib().nesie_pool_wgrad_parts(G), N, K), device="cuda")
+    _lib.call("nesie_pool_wgrad", G, k, N, K, _lib.ptr(d), _lib.ptr(arg), _lib.ptr(y), _lib.ptr(sc),
+              _lib.ptr(sh), _lib.ptr(parts), _lib.stream())
+    a = torch.relu(y * sc + sh).view(G, k, K).double()
+    picked = a.gather(1, arg.long().unsqueeze(-1).expand(-1, -1, K))              # (G, N, K)
+    want = (d.double().unsqueeze(-1) * picked).sum(0)
+    assert (parts.double().sum(0) - want).abs().max() < 1e-4
