@@ -357,8 +357,18 @@ int nesie_pool_wgrad_parts(long long groups);
 int nesie_pool_wgrad(long long groups, int k, int n, int k_in, const float *d_out,
                      const unsigned char *arg, const float *y_prev, const float *scale,
                      const float *shift, float *dw_part, void *stream);
+/* Data gradient of the same layer (k <= 64): d_a[g k + j, :] = sum over the channels c with arg[g, c] == j of
+ * d_out[g, c] * w[c, :] (w (n, k_in) row-major, n * k_in <= 55296: it is held in shared memory); every
+ * row of d_a (groups * k, k_in) is written. */
+int nesie_pool_dgrad(long long groups, int k, int n, int k_in, const float *d_out,
+                     const unsigned char *arg, const float *w, float *d_a, void *stream);
 /* out[g, :] = sum of rows g k .. g k + k - 1 of x (groups * k, n); n % 4 == 0. */
 int nesie_group_sum_rows(long long groups, int k, int n, const float *x, float *out, void *stream);
+/* out[n] = column sums of x (rows, n), one launch, fixed summation order; n % 4 == 0, n <= 1024.
+ * work: nesie_colsum_rows_workspace(n) bytes, 256-byte aligned, zeroed once by the caller; launches that
+ * share it must be stream-ordered. */
+long long nesie_colsum_rows_workspace(int n);
+int nesie_colsum_rows(long long rows, int n, const float *x, float *out, void *work, void *stream);
 /* d_x[g k + arg[g, c], c] += d[g, c]: the gradient of a group maximum added in place. */
 int nesie_scatter_rows_add(long long groups, int k, int n, const float *d, const unsigned char *arg,
                            float *d_x, void *stream);

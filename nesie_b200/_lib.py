@@ -55,7 +55,10 @@ SIGNATURES = {
     "nesie_pool_finalize": [_ll, _i, _i, _i, _p, _p, _p, _p, _p, _p],
     "nesie_pool_wgrad_parts": [_ll],
     "nesie_pool_wgrad": [_ll, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p],
+    "nesie_pool_dgrad": [_ll, _i, _i, _i, _p, _p, _p, _p, _p],
     "nesie_group_sum_rows": [_ll, _i, _i, _p, _p, _p],
+    "nesie_colsum_rows_workspace": [_i],
+    "nesie_colsum_rows": [_ll, _i, _p, _p, _p, _p],
     "nesie_scatter_rows_add": [_ll, _i, _i, _p, _p, _p, _p],
     "nesie_bn_relu_rows_backward_fused": [_ll, _i, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p],
     "nesie_gemm_wgrad_3xtf32_fused": [_ll, _i, _i, _p, _ll, _p, _ll, _p, _p, _p, _i, _p],

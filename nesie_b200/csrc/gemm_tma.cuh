@@ -279,6 +279,27 @@ gemm_nt_tma_kernel(const __grid_constant__ CUtensorMap tmA, GemmTmaParams p) {
         if (c0 >= p.npad) break;
         unsigned v[32];
         g_tmem_ld32(tmem + (unsigned)(acc * 256 + c0) + ((unsigned)(q * 32) << 16), v);
+        // rows >= R exist only in the last tile; with an operand prologue they are not zero
+        const long long row0 = (long long)tile * G_TILE + q * 32;
+        const long long left = (long long)p.R - row0;
+        const int nvalid = left >= 32 ? 32 : (left > 0 ? (int)left : 0);
+        // group constants (grp_shift >= 4: rows 0-15 and 16-31 of the block lie in one group each),
+        // requested while the accumulator load is in flight: e0 / e1 for this lane's column in the
+        // statistics loop, el / eh for its 16-byte chunk in the store loop
+        float e0 = 0.f, e1 = 0.f;
+        float4 el = make_float4(0.f, 0.f, 0.f, 0.f), eh = el;
+        if (p.grp_bias) {
+          const float *g0 = p.grp_bias + (row0 >> p.grp_shift) * p.N;
+          const float *g1 = p.grp_bias + ((row0 + 16) >> p.grp_shift) * p.N;
+          if (c0 + lane < p.N) {
+            if (nvalid > 0) e0 = __ldg(g0 + c0 + lane);
+            if (nvalid > 16) e1 = __ldg(g1 + c0 + lane);
+          }
+          if (c0 + qc * 4 < p.N) {
+            if (nvalid > 0) el = __ldg(reinterpret_cast<const float4 *>(g0 + c0 + qc * 4));
+            if (nvalid > 16) eh = __ldg(reinterpret_cast<const float4 *>(g1 + c0 + qc * 4));
+          }
+        }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (vec) {
 #pragma unroll
@@ -287,21 +308,11 @@ gemm_nt_tma_kernel(const __grid_constant__ CUtensorMap tmA, GemmTmaParams p) {
                      make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
                                  __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
           __syncwarp();
-          // rows >= R exist only in the last tile; with an operand prologue they are not zero
-          const long long row0 = (long long)tile * G_TILE + q * 32;
-          const long long left = (long long)p.R - row0;
-          const int nvalid = left >= 32 ? 32 : (left > 0 ? (int)left : 0);
           if ((p.col_stats && !p.bn_y) || p.pool_max) {
             float a1 = 0.f, a2 = 0.f;
             const unsigned wo = (unsigned)((lane & 3) << 2);
             const int ch = lane >> 2;
             const int col = c0 + lane;
-            // group constants of this lane's column for rows 0-15 / 16-31 of the block (grp_shift >= 4)
-            float e0 = 0.f, e1 = 0.f;
-            if (p.grp_bias && col < p.N) {
-              if (nvalid > 0) e0 = __ldg(p.grp_bias + (row0 >> p.grp_shift) * p.N + col);
-              if (nvalid > 16) e1 = __ldg(p.grp_bias + ((row0 + 16) >> p.grp_shift) * p.N + col);
-            }
             float mx0 = -INFINITY, mx1 = -INFINITY, mn0 = INFINITY, mn1 = INFINITY;
             int ix0 = 0, ix1 = 0, in0 = 0, in1 = 0;
             const bool want_min = p.pool_min != nullptr;
@@ -309,7 +320,7 @@ gemm_nt_tma_kernel(const __grid_constant__ CUtensorMap tmA, GemmTmaParams p) {
             for (int rr = 0; rr < 32; ++rr) {
               float y;
               asm volatile("ld.shared.f32 %0, [%1];" : "=f"(y) : "r"(stg + (unsigned)(rr * 128 + ((ch ^ (rr & 7)) << 4)) + wo) : "memory");
-              y += rr < 16 ? e0 : e1;
+              if (p.grp_bias) y += rr < 16 ? e0 : e1;
               if (rr < 16) {
                 if (y > mx0) { mx0 = y; ix0 = rr; }
                 if (want_min && y < mn0) { mn0 = y; in0 = rr; }
@@ -386,8 +397,7 @@ gemm_nt_tma_kernel(const __grid_constant__ CUtensorMap tmA, GemmTmaParams p) {
               float4 o = g_lds128(stg + (unsigned)(rr * 128 + ((qc ^ (rr & 7)) << 4)));
               if (grow + 4 * i < p.R && cc < p.N) {
                 if (p.grp_bias) {
-                  const float4 e = __ldg(reinterpret_cast<const float4 *>(
-                      p.grp_bias + ((grow + 4 * i) >> p.grp_shift) * p.N + cc));
+                  const float4 e = i < 4 ? el : eh;   // row qr + 4 i of the block: first / second 16 rows
                   o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w;
                 }
                 *reinterpret_cast<float4 *>(dst + (long long)(4 * i) * p.ldc) = o;

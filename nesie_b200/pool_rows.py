@@ -33,6 +33,13 @@ def enabled():
     return os.environ.get("NESIE_POOL_FUSE", "1") != "0"
 
 
+def _sparse_dgrad():
+    """nesie_pool_dgrad instead of scatter + dense GEMM for the pooled conv's data gradient.  Off by
+    default: measured 87 us against 44 us (group_max backward + tcgen05 GEMM) at 4096 boxes x 16 rows,
+    128 -> 256 channels -- the per-box sort and list walk are instruction-bound (profiles/r02_ncu_notes.md)."""
+    return os.environ.get("NESIE_POOL_DGRAD", "0") == "1"
+
+
 def pool_unit(k):
     """Rows per epilogue unit for groups of k rows, or 0 when the epilogue cannot pool them."""
     if k == 16:
@@ -76,6 +83,27 @@ def _finalize(pmax, amax, bias, k):
         _lib.call("nesie_pool_finalize", G, k, u, N, _lib.ptr(pmax), _lib.ptr(amax), _lib.ptr(bias),
                   _lib.ptr(out), _lib.ptr(arg), _lib.stream())
     return out, arg
+
+
+def _group_sum(x, k):
+    G = x.shape[0] // k
+    out = torch.empty((G, x.shape[1]), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.call("nesie_group_sum_rows", G, k, x.shape[1], _lib.ptr(x), _lib.ptr(out), _lib.stream())
+    return out
+
+
+def _colsum(x):
+    """Column sums of a (rows, n) matrix: one launch, fixed summation order (nesie_colsum_rows)."""
+    rows, n = x.shape
+    if n % 4 or n > 1024 or not x.is_contiguous():
+        return x.sum(dim=0)
+    out = torch.empty((n,), dtype=torch.float32, device=x.device)
+    ws = torch.empty((_lib.lib().nesie_colsum_rows_workspace(n),), dtype=torch.uint8, device=x.device)
+    ws[:256].zero_()                      # the kernel's arrival counter
+    with torch.cuda.device(x.device):
+        _lib.call("nesie_colsum_rows", rows, n, _lib.ptr(x), _lib.ptr(out), _lib.ptr(ws), _lib.stream())
+    return out
 
 
 def _bn_relu_backward(y_prev, g_act, stats):
@@ -149,11 +177,17 @@ class _BNReLULinearMax(Function):
                               _lib.ptr(y_prev), _lib.ptr(stats[2]), _lib.ptr(stats[3]), _lib.ptr(parts),
                               _lib.stream())
                     gw = sum_partials(parts)
-                gy = torch.empty((R, N), dtype=torch.float32, device=dev)
-                _lib.call("nesie_group_max_rows_backward", G, ctx.k, N, _lib.ptr(d_out), _lib.ptr(arg),
-                          _lib.ptr(gy), 0, None, _lib.stream())
-            g_act = gemm_nt(gy, w, transpose_w=True)
-            d_bias = d_out.sum(dim=0) if (ctx.has_bias and ctx.needs_input_grad[9]) else None
+                if _sparse_dgrad() and ctx.k <= 64 and N * K <= 55296:   # weights fit its shared memory
+                    w_c = w.contiguous()
+                    g_act = torch.empty((R, K), dtype=torch.float32, device=dev)
+                    _lib.call("nesie_pool_dgrad", G, ctx.k, N, K, _lib.ptr(d_out), _lib.ptr(arg),
+                              _lib.ptr(w_c), _lib.ptr(g_act), _lib.stream())
+                else:
+                    gy = torch.empty((R, N), dtype=torch.float32, device=dev)
+                    _lib.call("nesie_group_max_rows_backward", G, ctx.k, N, _lib.ptr(d_out), _lib.ptr(arg),
+                              _lib.ptr(gy), 0, None, _lib.stream())
+                    g_act = gemm_nt(gy, w, transpose_w=True)
+            d_bias = _colsum(d_out) if (ctx.has_bias and ctx.needs_input_grad[9]) else None
         d_y, d_gamma, d_beta = _bn_relu_backward(y_prev, g_act, stats)
         return d_y, None, d_gamma, d_beta, None, None, None, None, gw, d_bias, None, None
 
@@ -164,7 +198,7 @@ class _ConcatGlobalLinear(Function):
     arg its row, w (N, 2C) = [W_g | W_f].  Gradients: y (including the maximum's), bias, w."""
 
     @staticmethod
-    def forward(ctx, y, gmax, arg, bias, w, k):
+    def forward(ctx, y, gmax, arg, bias, w, k, zero_mean_grad):
         R, C = y.shape
         N = w.shape[0]
         dev = y.device
@@ -178,7 +212,7 @@ class _ConcatGlobalLinear(Function):
         e += torch.mv(w[:, C:], bias)                     # the bias of `y` through W_f: same for every row
         out, parts, _, _ = _gemm_pool(y, img_f, N, None, None, True, True, 0, grp_bias=e, grp_k=k)
         ctx.save_for_backward(y, gmax, arg, bias, w)
-        ctx.k = k
+        ctx.k, ctx.zero_mean_grad = k, zero_mean_grad
         ctx.mark_non_differentiable(parts)
         ctx.set_materialize_grads(False)
         return out, parts
@@ -187,29 +221,36 @@ class _ConcatGlobalLinear(Function):
     def backward(ctx, g_out, _gparts):
         y, gmax, arg, bias, w = ctx.saved_tensors
         if g_out is None:
-            return (None,) * 6
+            return (None,) * 7
         g_out = g_out.contiguous()
         R, C = y.shape
-        N = w.shape[0]
         G = gmax.shape[0]
         dev = y.device
         w_g, w_f = w[:, :C].contiguous(), w[:, C:].contiguous()
-        d_e = torch.empty((G, N), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
-            _lib.call("nesie_group_sum_rows", G, ctx.k, N, _lib.ptr(g_out), _lib.ptr(d_e), _lib.stream())
-        colsum = d_e.sum(dim=0)                                   # = column sums of g_out
+        d_e = _group_sum(g_out, ctx.k)
         d_y = gemm_nt(g_out, w_f, transpose_w=True)               # (R, C)
         d_g = gemm_nt(d_e, w_g, transpose_w=True)                 # (G, C) gradient of the group maximum
         with torch.cuda.device(dev):
             _lib.call("nesie_scatter_rows_add", G, ctx.k, C, _lib.ptr(d_g), _lib.ptr(arg), _lib.ptr(d_y),
                       _lib.stream())
+        # rows are y + bias: the bias reaches d_w_f and d_bias only through the column sums of g_out
+        # (d_bias = colsum(g_out) @ (W_f + W_g)), which are exactly zero when g_out comes out of a
+        # training-mode BatchNorm's backward -- a constant added in front of a BatchNorm has no
+        # gradient; the reference formulation computes rounding noise there.  zero_mean_grad skips
+        # those terms and returns d_bias = 0.
         d_w = d_bias = None
-        if ctx.needs_input_grad[4]:
-            d_wf = wgrad(g_out, y) + torch.outer(colsum, bias)    # rows are y + bias
-            d_w = torch.cat([wgrad(d_e, gmax), d_wf], dim=1)
-        if ctx.needs_input_grad[3]:
-            d_bias = d_g.sum(dim=0) + torch.mv(w_f.t(), colsum)   # sum over rows of d(y + bias)
-        return d_y, None, None, d_bias, d_w, None
+        if ctx.zero_mean_grad:
+            if ctx.needs_input_grad[4]:
+                d_w = torch.cat([wgrad(d_e, gmax), wgrad(g_out, y)], dim=1)
+            if ctx.needs_input_grad[3]:
+                d_bias = torch.zeros_like(bias)
+        else:
+            colsum = _colsum(d_e)
+            if ctx.needs_input_grad[4]:
+                d_w = torch.cat([wgrad(d_e, gmax), wgrad(g_out, y) + torch.outer(colsum, bias)], dim=1)
+            if ctx.needs_input_grad[3]:
+                d_bias = _colsum(d_g) + torch.mv(w_f.t(), colsum)     # sum over rows of d(y + bias)
+        return d_y, None, None, d_bias, d_w, None, None
 
 
 def bn_relu_linear_max(y_prev, parts_prev, bn, w, bias, k, store):
@@ -218,5 +259,6 @@ def bn_relu_linear_max(y_prev, parts_prev, bn, w, bias, k, store):
                                   w, bias, k, store)
 
 
-def concat_global_linear(y, gmax, arg, bias, w, k):
-    return _ConcatGlobalLinear.apply(y, gmax, arg, bias, w, k)
+def concat_global_linear(y, gmax, arg, bias, w, k, zero_mean_grad=False):
+    """zero_mean_grad: the result feeds a training-mode BatchNorm (its gradient has zero column sums)."""
+    return _ConcatGlobalLinear.apply(y, gmax, arg, bias, w, k, zero_mean_grad)

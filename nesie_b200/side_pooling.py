@@ -244,7 +244,7 @@ class SidePooling(nn.Module):
         if rows.shape[1] != wa.shape[1]:           # zero-padded input columns
             wa = F.pad(wa, (0, rows.shape[1] - wa.shape[1]))
         C = wb.shape[0]
-        if not (torch.is_grad_enabled() and bna.training and bnc.training and
+        if not (bna.training and bnc.training and
                 pool_rows.supported(rows, wa, bna, wb, G) and wc.shape[1] == 2 * C and
                 cb.bias is not None and cd.bias is not None and
                 bnc.affine and bnc.momentum is not None and C % 4 == 0 and
@@ -253,7 +253,7 @@ class SidePooling(nn.Module):
             return None
         y1, parts1 = mlp_rows._LinearStats.apply(rows, wa)
         ya, gmax, arg = pool_rows.bn_relu_linear_max(y1, parts1, bna, wb, cb.bias, G, True)
-        yc, partsc = pool_rows.concat_global_linear(ya, gmax, arg, cb.bias, wc, G)
+        yc, partsc = pool_rows.concat_global_linear(ya, gmax, arg, cb.bias, wc, G, zero_mean_grad=True)
         return pool_rows.bn_relu_linear_max(yc, partsc, bnc, wd, cd.bias, G, False)
 
     def _head(self, seq, x):

@@ -116,3 +116,57 @@ def test_pool_wgrad_kernel_is_a_row_gather():
     picked = a.gather(1, arg.long().unsqueeze(-1).expand(-1, -1, K))              # (G, N, K)
     want = (d.double().unsqueeze(-1) * picked).sum(0)
     assert (parts.double().sum(0) - want).abs().max() < 1e-4
+
+
+@pytest.mark.parametrize("rows,n", [(4096, 256), (4096, 128), (37, 4), (100000, 1024)])
+def test_colsum_rows(rows, n):
+    torch.manual_seed(rows)
+    x = torch.randn(rows, n, device="cuda")
+    got = pool_rows._colsum(x)
+    assert torch.allclose(got.double(), x.double().sum(0), rtol=1e-5, atol=1e-3)
+    assert torch.equal(got, pool_rows._colsum(x))        # fixed summation order
+
+
+@pytest.mark.parametrize("k,N,K", [(16, 128, 256), (64, 128, 256), (5, 36, 520), (16, 256, 128)])
+def test_pool_dgrad_kernel(k, N, K):
+    torch.manual_seed(k)
+    G = 200
+    d = torch.randn(G, N, device="cuda")
+    arg = torch.randint(0, k, (G, N), device="cuda", dtype=torch.uint8)
+    w = torch.randn(N, K, device="cuda")
+    got = torch.empty(G * k, K, device="cuda")
+    _lib.call("nesie_pool_dgrad", G, k, N, K, _lib.ptr(d), _lib.ptr(arg), _lib.ptr(w), _lib.ptr(got),
+              _lib.stream())
+    dy = torch.zeros(G, k, N, device="cuda", dtype=torch.float64)
+    dy.scatter_(1, arg.long().unsqueeze(1), d.double().unsqueeze(1))
+    want = dy.view(G * k, N) @ w.double()
+    assert (got.double() - want).abs().max() < 1e-4
+
+
+@pytest.mark.parametrize("zero_mean", [False, True])
+def test_concat_global_linear_matches_torch(zero_mean):
+    """cat([max.expand, y + b]) @ W^T through the group-bias GEMM, forward and every gradient; with
+    zero_mean_grad the output gradient is centred first (as a BatchNorm backward delivers it)."""
+    torch.manual_seed(5)
+    G, k, C, N = 256, 16, 128, 256
+    y = torch.randn(G * k, C, device="cuda", requires_grad=True)
+    b = torch.randn(C, device="cuda", requires_grad=True)
+    w = (torch.randn(N, 2 * C, device="cuda") * 0.1).requires_grad_(True)
+    f = (y + b).view(G, k, C)
+    gmax, arg = f.max(dim=1)
+    got, _ = pool_rows.concat_global_linear(y, gmax.detach(), arg.to(torch.uint8), b, w, k, zero_mean)
+    yd, bd, wd = (t.detach().double().requires_grad_(True) for t in (y, b, w))
+    fd = (yd + bd).view(G, k, C)
+    want = torch.cat([fd.max(dim=1).values.unsqueeze(1).expand(-1, k, -1), fd], dim=2).reshape(G * k, 2 * C) @ wd.t()
+    assert (got.double() - want).abs().max() < 2e-5
+    g = torch.randn(G * k, N, device="cuda")
+    if zero_mean:
+        g = g - g.mean(dim=0, keepdim=True)
+    got.backward(g)
+    want.backward(g.double())
+    for a, r in ((y, yd), (w, wd)):
+        assert (a.grad.double() - r.grad).abs().max() < 1e-4 * r.grad.abs().max().clamp_min(1.0)
+    if zero_mean:     # a constant in front of centred gradients: analytically zero, returned as zero
+        assert float(b.grad.abs().max()) == 0.0 and float(bd.grad.abs().max()) < 1e-3
+    else:
+        assert (b.grad.double() - bd.grad).abs().max() < 1e-4 * bd.grad.abs().max().clamp_min(1.0)
