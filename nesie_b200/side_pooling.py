@@ -27,6 +27,7 @@ import torch.nn.functional as F
 
 from . import _lib
 from . import bn_rows
+from . import gather_linear
 from . import group_max
 from . import mlp_rows
 from . import pool_rows
@@ -44,6 +45,38 @@ def rot_gpu(t):
     out[..., 1, 1] = c
     out[..., 2, 2] = 1
     return out
+
+
+class _GridSource:
+    """Input rows of one MiniPointNet, [grid point - box centre | features interpolated from the 3
+    nearest seeds | 0 pad], in factored form: the dense (B * n, ld) tensor is only built on demand."""
+
+    def __init__(self, xyz_count, table, idx, weight, head, ld):
+        self.m = xyz_count                 # seeds per scene
+        self.table = table                 # (B, m, C) point-major seed features
+        self.idx, self.weight, self.head = idx, weight, head      # (B, n, 3) each
+        self.ld = ld
+
+    @property
+    def shape(self):
+        return (self.idx.shape[0] * self.idx.shape[1], self.ld)
+
+    def tensors(self):
+        return [self.table, self.idx, self.weight, self.head]
+
+    def rows(self):
+        B, n = self.idx.shape[:2]
+        C = self.table.shape[2]
+        with torch.no_grad():
+            rows = torch.empty((B * n, self.ld), dtype=torch.float32, device=self.table.device)
+            with torch.cuda.device(self.table.device):
+                _lib.call("nesie_interp_rows", B, C, self.m, n, _lib.ptr(self.table), _lib.ptr(self.idx),
+                          _lib.ptr(self.weight), _lib.ptr(self.head), _lib.ptr(rows), self.ld, _lib.stream())
+        return rows
+
+
+def _gather_linear_enabled():
+    return os.environ.get("NESIE_GATHER_LINEAR", "1") != "0"
 
 
 class MiniPointNet(nn.Module):
@@ -188,11 +221,12 @@ class SidePooling(nn.Module):
 
     # ---- hot path hooks ----------------------------------------------------------------------
     def _grid_rows(self, origin_xyz, origin_features, grid, center, sides=1):
-        """grid (B, T, 3) world points, T = K * sides * G ordered (box, side, grid point) -> per side
+        """grid (B, T, 3) world points, T = K * sides * G ordered (box, side, grid point) -> per side the
         rows (B*K*G, ld) = [grid - centre | features interpolated from the 3 nearest seeds with
-        normalised inverse-distance weights | 0 pad]; one tensor when sides == 1, else a list.
-        Each side gets its own contiguous row block (the MiniPointNet of a side reads only its rows):
-        the 3-NN search runs once over all grid points, the row kernel once per side."""
+        normalised inverse-distance weights | 0 pad] as a _GridSource (factored: seed table + 3
+        neighbours + weights + relative position); one source when sides == 1, else a list.
+        Each side gets its own contiguous block (the MiniPointNet of a side reads only its rows):
+        the 3-NN search runs once over all grid points."""
         _lib.need_cuda(origin_xyz, origin_features, grid, center)
         B, T = grid.shape[:2]
         K = center.shape[1]
@@ -208,13 +242,7 @@ class SidePooling(nn.Module):
             out = []
             for i in range(sides):
                 pick = lambda t: t.view(B, K, sides, G, 3)[:, :, i].reshape(B, K * G, 3).contiguous()  # noqa: E731
-                rows = torch.empty((B * K * G, ld), dtype=torch.float32, device=grid.device)
-                idx_i, w_i, head_i = pick(idx), pick(weight), pick(head)   # kept alive across the launch
-                with torch.cuda.device(grid.device):
-                    _lib.call("nesie_interp_rows", B, C, origin_xyz.shape[1], K * G, _lib.ptr(table),
-                              _lib.ptr(idx_i), _lib.ptr(w_i), _lib.ptr(head_i),
-                              _lib.ptr(rows), ld, _lib.stream())
-                out.append(rows)
+                out.append(_GridSource(origin_xyz.shape[1], table, pick(idx), pick(weight), pick(head), ld))
         return out[0] if sides == 1 else out
 
     def _side_rows(self, origin_xyz, origin_features, side_grid, center):
@@ -222,10 +250,13 @@ class SidePooling(nn.Module):
         return self._grid_rows(origin_xyz, origin_features, side_grid, center, sides=6)
 
     def _mini_pointnet(self, mpn, rows, G):
-        """rows (R, ld) with every G consecutive rows one box -> (R / G, feature_dim)."""
+        """rows (R, ld) -- a tensor or a _GridSource -- with every G consecutive rows one box ->
+        (R / G, feature_dim)."""
         fused = self._mini_pointnet_pooled(mpn, rows, G)
         if fused is not None:
             return fused
+        if isinstance(rows, _GridSource):
+            rows = rows.rows()
         feat = _conv_bn_relu_conv(rows, mpn.first_conv[0], mpn.first_conv[1], mpn.first_conv[3],
                                   add_bias=False)
         # [max over the box's grid points, broadcast | feature] with the conv bias folded in
@@ -241,17 +272,34 @@ class SidePooling(nn.Module):
         (ca, bna, _, cb), (cc, bnc, _, cd) = mpn.first_conv, mpn.second_conv
         wa, wb = ca.weight.flatten(1), cb.weight.flatten(1)
         wc, wd = cc.weight.flatten(1), cd.weight.flatten(1)
-        if rows.shape[1] != wa.shape[1]:           # zero-padded input columns
-            wa = F.pad(wa, (0, rows.shape[1] - wa.shape[1]))
         C = wb.shape[0]
-        if not (bna.training and bnc.training and
-                pool_rows.supported(rows, wa, bna, wb, G) and wc.shape[1] == 2 * C and
+        R = rows.shape[0]
+        if not (bna.training and bnc.training and pool_rows.enabled() and pool_rows.pool_unit(G) > 0 and
+                R % G == 0 and (G & (G - 1)) == 0 and
+                bna.affine and bna.momentum is not None and bnc.affine and bnc.momentum is not None and
+                wa.shape[0] % 4 == 0 and wa.shape[0] <= 256 and wb.shape[1] == wa.shape[0] and
+                C % 4 == 0 and C <= 256 and wc.shape[1] == 2 * C and
                 cb.bias is not None and cd.bias is not None and
-                bnc.affine and bnc.momentum is not None and C % 4 == 0 and
                 wc.shape[0] % 4 == 0 and wc.shape[0] <= 256 and wd.shape[1] == wc.shape[0] and
                 wd.shape[0] % 4 == 0 and wd.shape[0] <= 256):
             return None
-        y1, parts1 = mlp_rows._LinearStats.apply(rows, wa)
+        if (isinstance(rows, _GridSource) and _gather_linear_enabled() and
+                gather_linear.supported(wa.shape[0]) and wa.shape[1] == 3 + rows.table.shape[2]):
+            # conv_a commuted with the interpolation: its GEMM runs over the seeds, the grid rows gather
+            # the transformed seeds (gather_linear.cu); the seed features carry no gradient (:83-95)
+            src = rows
+            B, m, Cs = src.table.shape
+            seeds = linear_rows(src.table.view(B * m, Cs), wa[:, 3:].contiguous())
+            y1, parts1 = gather_linear.gather_linear(seeds.view(B, m, -1), src.idx, src.weight, src.head,
+                                                     wa[:, :3], True)
+        else:
+            if isinstance(rows, _GridSource):
+                rows = rows.rows()
+            if rows.shape[1] != wa.shape[1]:           # zero-padded input columns
+                wa = F.pad(wa, (0, rows.shape[1] - wa.shape[1]))
+            if not mlp_rows.supported(rows, [(wa, bna)]):
+                return None
+            y1, parts1 = mlp_rows._LinearStats.apply(rows, wa)
         ya, gmax, arg = pool_rows.bn_relu_linear_max(y1, parts1, bna, wb, cb.bias, G, True)
         yc, partsc = pool_rows.concat_global_linear(ya, gmax, arg, cb.bias, wc, G, zero_mean_grad=True)
         return pool_rows.bn_relu_linear_max(yc, partsc, bnc, wd, cd.bias, G, False)
@@ -316,7 +364,8 @@ class SidePooling(nn.Module):
             return self._head(self.mlps_head[6], bbox_feats).transpose(2, 1)
 
         # tensors made on the caller's stream and read inside a branch (also by the branch's backward)
-        shared = [[side_rows[i], dist_feature] for i in range(6)] + [[bbox_rows]]
+        tens = lambda r: r.tensors() if isinstance(r, _GridSource) else [r]   # noqa: E731
+        shared = [tens(side_rows[i]) + [dist_feature] for i in range(6)] + [tens(bbox_rows)]
         outs = self._run_branches(branch, 7, size, shared)
         end_points[f"{prefix}side_scores"] = torch.stack(outs[:6], 0)
         end_points[f"{prefix}iou_scores"] = outs[6]

@@ -170,3 +170,62 @@ def test_concat_global_linear_matches_torch(zero_mean):
         assert float(b.grad.abs().max()) == 0.0 and float(bd.grad.abs().max()) < 1e-3
     else:
         assert (b.grad.double() - bd.grad).abs().max() < 1e-4 * bd.grad.abs().max().clamp_min(1.0)
+
+
+@pytest.mark.parametrize("J,C,with_head", [(3, 256, True), (1, 128, False), (3, 64, True), (1, 128, True)])
+def test_gather_linear_matches_torch(J, C, with_head):
+    from nesie_b200.gather_linear import gather_linear
+    torch.manual_seed(J * C)
+    B, M, n = 3, 200, 1000
+    table = torch.randn(B, M, C, device="cuda", requires_grad=True)
+    idx = torch.randint(0, M, (B, n, J), device="cuda", dtype=torch.int32)
+    w = torch.rand(B, n, J, device="cuda") if J == 3 else None
+    head = torch.randn(B, n, 3, device="cuda") if with_head else None
+    wx = torch.randn(C, 3, device="cuda", requires_grad=True) if with_head else None
+    y, parts = gather_linear(table, idx, w, head, wx, True)
+    td = table.detach().double().requires_grad_(True)
+    rows = torch.stack([td[b][idx[b].long()] for b in range(B)])            # (B, n, J, C)
+    want = (rows * (w.double().unsqueeze(-1) if w is not None else 1.0)).sum(2)
+    if with_head:
+        wxd = wx.detach().double().requires_grad_(True)
+        want = want + head.double() @ wxd.t()
+    want = want.reshape(B * n, C)
+    assert (y.double() - want).abs().max() < 1e-5
+    sums = parts.double().sum(0)
+    assert torch.allclose(sums[0], want.sum(0), rtol=1e-5, atol=1e-3)
+    assert torch.allclose(sums[1], (want * want).sum(0), rtol=1e-5, atol=1e-3)
+    g = torch.randn(B * n, C, device="cuda")
+    y.backward(g)
+    want.backward(g.double())
+    assert (table.grad.double() - td.grad).abs().max() < 1e-4
+    if with_head:
+        assert (wx.grad.double() - wxd.grad).abs().max() < 1e-3
+
+
+def test_factored_first_layer_equals_dense_rows(monkeypatch):
+    """SidePooling forward + parameter gradients with the first convolutions commuted with the
+    interpolation (gather_linear) against the dense-rows GEMM path."""
+    import copy
+    torch.manual_seed(2)
+    B, K, N, C = 2, 16, 128, 256
+    a = SidePooling(18, 1, 18, None, K // 2, "vote", seed_feat_dim=C).cuda()
+    b = copy.deepcopy(a)
+    g = torch.Generator().manual_seed(3)
+    center = (torch.rand(B, K, 3, generator=g) * 4 - 2).cuda()
+    size = (torch.rand(B, K, 3, generator=g) * 1.5 + 0.2).cuda()
+    heading = ((torch.rand(B, K, generator=g) - 0.5)).cuda()
+    ep = {"seed_points": (torch.rand(B, N, 3, generator=g) * 5 - 2.5).cuda(),
+          "seed_features": torch.randn(B, C, N, generator=g).cuda(),
+          "bbox_probs": torch.softmax(torch.randn(B, 6, 33, K // 2, generator=g), dim=2).cuda()}
+    outs = []
+    for mod, flag in ((a, "1"), (b, "0")):
+        monkeypatch.setenv("NESIE_GATHER_LINEAR", flag)
+        o = mod(center, size, heading, dict(ep))
+        ((o["side_scores"] ** 2).sum() + (o["iou_scores"] ** 2).sum()).backward()
+        outs.append(o)
+    for key in ("side_scores", "iou_scores"):
+        assert (outs[0][key] - outs[1][key]).abs().max() < 2e-5 * outs[1][key].abs().max().clamp_min(1.0), key
+    top = max(float(p.grad.norm()) for p in b.parameters())
+    for (name, p), q in zip(b.named_parameters(), a.parameters()):
+        err = float((q.grad - p.grad).norm())
+        assert err < 5e-3 * float(p.grad.norm()) or err < 1e-5 * top, (name, err, float(p.grad.norm()))
