@@ -275,18 +275,23 @@ int nesie_group_max_rows_backward(long long groups, int k, int c, const float *d
  * centre | features interpolated from 3 seeds]) needs its GEMM only over the b * m seeds,
  *   y[r, :] = sum_{i < j} weight[r, i] * table[batch(r), idx[r, i], :] + head[r, 0:3] @ wx^T,
  * table (b, m, c) = seed features @ W_f^T (point-major), idx / weight (b, n, j) with j = 3 (contraction as
- * in three_interpolate) or j = 1 (weight nullable = 1), head (b, n, 3) / wx (c, 3) nullable together,
- * y (b * n, c); c / 4 a power of two <= 256.  col_parts (nullable): nesie_gather_linear_parts(b, c, n)
- * blocks of [2][c] column sums of y and y^2 for nesie_bn_rows_forward_fused. */
+ * in three_interpolate) or j = 1 (weight nullable = 1); wx (c, 3) comes with head (b, n, 3) or, for the SA
+ * grouping (ops/group_points/group_points.py:104-160: rows = [(neighbour - centre) / radius | features]),
+ * with xyz (b, m, 3) + center (b, n / ns, 3): head[r] = (xyz[idx[r]] - center[r / ns]) * (1 / radius)
+ * (radius 0: not normalised), j = 1.  y (b * n, c); c / 4 a power of two <= 256.  col_parts (nullable):
+ * nesie_gather_linear_parts(b, c, n) blocks of [2][c] column sums of y and y^2 for
+ * nesie_bn_rows_forward_fused. */
 int nesie_gather_linear_parts(int b, int c, int n);
 int nesie_gather_linear_forward(int b, int c, int m, int n, int j, const float *table, const int *idx,
-                                const float *weight, const float *head, const float *wx, float *y,
+                                const float *weight, const float *head, const float *wx,
+                                const float *xyz, const float *center, int ns, float radius, float *y,
                                 float *col_parts, void *stream);
 /* d_table[batch(r), idx[r, i], :] += weight[r, i] * d_y[r, :] (vector reductions; d_table zeroed by the
- * caller) and, with head, dwx_part: nesie_gather_linear_parts blocks of [c][4] partial sums of
- * d_y[r, o] * head[r, 0..2] (fourth entry 0) for nesie_gemm_sum_partials. */
+ * caller) and, with head (or xyz + center), dwx_part: nesie_gather_linear_parts blocks of [c][4] partial
+ * sums of d_y[r, o] * head[r, 0..2] (fourth entry 0) for nesie_gemm_sum_partials. */
 int nesie_gather_linear_backward(int b, int c, int m, int n, int j, const float *d_y, const int *idx,
-                                 const float *weight, const float *head, float *d_table,
+                                 const float *weight, const float *head, const float *xyz,
+                                 const float *center, int ns, float radius, float *d_table,
                                  float *dwx_part, void *stream);
 
 /* Inverse-distance interpolation into row-major GEMM rows: the grid features of the SidePooling

@@ -53,8 +53,8 @@ SIGNATURES = {
     "nesie_gemm_nt_3xtf32_bnbwd": [_ll, _i, _i, _p, _ll, _p, _p, _ll, _p, _ll, _p, _p, _p],
     "nesie_gemm_nt_3xtf32_pool": [_ll, _i, _i, _p, _ll, _p, _p, _ll, _p, _p, _p, _i, _p, _p, _p, _p, _p, _i, _p],
     "nesie_gather_linear_parts": [_i, _i, _i],
-    "nesie_gather_linear_forward": [_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p],
-    "nesie_gather_linear_backward": [_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p],
+    "nesie_gather_linear_forward": [_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _i, _f, _p, _p, _p],
+    "nesie_gather_linear_backward": [_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _f, _p, _p, _p],
     "nesie_pool_finalize": [_ll, _i, _i, _i, _p, _p, _p, _p, _p, _p],
     "nesie_pool_wgrad_parts": [_ll],
     "nesie_pool_wgrad": [_ll, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p],

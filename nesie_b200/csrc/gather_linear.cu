@@ -9,6 +9,8 @@
 //
 //   y[r, :] = sum_j w[r, j] * (table @ W_f^T)[idx[r, j], :]  +  head[r, :] @ W_x^T
 //
+// (head given, or computed as (xyz[idx] - center) / radius for the SA grouping)
+//
 // needs the GEMM only over the TABLE (8192 seeds instead of 65536 .. 262144 grid rows per box set);
 // what is left per row is this gather of already-transformed rows plus 3 FMAs per output for the
 // coordinate columns.  The kernel also leaves the column sums of y and y^2 (the BatchNorm statistics
@@ -32,6 +34,7 @@ template <int J>
 __global__ void __launch_bounds__(GL_THREADS) gather_linear_fwd_kernel(
     int c, int m, int n, const float *__restrict__ table, const int *__restrict__ idx,
     const float *__restrict__ weight, const float *__restrict__ head, const float *__restrict__ wx,
+    const float *__restrict__ xyz, const float *__restrict__ center, int ns, float inv_radius,
     float *__restrict__ y, float *__restrict__ col_parts) {
   __shared__ float4 s_red[GL_THREADS];
   const int tpr = c >> 2, lanes = GL_THREADS / tpr;
@@ -39,7 +42,7 @@ __global__ void __launch_bounds__(GL_THREADS) gather_linear_fwd_kernel(
   const int b = blockIdx.y;
   const float4 *tab = reinterpret_cast<const float4 *>(table + (size_t)b * m * c) + c4;
   float4 wx0 = make_float4(0.f, 0.f, 0.f, 0.f), wx1 = wx0, wx2 = wx0;   // columns 0..2 of W_x for my 4 outputs
-  if (head) {
+  if (wx) {
     const float *w = wx + (size_t)c4 * 12;
     wx0 = make_float4(__ldg(w), __ldg(w + 3), __ldg(w + 6), __ldg(w + 9));
     wx1 = make_float4(__ldg(w + 1), __ldg(w + 4), __ldg(w + 7), __ldg(w + 10));
@@ -49,18 +52,28 @@ __global__ void __launch_bounds__(GL_THREADS) gather_linear_fwd_kernel(
   for (long long t = (long long)blockIdx.x * lanes + lane; t < n; t += (long long)gridDim.x * lanes) {
     const size_t r = (size_t)b * n + t;
     float4 v;
+    int a0;
     if (J == 3) {
-      const int a0 = __ldg(idx + r * 3), a1 = __ldg(idx + r * 3 + 1), a2 = __ldg(idx + r * 3 + 2);
+      a0 = __ldg(idx + r * 3);
+      const int a1 = __ldg(idx + r * 3 + 1), a2 = __ldg(idx + r * 3 + 2);
       const float w0 = __ldg(weight + r * 3), w1 = __ldg(weight + r * 3 + 1), w2 = __ldg(weight + r * 3 + 2);
       const float4 p0 = __ldg(tab + (size_t)a0 * tpr), p1 = __ldg(tab + (size_t)a1 * tpr), p2 = __ldg(tab + (size_t)a2 * tpr);
       v.x = fmaf(w2, p2.x, fmaf(w0, p0.x, w1 * p1.x)); v.y = fmaf(w2, p2.y, fmaf(w0, p0.y, w1 * p1.y));
       v.z = fmaf(w2, p2.z, fmaf(w0, p0.z, w1 * p1.z)); v.w = fmaf(w2, p2.w, fmaf(w0, p0.w, w1 * p1.w));
     } else {
-      v = __ldg(tab + (size_t)__ldg(idx + r) * tpr);
+      a0 = __ldg(idx + r);
+      v = __ldg(tab + (size_t)a0 * tpr);
       if (weight) { const float w0 = __ldg(weight + r); v.x *= w0; v.y *= w0; v.z *= w0; v.w *= w0; }
     }
-    if (head) {
-      const float h0 = __ldg(head + r * 3), h1 = __ldg(head + r * 3 + 1), h2 = __ldg(head + r * 3 + 2);
+    if (wx) {
+      float h0, h1, h2;
+      if (head) {
+        h0 = __ldg(head + r * 3); h1 = __ldg(head + r * 3 + 1); h2 = __ldg(head + r * 3 + 2);
+      } else {   // SA grouping: (neighbour - centre) [* 1 / radius], as nesie_group_rows writes it
+        const float *p = xyz + ((size_t)b * m + a0) * 3, *q = center + ((size_t)b * (n / ns) + t / ns) * 3;
+        h0 = __fsub_rn(__ldg(p), __ldg(q)); h1 = __fsub_rn(__ldg(p + 1), __ldg(q + 1)); h2 = __fsub_rn(__ldg(p + 2), __ldg(q + 2));
+        if (inv_radius > 0.f) { h0 = __fmul_rn(h0, inv_radius); h1 = __fmul_rn(h1, inv_radius); h2 = __fmul_rn(h2, inv_radius); }
+      }
       v.x = fmaf(h2, wx2.x, fmaf(h1, wx1.x, fmaf(h0, wx0.x, v.x))); v.y = fmaf(h2, wx2.y, fmaf(h1, wx1.y, fmaf(h0, wx0.y, v.y)));
       v.z = fmaf(h2, wx2.z, fmaf(h1, wx1.z, fmaf(h0, wx0.z, v.z))); v.w = fmaf(h2, wx2.w, fmaf(h1, wx1.w, fmaf(h0, wx0.w, v.w)));
     }
@@ -89,7 +102,8 @@ __global__ void __launch_bounds__(GL_THREADS) gather_linear_fwd_kernel(
 template <int J>
 __global__ void __launch_bounds__(GL_THREADS) gather_linear_bwd_kernel(
     int c, int m, int n, const float *__restrict__ d_y, const int *__restrict__ idx,
-    const float *__restrict__ weight, const float *__restrict__ head, float *__restrict__ d_table,
+    const float *__restrict__ weight, const float *__restrict__ head, const float *__restrict__ xyz,
+    const float *__restrict__ center, int ns, float inv_radius, float *__restrict__ d_table,
     float *__restrict__ dwx_part) {
   __shared__ float4 s_red[GL_THREADS];
   const int tpr = c >> 2, lanes = GL_THREADS / tpr;
@@ -106,8 +120,15 @@ __global__ void __launch_bounds__(GL_THREADS) gather_linear_bwd_kernel(
       const float w = weight ? __ldg(weight + r * J + j) : 1.f;
       red_add_v4(tab + (size_t)a * c, make_float4(w * d.x, w * d.y, w * d.z, w * d.w));
     }
-    if (head) {
-      const float h0 = __ldg(head + r * 3), h1 = __ldg(head + r * 3 + 1), h2 = __ldg(head + r * 3 + 2);
+    if (dwx_part) {
+      float h0, h1, h2;
+      if (head) {
+        h0 = __ldg(head + r * 3); h1 = __ldg(head + r * 3 + 1); h2 = __ldg(head + r * 3 + 2);
+      } else {
+        const float *p = xyz + ((size_t)b * m + __ldg(idx + r * J)) * 3, *q = center + ((size_t)b * (n / ns) + t / ns) * 3;
+        h0 = __fsub_rn(__ldg(p), __ldg(q)); h1 = __fsub_rn(__ldg(p + 1), __ldg(q + 1)); h2 = __fsub_rn(__ldg(p + 2), __ldg(q + 2));
+        if (inv_radius > 0.f) { h0 = __fmul_rn(h0, inv_radius); h1 = __fmul_rn(h1, inv_radius); h2 = __fmul_rn(h2, inv_radius); }
+      }
       g0.x = fmaf(d.x, h0, g0.x); g0.y = fmaf(d.y, h0, g0.y); g0.z = fmaf(d.z, h0, g0.z); g0.w = fmaf(d.w, h0, g0.w);
       g1.x = fmaf(d.x, h1, g1.x); g1.y = fmaf(d.y, h1, g1.y); g1.z = fmaf(d.z, h1, g1.z); g1.w = fmaf(d.w, h1, g1.w);
       g2.x = fmaf(d.x, h2, g2.x); g2.y = fmaf(d.y, h2, g2.y); g2.z = fmaf(d.z, h2, g2.z); g2.w = fmaf(d.w, h2, g2.w);
@@ -159,40 +180,51 @@ extern "C" int nesie_gather_linear_parts(int b, int c, int n) {
 
 extern "C" int nesie_gather_linear_forward(int b, int c, int m, int n, int j, const float *table,
                                            const int *idx, const float *weight, const float *head,
-                                           const float *wx, float *y, float *col_parts, void *stream) {
+                                           const float *wx, const float *xyz, const float *center,
+                                           int ns, float radius, float *y, float *col_parts,
+                                           void *stream) {
   NESIE_REQUIRE(b >= 0 && m >= 1 && n >= 0 && (j == 1 || j == 3), "need b >= 0, m >= 1, n >= 0, j in {1, 3}");
   NESIE_REQUIRE(gl_shape_ok(c), "c / 4 must be a power of two <= 256");
   if (b == 0 || n == 0) return NESIE_OK;
   NESIE_REQUIRE(table && idx && y, "null pointer");
   NESIE_REQUIRE(j == 1 || weight, "three neighbours need their weights");
-  NESIE_REQUIRE((head == nullptr) == (wx == nullptr), "head and wx go together");
+  NESIE_REQUIRE(!(head && xyz) && (xyz == nullptr) == (center == nullptr), "head, or xyz + center, or neither");
+  NESIE_REQUIRE((wx != nullptr) == (head != nullptr || xyz != nullptr), "wx goes with head or xyz + center");
+  NESIE_REQUIRE(!xyz || (j == 1 && ns >= 1 && n % ns == 0), "xyz + center: one neighbour per row, ns | n");
   NESIE_REQUIRE(b <= 65535, "b > 65535");
+  const float inv_radius = radius > 0.f ? 1.0f / radius : 0.f;
+  if (!xyz) ns = 1;
   NESIE_REQUIRE((reinterpret_cast<uintptr_t>(table) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
                     (reinterpret_cast<uintptr_t>(col_parts) & 15) == 0, "table, y and col_parts must be 16-byte aligned");
   const dim3 grid(gl_grid_x(c, n, b), b);
   if (j == 3)
-    gather_linear_fwd_kernel<3><<<grid, GL_THREADS, 0, (cudaStream_t)stream>>>(c, m, n, table, idx, weight, head, wx, y, col_parts);
+    gather_linear_fwd_kernel<3><<<grid, GL_THREADS, 0, (cudaStream_t)stream>>>(c, m, n, table, idx, weight, head, wx, xyz, center, ns, inv_radius, y, col_parts);
   else
-    gather_linear_fwd_kernel<1><<<grid, GL_THREADS, 0, (cudaStream_t)stream>>>(c, m, n, table, idx, weight, head, wx, y, col_parts);
+    gather_linear_fwd_kernel<1><<<grid, GL_THREADS, 0, (cudaStream_t)stream>>>(c, m, n, table, idx, weight, head, wx, xyz, center, ns, inv_radius, y, col_parts);
   return check_launch("nesie_gather_linear_forward");
 }
 
 extern "C" int nesie_gather_linear_backward(int b, int c, int m, int n, int j, const float *d_y,
                                             const int *idx, const float *weight, const float *head,
+                                            const float *xyz, const float *center, int ns, float radius,
                                             float *d_table, float *dwx_part, void *stream) {
   NESIE_REQUIRE(b >= 0 && m >= 1 && n >= 0 && (j == 1 || j == 3), "need b >= 0, m >= 1, n >= 0, j in {1, 3}");
   NESIE_REQUIRE(gl_shape_ok(c), "c / 4 must be a power of two <= 256");
   if (b == 0 || n == 0) return NESIE_OK;
   NESIE_REQUIRE(d_y && idx && d_table, "null pointer");
   NESIE_REQUIRE(j == 1 || weight, "three neighbours need their weights");
-  NESIE_REQUIRE((head == nullptr) == (dwx_part == nullptr), "head and dwx_part go together");
+  NESIE_REQUIRE(!(head && xyz) && (xyz == nullptr) == (center == nullptr), "head, or xyz + center, or neither");
+  NESIE_REQUIRE((dwx_part != nullptr) == (head != nullptr || xyz != nullptr), "dwx_part goes with head or xyz + center");
+  NESIE_REQUIRE(!xyz || (j == 1 && ns >= 1 && n % ns == 0), "xyz + center: one neighbour per row, ns | n");
   NESIE_REQUIRE(b <= 65535, "b > 65535");
+  const float inv_radius = radius > 0.f ? 1.0f / radius : 0.f;
+  if (!xyz) ns = 1;
   NESIE_REQUIRE((reinterpret_cast<uintptr_t>(d_table) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_y) & 15) == 0,
                 "d_table and d_y must be 16-byte aligned");
   const dim3 grid(gl_grid_x(c, n, b), b);
   if (j == 3)
-    gather_linear_bwd_kernel<3><<<grid, GL_THREADS, 0, (cudaStream_t)stream>>>(c, m, n, d_y, idx, weight, head, d_table, dwx_part);
+    gather_linear_bwd_kernel<3><<<grid, GL_THREADS, 0, (cudaStream_t)stream>>>(c, m, n, d_y, idx, weight, head, xyz, center, ns, inv_radius, d_table, dwx_part);
   else
-    gather_linear_bwd_kernel<1><<<grid, GL_THREADS, 0, (cudaStream_t)stream>>>(c, m, n, d_y, idx, weight, head, d_table, dwx_part);
+    gather_linear_bwd_kernel<1><<<grid, GL_THREADS, 0, (cudaStream_t)stream>>>(c, m, n, d_y, idx, weight, head, xyz, center, ns, inv_radius, d_table, dwx_part);
   return check_launch("nesie_gather_linear_backward");
 }

@@ -16,8 +16,8 @@ def supported(c):
 class _GatherLinear(Function):
 
     @staticmethod
-    def forward(ctx, table, idx, weight, head, wx, want_stats):
-        _lib.need_cuda(table, idx, weight, head, wx)
+    def forward(ctx, table, idx, weight, head, wx, want_stats, xyz=None, center=None, ns=1, radius=0.0):
+        _lib.need_cuda(table, idx, weight, head, wx, xyz, center)
         table = table.contiguous()
         B, M, C = table.shape
         n, J = idx.shape[1], idx.shape[2]
@@ -30,10 +30,11 @@ class _GatherLinear(Function):
         wx_c = wx.contiguous() if wx is not None else None
         with torch.cuda.device(dev):
             _lib.call("nesie_gather_linear_forward", B, C, M, n, J, _lib.ptr(table), _lib.ptr(idx),
-                      _lib.ptr(weight), _lib.ptr(head), _lib.ptr(wx_c), _lib.ptr(y), _lib.ptr(parts),
-                      _lib.stream())
-        ctx.save_for_backward(idx, weight, head)
+                      _lib.ptr(weight), _lib.ptr(head), _lib.ptr(wx_c), _lib.ptr(xyz), _lib.ptr(center),
+                      ns, float(radius), _lib.ptr(y), _lib.ptr(parts), _lib.stream())
+        ctx.save_for_backward(idx, weight, head, xyz, center)
         ctx.shape = (B, M, C, n, J)
+        ctx.ns, ctx.radius = ns, float(radius)
         ctx.has_wx = wx is not None
         if parts is not None:
             ctx.mark_non_differentiable(parts)
@@ -42,9 +43,9 @@ class _GatherLinear(Function):
 
     @staticmethod
     def backward(ctx, d_y, _gparts):
-        idx, weight, head = ctx.saved_tensors
+        idx, weight, head, xyz, center = ctx.saved_tensors
         if d_y is None:
-            return (None,) * 6
+            return (None,) * 10
         B, M, C, n, J = ctx.shape
         d_y = d_y.contiguous()
         dev = d_y.device
@@ -56,13 +57,17 @@ class _GatherLinear(Function):
                                 device=dev)
         with torch.cuda.device(dev):
             _lib.call("nesie_gather_linear_backward", B, C, M, n, J, _lib.ptr(d_y), _lib.ptr(idx),
-                      _lib.ptr(weight), _lib.ptr(head if want_wx else None), _lib.ptr(d_table),
-                      _lib.ptr(parts), _lib.stream())
+                      _lib.ptr(weight), _lib.ptr(head if want_wx else None),
+                      _lib.ptr(xyz if want_wx else None), _lib.ptr(center if want_wx else None), ctx.ns,
+                      ctx.radius, _lib.ptr(d_table), _lib.ptr(parts), _lib.stream())
         d_wx = sum_partials(parts)[:, :3] if want_wx else None
-        return (d_table if ctx.needs_input_grad[0] else None), None, None, None, d_wx, None
+        return ((d_table if ctx.needs_input_grad[0] else None), None, None, None, d_wx, None, None, None,
+                None, None)
 
 
-def gather_linear(table, idx, weight=None, head=None, wx=None, want_stats=False):
-    """table (B, M, C), idx (B, n, J) int32 [, weight (B, n, J), head (B, n, 3), wx (C, 3)] ->
+def gather_linear(table, idx, weight=None, head=None, wx=None, want_stats=False, xyz=None, center=None,
+                  ns=1, radius=0.0):
+    """table (B, M, C), idx (B, n, J) int32 [, weight (B, n, J)], wx (C, 3) with head (B, n, 3) or with
+    xyz (B, M, 3) + center (B, n / ns, 3) (head = (xyz[idx] - center) / radius, no gradient to either) ->
     (y (B * n, C), column-sum partials (parts, 2, C) | None)."""
-    return _GatherLinear.apply(table, idx, weight, head, wx, want_stats)
+    return _GatherLinear.apply(table, idx, weight, head, wx, want_stats, xyz, center, ns, radius)

@@ -208,6 +208,29 @@ def mlp_rows(x, layers, pool_k=0):
     consecutive rows -> (R / pool_k, C).  `supported(x, layers)` must hold."""
     w0, _ = layers[0]
     y, parts = _LinearStats.apply(x, w0)
+    return mlp_rows_tail(y, parts, layers, pool_k)
+
+
+def supported_tail(layers):
+    """The layers after the first (whose output y (R, N1) and column sums come from elsewhere, e.g.
+    gather_linear): bias-free convs with training-mode affine BatchNorms on the fused kernels."""
+    if not enabled():
+        return False
+    k = layers[0][0].shape[0]
+    if k > 512 or k % 4:
+        return False
+    for li, (w, bn) in enumerate(layers):
+        n = w.shape[0]
+        if not (bn.training and bn.affine and bn.momentum is not None):
+            return False
+        if li and not (w.shape[1] == k and n % 4 == 0 and 4 <= n <= 256):
+            return False
+        k = n
+    return True
+
+
+def mlp_rows_tail(y, parts, layers, pool_k=0):
+    """mlp_rows from the first layer's pre-activation y = x @ W1^T and its column-sum partials on."""
     for li in range(1, len(layers)):
         bn = layers[li - 1][1]
         rm, rv = _bn_buffers(bn)

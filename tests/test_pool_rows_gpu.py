@@ -229,3 +229,48 @@ def test_factored_first_layer_equals_dense_rows(monkeypatch):
     for (name, p), q in zip(b.named_parameters(), a.parameters()):
         err = float((q.grad - p.grad).norm())
         assert err < 5e-3 * float(p.grad.norm()) or err < 1e-5 * top, (name, err, float(p.grad.norm()))
+
+
+def test_gather_linear_sa_grouping_head():
+    """xyz + center mode: head = (xyz[idx] - center) / radius, as nesie_group_rows builds the rows."""
+    from nesie_b200.gather_linear import gather_linear
+    torch.manual_seed(8)
+    B, M, npoint, ns, C = 2, 300, 40, 16, 128
+    table = torch.randn(B, M, C, device="cuda")
+    xyz = torch.randn(B, M, 3, device="cuda")
+    center = torch.randn(B, npoint, 3, device="cuda")
+    idx = torch.randint(0, M, (B, npoint * ns, 1), device="cuda", dtype=torch.int32)
+    wx = torch.randn(C, 3, device="cuda", requires_grad=True)
+    y, _ = gather_linear(table, idx, None, None, wx, True, xyz, center, ns, 0.4)
+    li = idx.long().squeeze(-1)
+    head = (torch.stack([xyz[b][li[b]] for b in range(B)]) - center.repeat_interleave(ns, dim=1)) * (1.0 / 0.4)
+    want = torch.stack([table[b][li[b]] for b in range(B)]).double() + head.double() @ wx.detach().double().t()
+    assert (y.double() - want.reshape(-1, C)).abs().max() < 1e-5
+    g = torch.randn_like(y)
+    y.backward(g)
+    want_wx = g.double().t() @ head.double().reshape(-1, 3)
+    assert (wx.grad.double() - want_wx).abs().max() < 1e-3
+
+
+def test_sa_module_commuted_first_layer_equals_grouped_rows(monkeypatch):
+    from nesie_b200.pointnet_modules import PointSAModule
+    torch.manual_seed(6)
+    sa = PointSAModule(num_point=64, radius=0.4, num_sample=16, mlp_channels=[128, 128, 128, 256],
+                       use_xyz=True, normalize_xyz=True).cuda()
+    xyz = torch.rand(2, 512, 3, device="cuda")
+    feats = torch.randn(2, 128, 512, device="cuda", requires_grad=True)
+    res = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("NESIE_GATHER_LINEAR", flag)
+        sa.zero_grad()
+        feats.grad = None
+        _, out, _ = sa(xyz, feats)
+        (out * out).sum().backward()
+        res.append((out.detach().clone(), feats.grad.clone(), [p.grad.clone() for p in sa.parameters()]))
+    (o1, f1, p1), (o0, f0, p0) = res
+    assert (o1 - o0).abs().max() < 2e-5 * o0.abs().max()
+    assert (f1 - f0).norm() < 2e-3 * f0.norm()
+    top = max(float(g.norm()) for g in p0)
+    for (name, _), a, b in zip(sa.named_parameters(), p1, p0):
+        err = float((a - b).norm())
+        assert err < 5e-3 * float(b.norm()) or err < 1e-5 * top, (name, err, float(b.norm()))
