@@ -290,13 +290,32 @@ def gemm_census(trace, dev, min_reps=5, hbm_gbs=6459.6, bf16_tflops=1684.1):
     shapes = {}
     for name, a in trace:
         if name in fam:
-            key = (fam[name], int(a[0]), int(a[1]), int(a[2]))
+            key = (fam[name], int(a[0]), int(a[1]), int(a[2]), 1, 0, 0)
+            shapes[key] = shapes.get(key, 0) + 1
+        elif name == "nesie_gemm_nt_3xtf32_pool":
+            # (store the output?, pooling unit, rows per group bias): the launch is timed in its own mode
+            key = ("gemm_nt", int(a[0]), int(a[1]), int(a[2]), int(a[6] is not None),
+                   int(a[11]) if a[12] is not None else 0, int(a[17]) if a[16] is not None else 0)
             shapes[key] = shapes.get(key, 0) + 1
     out = {}
-    for (family, R, N, K), count in sorted(shapes.items()):
+    for (family, R, N, K, store, pool_u, grp_k), count in sorted(shapes.items()):
         if R < 1:
             continue
-        if family == "gemm_nt":
+        if family == "gemm_nt" and (not store or pool_u or grp_k):
+            per = 4 * R * K + (4 * R * N if store else 0)
+            ncopy = max(1, min(8, int(300e6 // max(per, 1)) + 1))
+            xs = [torch.randn(R, K, device=dev) for _ in range(ncopy)]
+            ys = [torch.empty(R, N, device=dev) if store else None for _ in range(ncopy)]
+            img = lr._pack(torch.randn(N, K, device=dev), N, K, K, 1)
+            pmax = torch.empty((R // pool_u, N), device=dev) if pool_u else None
+            amax = torch.empty((R // pool_u, N), dtype=torch.uint8, device=dev) if pool_u else None
+            grp = torch.randn((R // grp_k, N), device=dev) if grp_k else None
+
+            def launch(i):
+                _lib.call("nesie_gemm_nt_3xtf32_pool", R, N, K, _lib.ptr(xs[i % ncopy]), K, _lib.ptr(img),
+                          _lib.ptr(ys[i % ncopy]), N, None, None, None, pool_u, _lib.ptr(pmax), _lib.ptr(amax),
+                          None, None, _lib.ptr(grp), grp_k, _lib.stream())
+        elif family == "gemm_nt":
             # operands rotate through enough copies that nothing is served from the 126 MB L2
             per = 4 * R * (K + N)
             ncopy = max(1, min(8, int(300e6 // max(per, 1)) + 1))
@@ -332,7 +351,8 @@ def gemm_census(trace, dev, min_reps=5, hbm_gbs=6459.6, bf16_tflops=1684.1):
         torch.cuda.synchronize()
         ms = a.elapsed_time(b) / reps
         if os.environ.get("NESIE_BENCH_CENSUS_DUMP"):
-            sys.stderr.write(f"[census] {family} R={R} K={K} N={N} x{count}: {ms * 1e3:.1f} us, "
+            mode = ("" if store else " no-store") + (f" pool{pool_u}" if pool_u else "") + (f" grp{grp_k}" if grp_k else "")
+            sys.stderr.write(f"[census] {family} R={R} K={K} N={N}{mode} x{count}: {ms * 1e3:.1f} us, "
                              f"{per / (ms * 1e-3) / 1e9:.0f} GB/s, {2.0 * R * N * K / (ms * 1e-3) / 1e12:.1f} TF/s fp32-equiv\n")
         f = out.setdefault(family, dict(bytes=0.0, ms=0.0, launches=0, flops=0.0, best=None, bound_ms=0.0))
         # per-launch lower bound: HBM time of the algorithmic bytes vs tensor time of the 3 TF32 MMAs per

@@ -771,9 +771,36 @@ static int gemm_nt_impl(long long r, int n, int k, const float *a, long long lda
       if (q.nstages > G_MAXSTAGES) q.nstages = G_MAXSTAGES;
       const size_t smem = (size_t)q.nstages * stage + epi + T_CTRL_BYTES;
       const int regs = gemm_tma_regs();
-      auto kern = regs == 64 ? gemm_nt_tma_kernel<64> : (regs == 88 ? gemm_nt_tma_kernel<88> : gemm_nt_tma_kernel<96>);
-      NESIE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G_MAX_DYN_SMEM));
       int grid = gemm_grid_sms();
+      // CTA pairs sharing the weight slabs (multicast): where the weight stream outweighs the
+      // activations (wide N x K) and there are at least two tiles per CTA
+      if (regs == 96 && gemm_pair_enabled() && p.npad * p.nslab >= 128 * 4 && ntiles_all >= 2 * grid) {
+        auto kp = gemm_nt_tma_kernel<96, true>;
+        NESIE_CUDA(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, G_MAX_DYN_SMEM));
+        cudaLaunchConfig_t cfg = {};
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.gridDim = dim3((unsigned)(grid & ~1), 1, 1);
+        cfg.blockDim = dim3(T_THREADS, 1, 1);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = (cudaStream_t)stream;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        static int max_pairs = -1;   // co-resident clusters of two (one CTA per SM)
+        if (max_pairs < 0) {
+          int nc = 0;
+          if (cudaOccupancyMaxActiveClusters(&nc, kp, &cfg) != cudaSuccess) { (void)cudaGetLastError(); nc = 0; }
+          max_pairs = nc;
+        }
+        if (max_pairs >= 8) {
+          if ((int)cfg.gridDim.x > 2 * max_pairs) cfg.gridDim.x = 2u * (unsigned)max_pairs;
+          NESIE_CUDA(cudaLaunchKernelEx(&cfg, kp, tm, q));
+          return check_launch("nesie_gemm_nt_3xtf32 (pairs)");
+        }
+      }
+      auto kern = regs == 64 ? gemm_nt_tma_kernel<64, false>
+                             : (regs == 88 ? gemm_nt_tma_kernel<88, false> : gemm_nt_tma_kernel<96, false>);
+      NESIE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G_MAX_DYN_SMEM));
       if (ntiles_all < grid) grid = ntiles_all;
       kern<<<grid, T_THREADS, smem, (cudaStream_t)stream>>>(tm, q);
       return check_launch("nesie_gemm_nt_3xtf32");

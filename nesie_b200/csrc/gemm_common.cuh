@@ -77,6 +77,23 @@ __device__ __forceinline__ void g_commit(unsigned mbar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar)
                : "memory");
 }
+// ... and on the barrier at the same offset in every CTA of `cta_mask` (CTA pairs that share operand
+// slabs through multicast copies: a stage is free once BOTH CTAs' MMAs have read it)
+__device__ __forceinline__ void g_commit_mc(unsigned mbar, unsigned short cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(mbar), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ unsigned g_cluster_ctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void g_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void g_mbar_init(unsigned mbar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
 }
@@ -109,6 +126,15 @@ __device__ __forceinline__ void g_bulk_g2s(unsigned dst, const void *src, unsign
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
       ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar)
+      : "memory");
+}
+// the same copy delivered to the same shared-memory offset (and signalled on the barrier at the same
+// offset) of every CTA in cta_mask
+__device__ __forceinline__ void g_bulk_g2s_mc(unsigned dst, const void *src, unsigned bytes,
+                                              unsigned mbar, unsigned short cta_mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+      ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar), "h"(cta_mask)
       : "memory");
 }
 __device__ __forceinline__ void g_tmem_ld32(unsigned taddr, unsigned (&r)[32]) {

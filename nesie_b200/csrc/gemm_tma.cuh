@@ -106,7 +106,11 @@ struct GemmTmaParams {
   int dbg;
 };
 
-template <int MAXREG>
+// PAIR: launched as clusters of two CTAs that walk tiles 2i, 2i + 1 in lockstep; each CTA fetches half
+// of every weight slab and multicasts it to both, so a slab crosses L2 -> shared memory once per PAIR
+// of row tiles (at N x K >= 128 x 256 the weight stream, 2x the activation bytes per tile, is what
+// bounds the kernel: profiles/r02_ncu_notes.md).  A stage is refilled when both CTAs have read it.
+template <int MAXREG, bool PAIR>
 __global__ void __maxnreg__(MAXREG)
 gemm_nt_tma_kernel(const __grid_constant__ CUtensorMap tmA, GemmTmaParams p) {
   // No static shared memory and no alignment slack: the kernel's 224 KB + 256 B then leave room on
@@ -121,6 +125,10 @@ gemm_nt_tma_kernel(const __grid_constant__ CUtensorMap tmA, GemmTmaParams p) {
   const int ntiles = (p.R + G_TILE - 1) / G_TILE;
   const unsigned smem_base = g_smem_u32(smem);
   if (smem_base & 1023u) __trap();
+  const int crank = PAIR ? (int)g_cluster_ctarank() : 0;
+  // first tile of this CTA (of its pair) and the tile stride; a pair's second CTA may run one tile past
+  // the end (all-zero operand rows, nothing stored) so that both make the same number of steps
+  const int tile0 = PAIR ? (int)(blockIdx.x & ~1u) : (int)blockIdx.x;
   unsigned long long *ctrl = reinterpret_cast<unsigned long long *>(
       smem + (size_t)p.nstages * stage_bytes + (size_t)T_EPIW * 4096);
   unsigned long long *s_tma = ctrl, *s_full = ctrl + G_MAXSTAGES, *s_empty = ctrl + 2 * G_MAXSTAGES;
@@ -138,7 +146,7 @@ gemm_nt_tma_kernel(const __grid_constant__ CUtensorMap tmA, GemmTmaParams p) {
     for (int s = 0; s < p.nstages; ++s) {
       g_mbar_init(g_smem_u32(&s_tma[s]), 1);
       g_mbar_init(g_smem_u32(&s_full[s]), 32 * T_XFW);
-      g_mbar_init(g_smem_u32(&s_empty[s]), 1);
+      g_mbar_init(g_smem_u32(&s_empty[s]), PAIR ? 2 : 1);
     }
     for (int a = 0; a < 2; ++a) {
       g_mbar_init(g_smem_u32(&s_accf[a]), 1);
@@ -148,6 +156,7 @@ gemm_nt_tma_kernel(const __grid_constant__ CUtensorMap tmA, GemmTmaParams p) {
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (PAIR) g_cluster_sync();   // the peer's barriers exist before anything is multicast to them
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const unsigned tmem = s_tmem;
 
@@ -156,7 +165,8 @@ gemm_nt_tma_kernel(const __grid_constant__ CUtensorMap tmA, GemmTmaParams p) {
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
       unsigned it = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int tb = tile0; tb < ntiles; tb += gridDim.x) {
+        const int tile = tb + crank;
         for (int ks = 0; ks < p.nslab; ++ks, ++it) {
           const int st = it % p.nstages;
           const unsigned ph = (it / p.nstages) & 1u;
@@ -167,8 +177,14 @@ gemm_nt_tma_kernel(const __grid_constant__ CUtensorMap tmA, GemmTmaParams p) {
           g_mbar_arm(bar, (unsigned)G_ASLAB + 2u * (unsigned)bslab);
           // box = 32 floats x 128 rows; columns >= K and rows >= R arrive as zeros
           g_tma_2d(sa, &tmA, ks * G_SLABK, tile * G_TILE, bar);
-          g_bulk_g2s(sb, p.Bimg + (size_t)ks * bslab, (unsigned)bslab, bar);
-          g_bulk_g2s(sb + bslab, p.Bimg + (size_t)(p.nslab + ks) * bslab, (unsigned)bslab, bar);
+          if (PAIR) {
+            const unsigned half = (unsigned)bslab >> 1, off = (unsigned)crank * half;
+            g_bulk_g2s_mc(sb + off, p.Bimg + (size_t)ks * bslab + off, half, bar, 3);
+            g_bulk_g2s_mc(sb + bslab + off, p.Bimg + (size_t)(p.nslab + ks) * bslab + off, half, bar, 3);
+          } else {
+            g_bulk_g2s(sb, p.Bimg + (size_t)ks * bslab, (unsigned)bslab, bar);
+            g_bulk_g2s(sb + bslab, p.Bimg + (size_t)(p.nslab + ks) * bslab, (unsigned)bslab, bar);
+          }
         }
       }
     }
@@ -177,7 +193,7 @@ gemm_nt_tma_kernel(const __grid_constant__ CUtensorMap tmA, GemmTmaParams p) {
     const int xt = tid - 32 * T_XF0;  // 0..255
     unsigned it = 0;
     long long w_wait = 0, w_work = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int tb = tile0; tb < ntiles; tb += gridDim.x) {
       for (int ks = 0; ks < p.nslab; ++ks, ++it) {
         const int st = it % p.nstages;
         const unsigned ph = (it / p.nstages) & 1u;
@@ -218,7 +234,7 @@ gemm_nt_tma_kernel(const __grid_constant__ CUtensorMap tmA, GemmTmaParams p) {
     const unsigned idesc = g_idesc(128, p.npad);
     unsigned it = 0, tcount = 0;
     long long w_acce = 0, w_full = 0, w_issue = 0, t_begin = clock64();
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+    for (int tb = tile0; tb < ntiles; tb += gridDim.x, ++tcount) {
       const int acc = tcount & 1;
       const unsigned d = tmem + (unsigned)(acc * 256);
       long long ta = clock64();
@@ -243,7 +259,8 @@ gemm_nt_tma_kernel(const __grid_constant__ CUtensorMap tmA, GemmTmaParams p) {
             g_mma(d, ah0 + 2 * k, bl0 + 2 * k, idesc, 1u);
             g_mma(d, al0 + 2 * k, bh0 + 2 * k, idesc, 1u);
           }
-          g_commit(g_smem_u32(&s_empty[st]));  // stage reusable once these MMAs have read it
+          // stage reusable once these MMAs have read it (in a pair: told to both CTAs)
+          if (PAIR) g_commit_mc(g_smem_u32(&s_empty[st]), 3); else g_commit(g_smem_u32(&s_empty[st]));
           if (ks == p.nslab - 1) g_commit(g_smem_u32(&s_accf[acc]));
         }
         __syncwarp();
@@ -266,7 +283,8 @@ gemm_nt_tma_kernel(const __grid_constant__ CUtensorMap tmA, GemmTmaParams p) {
     // optional BatchNorm statistics of the OUTPUT: lane l sums column c0 + l of every 32 x 32 block
     // this warp drains (rows >= R are zero: TMA zero fill) -- up to four blocks (N = 256) per warp
     float cs1[4] = {0.f, 0.f, 0.f, 0.f}, cs2[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+    for (int tb = tile0; tb < ntiles; tb += gridDim.x, ++tcount) {
+      const int tile = tb + crank;
       const int acc = tcount & 1;
       const long long gr = (long long)tile * G_TILE + q * 32 + lane;
       const long long te0 = clock64();
@@ -434,6 +452,7 @@ gemm_nt_tma_kernel(const __grid_constant__ CUtensorMap tmA, GemmTmaParams p) {
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (PAIR) g_cluster_sync();   // no CTA leaves while its peer may still signal its barriers
   if (warp == 0)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u)
                  : "memory");
@@ -762,6 +781,17 @@ inline int gemm_tma_regs() {
   const char *e = getenv("NESIE_GEMM_REGS");
   const int r = e ? atoi(e) : 96;
   return r <= 64 ? 64 : (r <= 88 ? 88 : 96);
+}
+
+// NESIE_GEMM_PAIR=1 launches the wide NT GEMMs as CTA pairs with multicast weight slabs.  Off by default:
+// measured on a B200 it halves the L2 -> shared-memory weight traffic but not the time (65536 x 256 -> 128:
+// 38.4 us against 37.2 us; 262144 x 128 -> 256: 104 against 102; pretrain step 14.80 against 14.73 ms) --
+// the kernel waits on the LATENCY of its two or three 64-96 KB stages, not on L2 bandwidth, and the pair's
+// lockstep adds a little (profiles/r02_ncu_notes.md).
+inline bool gemm_pair_enabled() {
+  static int v = -1;
+  if (v < 0) { const char *e = getenv("NESIE_GEMM_PAIR"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
 }
 
 inline void gemm_apply_env_once() {

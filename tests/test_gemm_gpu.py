@@ -62,3 +62,28 @@ def test_sum_partials_is_deterministic_and_exact_enough(ns, N, K):
     assert torch.equal(got, sum_partials(parts))                       # fixed association
     want = parts.double().sum(0)
     assert ((got.double() - want).abs().max() / want.abs().max()).item() < 2e-6
+
+
+def test_cta_pair_multicast_mode_matches_single_ctas():
+    """NESIE_GEMM_PAIR=1 (clusters of two CTAs sharing the weight slabs by multicast) gives the same
+    bits as the default launch: same MMAs per tile, only the operand delivery differs.  The switch is
+    read once per process, hence the child process."""
+    import os
+    import subprocess
+    import sys
+    code = ("import torch, hashlib\n"
+            "from nesie_b200.linear_rows import gemm_nt\n"
+            "torch.manual_seed(0)\n"
+            "out = []\n"
+            "for R, N, K in ((65536, 128, 256), (70000 - 64, 256, 132)):\n"
+            "    a = torch.randn(R, K, device='cuda'); w = torch.randn(N, K, device='cuda')\n"
+            "    out.append(hashlib.sha256(gemm_nt(a, w).cpu().numpy().tobytes()).hexdigest())\n"
+            "print(' '.join(out))\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = []
+    for flag in ("0", "1"):
+        env = dict(os.environ, NESIE_GEMM_PAIR=flag, PYTHONPATH=root)
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        res.append(r.stdout.strip().splitlines()[-1])
+    assert res[0] == res[1]

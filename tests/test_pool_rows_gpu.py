@@ -13,7 +13,8 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("R,K,N,k", [(4096, 256, 128, 16), (4096 + 64, 128, 256, 32), (2048, 64, 128, 64),
-                                     (1600, 260, 132, 16)])
+                                     (1600, 260, 132, 16), (65536 + 128, 256, 128, 16),   # CTA-pair launch,
+                                     (40000 - 32, 128, 256, 32)])                         # odd tile count
 def test_gemm_pool_epilogue(R, K, N, k):
     """Unit maxima + first maximising row, with and without storing the output; integers so that the
     3xTF32 product is exact and ties are real ties."""
