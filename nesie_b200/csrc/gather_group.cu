@@ -274,6 +274,30 @@ __global__ void __launch_bounds__(256) group_rows_kernel(
   }
 }
 
+// Rows of four floats (c <= 1: the first SA level, coordinates + height): one thread per row and one
+// 16-byte store -- a warp per 16-byte row leaves 29 of its lanes idle over a million rows.
+__global__ void __launch_bounds__(256) group_rows4_kernel(
+    int c, int n, int npoints, int nsample, const float *__restrict__ xyz,
+    const float *__restrict__ center, const float *__restrict__ table,
+    const int *__restrict__ idx, float inv_radius, float4 *__restrict__ out, long long nrows_scene) {
+  const int b = blockIdx.y;
+  idx += (size_t)b * nrows_scene;
+  out += (size_t)b * nrows_scene;
+  for (long long row = (long long)blockIdx.x * 256 + threadIdx.x; row < nrows_scene;
+       row += (long long)gridDim.x * 256) {
+    const int pt = __ldg(idx + row);
+    const float *p = xyz + ((size_t)b * n + pt) * 3;
+    const float *q = center + ((size_t)b * npoints + (int)(row / nsample)) * 3;
+    float4 v;
+    v.x = __fsub_rn(__ldg(p), __ldg(q));
+    v.y = __fsub_rn(__ldg(p + 1), __ldg(q + 1));
+    v.z = __fsub_rn(__ldg(p + 2), __ldg(q + 2));
+    if (inv_radius > 0.f) { v.x = __fmul_rn(v.x, inv_radius); v.y = __fmul_rn(v.y, inv_radius); v.z = __fmul_rn(v.z, inv_radius); }
+    v.w = c ? __ldg(table + (size_t)b * n + pt) : 0.f;
+    out[row] = v;
+  }
+}
+
 // grad_rows (.., 3+c) -> grad_table (b, n, c) [+= by index], grad_xyz (b, n, 3), grad_center (b, m, 3)
 __global__ void __launch_bounds__(256) group_rows_grad_kernel(
     int c, int n, int npoints, int nsample, const float *__restrict__ grad_rows,
@@ -313,6 +337,14 @@ extern "C" int nesie_group_rows(int b, int c, int n, int npoints, int nsample, c
   if (b == 0 || npoints == 0 || nsample == 0) return NESIE_OK;
   NESIE_REQUIRE(b <= 65535, "b > 65535");
   const long long nr = (long long)npoints * nsample;
+  if (ld == 4 && c <= 1 && (reinterpret_cast<uintptr_t>(rows) & 15) == 0) {
+    long long g4 = (nr + 1023) / 1024;   // four rows per thread
+    if (g4 > 8LL * nesie::num_sms()) g4 = 8LL * nesie::num_sms();
+    nesie::group_rows4_kernel<<<dim3((unsigned)(g4 < 1 ? 1 : g4), b), 256, 0, (cudaStream_t)stream>>>(
+        c, n, npoints, nsample, xyz, center_xyz, table_pm, idx, radius > 0.f ? 1.0f / radius : 0.f,
+        reinterpret_cast<float4 *>(rows), nr);
+    return nesie::check_launch("nesie_group_rows");
+  }
   int gx = (int)((nr + 7) / 8);
   if (gx > 8 * nesie::num_sms()) gx = 8 * nesie::num_sms();
   nesie::group_rows_kernel<<<dim3(gx, b), 256, 0, (cudaStream_t)stream>>>(

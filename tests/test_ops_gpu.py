@@ -226,6 +226,18 @@ def test_query_and_group_rows_layout_matches_channel_major(pad_to):
         assert torch.allclose(a.grad, b.grad, rtol=1e-5, atol=1e-5)
 
 
+def test_query_and_group_rows_four_float_rows():
+    """SA1's rows (coordinates + one feature: 16 bytes) take the thread-per-row kernel: same bits."""
+    xyz = scene_xyz(2, 3000, 12)
+    feats = torch.randn(2, 1, 3000)
+    centres = xyz[:, :256].contiguous()
+    grouper = nb.QueryAndGroup(0.2, 64, use_xyz=True, normalize_xyz=True)
+    want = grouper(dev(xyz), dev(centres), dev(feats))           # (B, 4, 256, 64)
+    rows = grouper.forward_rows(dev(xyz), dev(centres), dev(feats), pad_to=4)
+    assert rows.shape == (2 * 256 * 64, 4)
+    assert torch.equal(rows.view(2, 256, 64, 4).permute(0, 3, 1, 2), want)
+
+
 # ---------------------------------------------------------------- three_nn / interpolate
 @pytest.mark.parametrize("B,n,m", [(2, 512, 256), (2, 1024, 512), (1, 7, 2), (1, 5, 1), (1, 3000, 2500),
                                    (8, 20001, 1000)])   # last: the 4-targets-per-thread path
