@@ -140,6 +140,13 @@ int nesie_group_rows_grad(int b, int c, int n, int npoints, int nsample, const f
 int nesie_three_nn(int b, int n, int m, const float *unknown, const float *known, float *dist2,
                    int *idx, void *stream);
 
+/* nesie_three_nn through a uniform grid over the sources (bit-identical results): each target visits
+ * the shells of cells around its own until nothing unvisited can enter its top three.  workspace:
+ * nesie_ball_query_grid_workspace(b, m, 0) bytes, 16-byte aligned; build != 0 bins the sources first,
+ * 0 reuses the grid a previous (stream-ordered) call built over the same sources. */
+int nesie_three_nn_grid(int b, int n, int m, const float *unknown, const float *known, float *dist2,
+                        int *idx, void *workspace, long long workspace_bytes, int build, void *stream);
+
 /* three_interpolate: out[b,c,j] = fma(w2,p2,fma(w0,p0,w1*p1)), p_i = points[b,c,idx[b,j,i]].
  * Replaces three_interpolate_kernel_launcher / three_interpolate_grad_kernel_launcher
  *   ops/interpolate/src/three_interpolate_cuda.cu:37-59,86-110, wrappers interpolate.cpp:58-93.

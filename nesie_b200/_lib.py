@@ -52,6 +52,7 @@ SIGNATURES = {
     "nesie_gemm_nt_3xtf32_fused": [_ll, _i, _i, _p, _ll, _p, _p, _ll, _p, _p, _p, _p],
     "nesie_gemm_nt_3xtf32_bnbwd": [_ll, _i, _i, _p, _ll, _p, _p, _ll, _p, _ll, _p, _p, _p],
     "nesie_gemm_nt_3xtf32_pool": [_ll, _i, _i, _p, _ll, _p, _p, _ll, _p, _p, _p, _i, _p, _p, _p, _p, _p, _i, _p],
+    "nesie_three_nn_grid": [_i, _i, _i, _p, _p, _p, _p, _p, _ll, _i, _p],
     "nesie_gather_linear_parts": [_i, _i, _i],
     "nesie_gather_linear_forward": [_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _i, _f, _p, _p, _p],
     "nesie_gather_linear_backward": [_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _f, _p, _p, _p],

@@ -95,6 +95,13 @@ __global__ void __launch_bounds__(BUILD_THREADS) bq_grid_build(int n, float cell
       if (!(h[a] >= l[a]) || !isfinite(l[a]) || !isfinite(h[a])) { l[a] = 0.f; h[a] = 0.f; }
     }
     float cs = cell_min;
+    if (!(cs > 0.f)) {   // nearest-neighbour use: about two points per cell of the bounding box
+      const float ex = h[0] - l[0], ey = h[1] - l[1], ez = h[2] - l[2];
+      const float emax = fmaxf(ex, fmaxf(ey, ez));
+      cs = 1.25f * cbrtf(fmaxf(ex, emax * 0.05f) * fmaxf(ey, emax * 0.05f) * fmaxf(ez, emax * 0.05f) /
+                         (float)max(n, 1));
+      cs = fmaxf(cs, fmaxf(emax * (1.0f / 200.f), 1e-6f));
+    }
     int nx, ny, nz;
     while (true) {
       nx = min(MAXDIM, (int)((h[0] - l[0]) / cs) + 1);
@@ -162,6 +169,93 @@ __global__ void __launch_bounds__(BUILD_THREADS) bq_grid_build(int n, float cell
     const int pos = atomicAdd(&s_hist[c], 1);
     sorted[pos] = make_float4(x, y, z, __int_as_float(k));
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// three_nn over the same grid (the SidePooling grids ask for 650 k targets x 1024 seeds per step;
+// brute force is 0.7 G distance evaluations).  One thread per target walks the shells of cells around
+// its own cell (x-neighbours are contiguous runs of the sorted points) and keeps the three smallest
+// (d2, index) pairs in lexicographic order -- exactly the brute-force kernel's result, whose strict '<'
+// cascade over ascending indices keeps the earliest index among equal distances.  After shell rho every
+// unvisited point lies beyond one of the block's interior faces, i.e. at least `gap` away along that
+// axis; the walk stops once the third-best d2 is below gap^2 (with a relative margin for the rounding of
+// the cell function and of d2), or when the block covers the grid.  Same d2 expression (sqdist_ref) as
+// three_nn_kernel, so distances and indices are bit-identical.
+constexpr int NNG_THREADS = 128;
+
+__device__ __forceinline__ void nn3_insert(float d, int id, float &b1, float &b2, float &b3, int &i1,
+                                           int &i2, int &i3) {
+  if (d < b3 || (d == b3 && id < i3)) {
+    if (d < b1 || (d == b1 && id < i1)) {
+      b3 = b2; i3 = i2; b2 = b1; i2 = i1; b1 = d; i1 = id;
+    } else if (d < b2 || (d == b2 && id < i2)) {
+      b3 = b2; i3 = i2; b2 = d; i2 = id;
+    } else {
+      b3 = d; i3 = id;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NNG_THREADS) three_nn_grid_kernel(
+    int n, int m, const float *__restrict__ unknown, const unsigned char *__restrict__ ws,
+    float *__restrict__ dist2, int *__restrict__ idx) {
+  const int scene = blockIdx.y;
+  const int pt = blockIdx.x * NNG_THREADS + threadIdx.x;
+  if (pt >= n) return;
+  ws += (size_t)scene * ws_scene_bytes(m);
+  const GridInfo g = *reinterpret_cast<const GridInfo *>(ws);
+  const int *cell_start = reinterpret_cast<const int *>(ws + ws_cells_off());
+  const float4 *sorted = reinterpret_cast<const float4 *>(ws + ws_sorted_off());
+  const float *u = unknown + ((size_t)scene * n + pt) * 3;
+  const float ux = u[0], uy = u[1], uz = u[2];
+  const int cx = cell_coord(ux, g.ox, g.inv_cs, g.nx), cy = cell_coord(uy, g.oy, g.inv_cs, g.ny),
+            cz = cell_coord(uz, g.oz, g.inv_cs, g.nz);
+  const float cs = 1.0f / g.inv_cs;
+  float b1 = CUDART_INF_F, b2 = CUDART_INF_F, b3 = CUDART_INF_F;
+  int i1 = 0, i2 = 0, i3 = 0;
+  for (int rho = 0;; ++rho) {
+    const int z0 = max(cz - rho, 0), z1 = min(cz + rho, g.nz - 1);
+    const int y0 = max(cy - rho, 0), y1 = min(cy + rho, g.ny - 1);
+    const int x0 = max(cx - rho, 0), x1 = min(cx + rho, g.nx - 1);
+    for (int z = z0; z <= z1; ++z) {
+      for (int y = y0; y <= y1; ++y) {
+        const int rowc = (z * g.ny + y) * g.nx;
+        const bool shell = (z - cz == rho) || (cz - z == rho) || (y - cy == rho) || (cy - y == rho);
+        // shell rows: the whole x range; interior rows: only the two end cells (when they exist)
+        for (int part = 0; part < 2; ++part) {
+          int xa, xb;
+          if (shell) {
+            if (part) break;
+            xa = x0; xb = x1;
+          } else {
+            if (rho == 0) break;
+            xa = xb = part ? cx + rho : cx - rho;
+            if (xa < 0 || xa >= g.nx) continue;
+          }
+          const int beg = __ldg(cell_start + rowc + xa), end = __ldg(cell_start + rowc + xb + 1);
+          for (int k = beg; k < end; ++k) {
+            const float4 sp = __ldg(sorted + k);
+            nn3_insert(sqdist_ref(ux, uy, uz, sp.x, sp.y, sp.z), __float_as_int(sp.w), b1, b2, b3, i1, i2, i3);
+          }
+        }
+      }
+    }
+    // distance to the nearest interior face of the visited block
+    float gap = CUDART_INF_F;
+    if (cx - rho > 0) gap = fminf(gap, ux - (g.ox + (float)(cx - rho) * cs));
+    if (cx + rho < g.nx - 1) gap = fminf(gap, (g.ox + (float)(cx + rho + 1) * cs) - ux);
+    if (cy - rho > 0) gap = fminf(gap, uy - (g.oy + (float)(cy - rho) * cs));
+    if (cy + rho < g.ny - 1) gap = fminf(gap, (g.oy + (float)(cy + rho + 1) * cs) - uy);
+    if (cz - rho > 0) gap = fminf(gap, uz - (g.oz + (float)(cz - rho) * cs));
+    if (cz + rho < g.nz - 1) gap = fminf(gap, (g.oz + (float)(cz + rho + 1) * cs) - uz);
+    if (gap == CUDART_INF_F) break;                       // the block covers the whole grid
+    gap -= 1e-4f * cs;                                    // rounding of the cell function
+    if (gap > 0.f && b3 < gap * gap * 0.9999f) break;     // nothing unvisited can enter the top three
+  }
+  float *od = dist2 + ((size_t)scene * n + pt) * 3;
+  int *oi = idx + ((size_t)scene * n + pt) * 3;
+  od[0] = b1; od[1] = b2; od[2] = b3;
+  oi[0] = i1; oi[1] = i2; oi[2] = i3;
 }
 
 __global__ void __launch_bounds__(Q_THREADS) bq_grid_query(
@@ -295,4 +389,34 @@ extern "C" int nesie_ball_query_grid(int b, int n, int m, float min_radius, floa
                                                reinterpret_cast<const unsigned char *>(workspace),
                                                idx);
   return check_launch("nesie_ball_query_grid(query)");
+}
+
+// three_nn through the grid: `workspace` as for nesie_ball_query_grid with n := m (the SOURCE count;
+// nesie_ball_query_grid_workspace(b, m, 0) bytes).  build != 0 bins the sources first; pass 0 to reuse
+// the grid of a previous call over the same sources (stream-ordered).  Results are bit-identical to
+// nesie_three_nn.
+extern "C" int nesie_three_nn_grid(int b, int n, int m, const float *unknown, const float *known,
+                                   float *dist2, int *idx, void *workspace, long long workspace_bytes,
+                                   int build, void *stream) {
+  NESIE_REQUIRE(b >= 0 && n >= 0 && m >= 1, "need b >= 0, n >= 0, m >= 1");
+  if (b == 0 || n == 0) return NESIE_OK;
+  NESIE_REQUIRE(unknown && known && dist2 && idx, "null pointer");
+  NESIE_REQUIRE(b <= 65535, "b > 65535");
+  NESIE_REQUIRE(workspace && workspace_bytes >= nesie_ball_query_grid_workspace(b, m, 0),
+                "workspace too small (see nesie_ball_query_grid_workspace)");
+  NESIE_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "workspace must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (build) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      NESIE_CUDA(cudaFuncSetAttribute(bq_grid_build, cudaFuncAttributeMaxDynamicSharedMemorySize, NCMAX * 4));
+      attr_set = true;
+    }
+    bq_grid_build<<<b, BUILD_THREADS, NCMAX * 4, st>>>(m, 0.f, known, reinterpret_cast<unsigned char *>(workspace));
+    const int rc = check_launch("nesie_three_nn_grid(build)");
+    if (rc) return rc;
+  }
+  three_nn_grid_kernel<<<dim3(ceil_div(n, NNG_THREADS), b), NNG_THREADS, 0, st>>>(
+      n, m, unknown, reinterpret_cast<const unsigned char *>(workspace), dist2, idx);
+  return check_launch("nesie_three_nn_grid");
 }

@@ -34,6 +34,28 @@ class ThreeNN(Function):
 three_nn = ThreeNN.apply
 
 
+def three_nn_grid(target, source, workspace=None):
+    """three_nn through a uniform grid over the sources (nesie_three_nn_grid): bit-identical distances
+    and indices, ~10x fewer distance evaluations when there are hundreds of sources or more.
+    -> (sqrt(d^2) (B, N, 3), idx int32 (B, N, 3), workspace); pass the returned workspace back in to
+    search further target sets against the SAME sources without binning them again."""
+    assert target.is_contiguous() and source.is_contiguous()
+    _lib.need_cuda(target, source)
+    B, N, _ = target.size()
+    m = source.size(1)
+    dev = target.device
+    dist2 = torch.empty((B, N, 3), dtype=torch.float32, device=dev)
+    idx = torch.empty((B, N, 3), dtype=torch.int32, device=dev)
+    build = workspace is None
+    if build:
+        workspace = torch.empty((_lib.lib().nesie_ball_query_grid_workspace(B, m, 0),), dtype=torch.uint8,
+                                device=dev)
+    with torch.cuda.device(dev):
+        _lib.call("nesie_three_nn_grid", B, N, m, _lib.ptr(target), _lib.ptr(source), _lib.ptr(dist2),
+                  _lib.ptr(idx), _lib.ptr(workspace), workspace.numel(), int(build), _lib.stream())
+    return torch.sqrt(dist2), idx, workspace
+
+
 class ThreeInterpolate(Function):
     """out[b,c,j] = sum_i weight[b,j,i] * features[b,c,indices[b,j,i]]; differentiable w.r.t.
     features only (three_interpolate.py:11-60)."""

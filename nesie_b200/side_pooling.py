@@ -31,7 +31,7 @@ from . import gather_linear
 from . import group_max
 from . import mlp_rows
 from . import pool_rows
-from .interpolate import three_nn
+from .interpolate import three_nn, three_nn_grid
 from .linear_rows import linear_rows
 
 
@@ -220,7 +220,7 @@ class SidePooling(nn.Module):
         return stat.permute(1, 0, 2, 3).repeat(1, 1, 1, 2)
 
     # ---- hot path hooks ----------------------------------------------------------------------
-    def _grid_rows(self, origin_xyz, origin_features, grid, center, sides=1):
+    def _grid_rows(self, origin_xyz, origin_features, grid, center, sides=1, nn_cache=None):
         """grid (B, T, 3) world points, T = K * sides * G ordered (box, side, grid point) -> per side the
         rows (B*K*G, ld) = [grid - centre | features interpolated from the 3 nearest seeds with
         normalised inverse-distance weights | 0 pad] as a _GridSource (factored: seed table + 3
@@ -233,7 +233,18 @@ class SidePooling(nn.Module):
         G = T // (K * sides)
         C = origin_features.shape[1]
         with torch.no_grad():
-            dist, idx = three_nn(grid, origin_xyz)
+            if origin_xyz.shape[1] >= 64 and os.environ.get("NESIE_THREE_NN_GRID", "0") == "1":
+                # exact 3-NN through a grid over the seeds, binned once per forward (nn_cache).  Off by
+                # default: measured (tools/nn_probe.py, 8 x 81920 grid points, 1024 seeds) 304 us against
+                # 443 us brute force when every grid point lies within ~0.2 m of a seed, 473 us at ~0.6 m
+                # and 1.7 ms at ~2 m (the shells a thread walks diverge and grow); the boxes of an
+                # untrained or early-training head put most grid points in the last regime.
+                ws = nn_cache.get("ws") if nn_cache is not None else None
+                dist, idx, ws = three_nn_grid(grid, origin_xyz, ws)
+                if nn_cache is not None:
+                    nn_cache["ws"] = ws
+            else:
+                dist, idx = three_nn(grid, origin_xyz)
             weight = 1.0 / (dist + 1e-8)
             weight = weight / weight.sum(dim=2, keepdim=True)
             head = grid.view(B, K, sides * G, 3) - center.unsqueeze(2)
@@ -245,9 +256,9 @@ class SidePooling(nn.Module):
                 out.append(_GridSource(origin_xyz.shape[1], table, pick(idx), pick(weight), pick(head), ld))
         return out[0] if sides == 1 else out
 
-    def _side_rows(self, origin_xyz, origin_features, side_grid, center):
+    def _side_rows(self, origin_xyz, origin_features, side_grid, center, nn_cache=None):
         """Rows of the six face grids, one contiguous block per side."""
-        return self._grid_rows(origin_xyz, origin_features, side_grid, center, sides=6)
+        return self._grid_rows(origin_xyz, origin_features, side_grid, center, sides=6, nn_cache=nn_cache)
 
     def _mini_pointnet(self, mpn, rows, G):
         """rows (R, ld) -- a tensor or a _GridSource -- with every G consecutive rows one box ->
@@ -349,8 +360,9 @@ class SidePooling(nn.Module):
         whole_grid = self.generate_grid(size)
         side_grid = self.grid_for_side(whole_grid, center, heading).reshape(B, -1, 3).contiguous()
         bbox_grid = self.grid_for_bbox(whole_grid, center, heading).reshape(B, -1, 3).contiguous()
-        side_rows = self._side_rows(origin_xyz, origin_features, side_grid, center)
-        bbox_rows = self._grid_rows(origin_xyz, origin_features, bbox_grid, center)
+        nn_cache = {}      # the seeds are binned once for both grids
+        side_rows = self._side_rows(origin_xyz, origin_features, side_grid, center, nn_cache=nn_cache)
+        bbox_rows = self._grid_rows(origin_xyz, origin_features, bbox_grid, center, nn_cache=nn_cache)
         dist_feature = self.dist_feature(end_points, prefix)
 
         def branch(i):

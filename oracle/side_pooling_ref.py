@@ -18,7 +18,7 @@ from oracle import cpu
 
 class SidePoolingOracle(SidePooling):
 
-    def _grid_rows(self, origin_xyz, origin_features, grid, center):
+    def _grid_rows(self, origin_xyz, origin_features, grid, center, nn_cache=None):
         B, T = grid.shape[:2]
         K = center.shape[1]
         C = origin_features.shape[1]
@@ -35,7 +35,7 @@ class SidePoolingOracle(SidePooling):
         head = grid.view(B, K, T // K, 3) - center.unsqueeze(2)
         return torch.cat([head.reshape(B * T, 3), feats.reshape(B * T, C)], dim=1)
 
-    def _side_rows(self, origin_xyz, origin_features, side_grid, center):
+    def _side_rows(self, origin_xyz, origin_features, side_grid, center, nn_cache=None):
         rows = self._grid_rows(origin_xyz, origin_features, side_grid, center)
         B, K = center.shape[:2]
         rows = rows.view(B * K, 6, -1, rows.shape[-1])

@@ -357,3 +357,39 @@ def test_ball_query_grid_duplicates_overflow_and_full_size(monkeypatch):
     assert torch.equal(grid, brute)
     if ref_cuda.available():
         assert torch.equal(grid, ref_cuda.ball_query(0.0, 0.2, 64, xyz, centres))
+
+
+@pytest.mark.parametrize("case", ["room", "uniform", "clustered", "flat", "duplicates", "few", "outside"])
+def test_three_nn_grid_is_bit_identical_to_brute_force(case):
+    """Exact 3-NN through the uniform grid: same distances and indices as nesie_three_nn, including the
+    earliest-index tie rule, targets outside the sources' bounding box and degenerate source sets."""
+    from nesie_b200.interpolate import three_nn_grid
+    g = torch.Generator().manual_seed(hash(case) % 1000)
+    B, n, m = 3, 5000, 1024
+    if case == "room":
+        src, tgt = scene_xyz(B, m, 40), scene_xyz(B, n, 41)
+    elif case == "uniform":
+        src, tgt = torch.rand(B, m, 3, generator=g) * 6, torch.rand(B, n, 3, generator=g) * 6
+    elif case == "clustered":
+        src = torch.randn(B, m, 3, generator=g) * 0.05 + torch.randint(0, 3, (B, m, 3), generator=g).float() * 2
+        tgt = torch.rand(B, n, 3, generator=g) * 5
+    elif case == "flat":
+        src = torch.rand(B, m, 3, generator=g) * 4
+        src[..., 2] = 1.0
+        tgt = torch.rand(B, n, 3, generator=g) * 4
+    elif case == "duplicates":
+        src = torch.rand(B, 8, 3, generator=g).repeat(1, m // 8, 1)        # every source 128 times
+        tgt = torch.rand(B, n, 3, generator=g)
+    elif case == "few":
+        m = 2
+        src, tgt = torch.rand(B, m, 3, generator=g), torch.rand(B, n, 3, generator=g)
+    else:
+        src = torch.rand(B, m, 3, generator=g)
+        tgt = torch.rand(B, n, 3, generator=g) * 20 - 10
+    src, tgt = dev(src.contiguous()), dev(tgt.contiguous())
+    d0, i0 = nb.three_nn(tgt, src)
+    d1, i1, ws = three_nn_grid(tgt, src)
+    assert torch.equal(d0, d1)
+    assert torch.equal(i0, i1)
+    d2, i2, _ = three_nn_grid(tgt[:, :777].contiguous(), src, ws)          # reuse the binned sources
+    assert torch.equal(d2, d0[:, :777]) and torch.equal(i2, i0[:, :777])
