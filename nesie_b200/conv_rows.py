@@ -5,6 +5,7 @@ from torch.nn import functional as F
 
 from . import bn_rows
 from . import mlp_rows
+from .pool_rows import add_bias_rows
 from .pointnet_modules import ConvModule, _fused_bn, _rows_linear
 
 
@@ -27,7 +28,7 @@ def conv1d_rows(seq, x):
         conv = m.conv if isinstance(m, ConvModule) else m
         r = _rows_linear(r, conv.weight.flatten(1))
         if conv.bias is not None:
-            r = r + conv.bias
+            r = add_bias_rows(r, conv.bias)
         if isinstance(m, ConvModule):
             bn = m.bn
             if _fused_bn() and bn_rows.supported(r, bn):

@@ -771,10 +771,11 @@ static int gemm_nt_impl(long long r, int n, int k, const float *a, long long lda
       if (q.nstages > G_MAXSTAGES) q.nstages = G_MAXSTAGES;
       const size_t smem = (size_t)q.nstages * stage + epi + T_CTRL_BYTES;
       const int regs = gemm_tma_regs();
-      int grid = gemm_grid_sms();
+      int grid = gemm_balanced_grid(ntiles_all);
       // CTA pairs sharing the weight slabs (multicast): where the weight stream outweighs the
       // activations (wide N x K) and there are at least two tiles per CTA
-      if (regs == 96 && gemm_pair_enabled() && p.npad * p.nslab >= 128 * 4 && ntiles_all >= 2 * grid) {
+      if (regs == 96 && gemm_pair_enabled() && p.npad * p.nslab >= 128 * 4 && ntiles_all >= 2 * grid &&
+          (grid & 1) == 0) {   // (the statistics partials are sized for `grid` CTAs)
         auto kp = gemm_nt_tma_kernel<96, true>;
         NESIE_CUDA(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, G_MAX_DYN_SMEM));
         cudaLaunchConfig_t cfg = {};
@@ -793,15 +794,15 @@ static int gemm_nt_impl(long long r, int n, int k, const float *a, long long lda
           max_pairs = nc;
         }
         if (max_pairs >= 8) {
-          if ((int)cfg.gridDim.x > 2 * max_pairs) cfg.gridDim.x = 2u * (unsigned)max_pairs;
+          if ((int)cfg.gridDim.x <= 2 * max_pairs) {
           NESIE_CUDA(cudaLaunchKernelEx(&cfg, kp, tm, q));
           return check_launch("nesie_gemm_nt_3xtf32 (pairs)");
+          }
         }
       }
       auto kern = regs == 64 ? gemm_nt_tma_kernel<64, false>
                              : (regs == 88 ? gemm_nt_tma_kernel<88, false> : gemm_nt_tma_kernel<96, false>);
       NESIE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G_MAX_DYN_SMEM));
-      if (ntiles_all < grid) grid = ntiles_all;
       kern<<<grid, T_THREADS, smem, (cudaStream_t)stream>>>(tm, q);
       return check_launch("nesie_gemm_nt_3xtf32");
     }
@@ -838,7 +839,7 @@ extern "C" int nesie_gemm_fused_supported(long long r, int n, int k, const float
 extern "C" int nesie_gemm_stats_parts(long long r) {
   if (r <= 0) return 0;
   const long long ntiles = (r + G_TILE - 1) / G_TILE;
-  return 4 * (int)(ntiles < gemm_grid_sms() ? ntiles : gemm_grid_sms());
+  return 4 * gemm_balanced_grid(ntiles);
 }
 
 extern "C" int nesie_gemm_nt_3xtf32_fused(long long r, int n, int k, const float *a, long long lda,

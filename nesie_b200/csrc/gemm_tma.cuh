@@ -776,6 +776,20 @@ inline int gemm_grid_sms() {
   return g;
 }
 
+// CTAs of a persistent launch over `ntiles` equal tiles: the smallest grid that still finishes in the same
+// number of waves (512 tiles on 148 SMs are 4 waves with 148 CTAs and with 128): the launch is no slower
+// and the SMs it leaves alone run the small kernels of the other branches of the step.
+// NESIE_GEMM_BALANCE=0 always takes every SM.
+inline int gemm_balanced_grid(long long ntiles) {
+  static int on = -1;
+  if (on < 0) { const char *e = getenv("NESIE_GEMM_BALANCE"); on = (e && e[0] == '0') ? 0 : 1; }
+  const int sms = gemm_grid_sms();
+  if (ntiles <= sms) return (int)ntiles;
+  if (!on) return sms;
+  const long long waves = (ntiles + sms - 1) / sms;
+  return (int)((ntiles + waves - 1) / waves);
+}
+
 // register cap of the build to launch: 64, 88 or 96 (NESIE_GEMM_REGS; default 96)
 inline int gemm_tma_regs() {
   const char *e = getenv("NESIE_GEMM_REGS");

@@ -48,10 +48,18 @@ def wgrad(gy, x):
     _lib.need_cuda(gy, x)
     R, N = gy.shape
     K = x.shape[1]
-    ns = _lib.lib().nesie_gemm_wgrad_splits(R, N, K)
-    parts = torch.empty((ns, N, K), dtype=torch.float32, device=gy.device)
+    if N > 256:     # the kernel takes at most 256 rows of the result: column blocks of gy (row stride N)
+        return torch.cat([_wgrad_block(gy, x, n0, min(256, N - n0)) for n0 in range(0, N, 256)], dim=0)
+    return _wgrad_block(gy, x, 0, N)
+
+
+def _wgrad_block(gy, x, n0, nb):
+    R, N = gy.shape
+    K = x.shape[1]
+    ns = _lib.lib().nesie_gemm_wgrad_splits(R, nb, K)
+    parts = torch.empty((ns, nb, K), dtype=torch.float32, device=gy.device)
     with torch.cuda.device(gy.device):
-        _lib.call("nesie_gemm_wgrad_3xtf32", R, N, K, _lib.ptr(gy), N, _lib.ptr(x), K,
+        _lib.call("nesie_gemm_wgrad_3xtf32", R, nb, K, _lib.ptr(gy) + 4 * n0, N, _lib.ptr(x), K,
                   _lib.ptr(parts), ns, _lib.stream())
     return sum_partials(parts)
 
@@ -91,7 +99,7 @@ class _LinearRows(Function):
             else:
                 gx = gy @ w
         if ctx.needs_input_grad[1]:
-            if gy.shape[1] <= 256 and x.shape[1] <= 512 and gy.shape[0] >= 1:
+            if x.shape[1] <= 512 and gy.shape[0] >= 1:
                 gw = wgrad(gy, x.contiguous())
             else:
                 gw = gy.t() @ x

@@ -106,6 +106,23 @@ def _colsum(x):
     return out
 
 
+class _AddBiasRows(Function):
+    """x (R, n) + bias (n); the bias gradient is the one-launch column sum (ATen's reduction of a
+    4096 x 128 matrix over dim 0 takes 13 us, x 21 Conv1d biases per SidePooling forward)."""
+
+    @staticmethod
+    def forward(ctx, x, bias):
+        return x + bias
+
+    @staticmethod
+    def backward(ctx, gy):
+        return gy, (_colsum(gy.contiguous()) if ctx.needs_input_grad[1] else None)
+
+
+def add_bias_rows(x, bias):
+    return _AddBiasRows.apply(x, bias) if x.is_cuda else x + bias
+
+
 def _bn_relu_backward(y_prev, g_act, stats):
     """Gradient of relu(bn(y_prev)) w.r.t. y_prev / gamma / beta given g_act = dL/d(relu(bn(y_prev)))."""
     R, C = y_prev.shape

@@ -330,7 +330,7 @@ class SidePooling(nn.Module):
                     w = F.pad(w, (0, rp.shape[1] - w.shape[1]))
                 r = linear_rows(rp.contiguous(), w)
                 if m.bias is not None:
-                    r = r + m.bias
+                    r = pool_rows.add_bias_rows(r, m.bias)
                 i += 1
             elif isinstance(m, nn.BatchNorm1d):
                 relu = i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU)

@@ -87,3 +87,15 @@ def test_cta_pair_multicast_mode_matches_single_ctas():
         assert r.returncode == 0, r.stderr[-2000:]
         res.append(r.stdout.strip().splitlines()[-1])
     assert res[0] == res[1]
+
+
+def test_wgrad_wider_than_one_accumulator():
+    """gy with more than 256 columns (VoteModule's 259-channel output conv): column blocks, no library GEMM."""
+    from nesie_b200.linear_rows import wgrad
+    torch.manual_seed(4)
+    gy = torch.randn(8192, 259, device="cuda")
+    x = torch.randn(8192, 256, device="cuda")
+    want = gy.double().t() @ x.double()
+    got = wgrad(gy, x)
+    assert got.shape == (259, 256)
+    assert ((got.double() - want).abs().max() / want.abs().max()).item() < 6e-6
