@@ -456,7 +456,7 @@ class NesieHead(nn.Module):
 
     # ---- supervised loss ------------------------------------------------------------------------
     def _loss_streams(self):
-        return int(os.environ.get("NESIE_LOSS_STREAMS", "4"))
+        return int(os.environ.get("NESIE_LOSS_STREAMS", "5"))
 
     def loss_padded(self, bbox_preds, points, boxes, labels, valid, ret_target=False):
         """All eight loss terms.  After the (sequential) target assignment the terms are independent

@@ -387,5 +387,5 @@ class SidePooling(nn.Module):
         """The seven MiniPointNet + head chains are independent: on CUDA they run as forked branches
         (branches.py), so the dozens of small kernels of one chain overlap the large GEMMs of another."""
         from .branches import run_branches
-        width = int(os.environ.get("NESIE_SIDEPOOL_STREAMS", "3"))
+        width = int(os.environ.get("NESIE_SIDEPOOL_STREAMS", "7"))
         return run_branches([lambda i=i: branch(i) for i in range(n)], like, shared, width)
