@@ -136,6 +136,18 @@ def _bn_stats(y, parts, gamma, beta, rm, rv, eps, momentum):
     return stats
 
 
+def _fork2(f_w, f_d, like, shared):
+    """Weight gradient beside the data-gradient chain of a layer's backward: the weight gradient only
+    feeds the optimizer, the data gradient is what the rest of the backward waits for, and the two use
+    different parts of an SM (tensor pipe + shared memory against HBM streaming in the BatchNorm kernels).
+    NESIE_WGRAD_FORK=1 issues them as two forked branches (branches.py)."""
+    if os.environ.get("NESIE_WGRAD_FORK", "0") != "1" or f_w is None or f_d is None:
+        return (f_w() if f_w else None), (f_d() if f_d else None)
+    from .branches import run_branches
+    out = run_branches([f_w, f_d], like, shared, 2)
+    return out[0], out[1]
+
+
 class _LinearStats(Function):
     """First layer: y = x @ w.T plus the column sums of y."""
 
@@ -178,21 +190,27 @@ class _BNReLULinear(Function):
         gy = gy.contiguous()
         R, C = y_prev.shape
         dev = y_prev.device
-        gw = _wgrad_fused(gy, y_prev, stats[2], stats[3]) if ctx.needs_input_grad[8] else None
         if (bnbwd_fused_enabled() and C <= 256 and C % 4 == 0 and gy.shape[1] % 4 == 0 and
                 _gemm_supported(gy, C, gy.shape[1])):
+            gw = _wgrad_fused(gy, y_prev, stats[2], stats[3]) if ctx.needs_input_grad[8] else None
             d_y, d_gamma, d_beta = _dgrad_bn_backward(gy, w.contiguous(), y_prev, stats)
             return d_y, None, d_gamma, d_beta, None, None, None, None, gw
-        g_act = gemm_nt(gy, w, transpose_w=True)          # gradient w.r.t. relu(bn(y_prev))
-        d_y = torch.empty_like(y_prev)
-        d_gamma = torch.empty((C,), dtype=torch.float32, device=dev)
-        d_beta = torch.empty((C,), dtype=torch.float32, device=dev)
-        ws = torch.empty((_lib.lib().nesie_bn_rows_workspace_bytes(C),), dtype=torch.uint8, device=dev)
-        with torch.cuda.device(dev):
-            _lib.call("nesie_bn_relu_rows_backward", R, C, 0, _lib.ptr(y_prev), _lib.ptr(g_act), None,
-                      _lib.ptr(stats), _lib.ptr(d_y), _lib.ptr(d_gamma), _lib.ptr(d_beta),
-                      _lib.ptr(ws), _lib.stream())
-            _lib.LAUNCHES += 2
+
+        def data_grad():
+            g_act = gemm_nt(gy, w, transpose_w=True)          # gradient w.r.t. relu(bn(y_prev))
+            d_y = torch.empty_like(y_prev)
+            d_gamma = torch.empty((C,), dtype=torch.float32, device=dev)
+            d_beta = torch.empty((C,), dtype=torch.float32, device=dev)
+            ws = torch.empty((_lib.lib().nesie_bn_rows_workspace_bytes(C),), dtype=torch.uint8, device=dev)
+            with torch.cuda.device(dev):
+                _lib.call("nesie_bn_relu_rows_backward", R, C, 0, _lib.ptr(y_prev), _lib.ptr(g_act), None,
+                          _lib.ptr(stats), _lib.ptr(d_y), _lib.ptr(d_gamma), _lib.ptr(d_beta),
+                          _lib.ptr(ws), _lib.stream())
+                _lib.LAUNCHES += 2
+            return d_y, d_gamma, d_beta
+
+        f_w = (lambda: _wgrad_fused(gy, y_prev, stats[2], stats[3])) if ctx.needs_input_grad[8] else None
+        gw, (d_y, d_gamma, d_beta) = _fork2(f_w, data_grad, gy, [gy, y_prev, stats, w])
         return d_y, None, d_gamma, d_beta, None, None, None, None, gw
 
 

@@ -173,9 +173,11 @@ class _BNReLULinearMax(Function):
             if gy is None:
                 return none
             gy = gy.contiguous()
-            gw = mlp_rows._wgrad_fused(gy, y_prev, stats[2], stats[3]) if ctx.needs_input_grad[8] else None
-            g_act = gemm_nt(gy, w, transpose_w=True)
-            d_bias = None
+            f_w = (lambda: mlp_rows._wgrad_fused(gy, y_prev, stats[2], stats[3])) if ctx.needs_input_grad[8] else None
+            gw, (d_y, d_gamma, d_beta) = mlp_rows._fork2(
+                f_w, lambda: _bn_relu_backward(y_prev, gemm_nt(gy, w, transpose_w=True), stats), gy,
+                [gy, y_prev, stats, w])
+            return d_y, None, d_gamma, d_beta, None, None, None, None, gw, None, None, None
         else:
             y_prev, stats, w, arg = ctx.saved_tensors
             d_out = grads[0]
@@ -245,11 +247,17 @@ class _ConcatGlobalLinear(Function):
         dev = y.device
         w_g, w_f = w[:, :C].contiguous(), w[:, C:].contiguous()
         d_e = _group_sum(g_out, ctx.k)
-        d_y = gemm_nt(g_out, w_f, transpose_w=True)               # (R, C)
-        d_g = gemm_nt(d_e, w_g, transpose_w=True)                 # (G, C) gradient of the group maximum
-        with torch.cuda.device(dev):
-            _lib.call("nesie_scatter_rows_add", G, ctx.k, C, _lib.ptr(d_g), _lib.ptr(arg), _lib.ptr(d_y),
-                      _lib.stream())
+
+        def data_grad():
+            d_y = gemm_nt(g_out, w_f, transpose_w=True)           # (R, C)
+            d_g = gemm_nt(d_e, w_g, transpose_w=True)             # (G, C) gradient of the group maximum
+            with torch.cuda.device(dev):
+                _lib.call("nesie_scatter_rows_add", G, ctx.k, C, _lib.ptr(d_g), _lib.ptr(arg), _lib.ptr(d_y),
+                          _lib.stream())
+            return d_y, d_g
+
+        f_w = (lambda: (wgrad(d_e, gmax), wgrad(g_out, y))) if ctx.needs_input_grad[4] else None
+        wg, (d_y, d_g) = mlp_rows._fork2(f_w, data_grad, g_out, [g_out, d_e, y, gmax, arg, w_g, w_f])
         # rows are y + bias: the bias reaches d_w_f and d_bias only through the column sums of g_out
         # (d_bias = colsum(g_out) @ (W_f + W_g)), which are exactly zero when g_out comes out of a
         # training-mode BatchNorm's backward -- a constant added in front of a BatchNorm has no
@@ -258,13 +266,13 @@ class _ConcatGlobalLinear(Function):
         d_w = d_bias = None
         if ctx.zero_mean_grad:
             if ctx.needs_input_grad[4]:
-                d_w = torch.cat([wgrad(d_e, gmax), wgrad(g_out, y)], dim=1)
+                d_w = torch.cat([wg[0], wg[1]], dim=1)
             if ctx.needs_input_grad[3]:
                 d_bias = torch.zeros_like(bias)
         else:
             colsum = _colsum(d_e)
             if ctx.needs_input_grad[4]:
-                d_w = torch.cat([wgrad(d_e, gmax), wgrad(g_out, y) + torch.outer(colsum, bias)], dim=1)
+                d_w = torch.cat([wg[0], wg[1] + torch.outer(colsum, bias)], dim=1)
             if ctx.needs_input_grad[3]:
                 d_bias = _colsum(d_g) + torch.mv(w_f.t(), colsum)     # sum over rows of d(y + bias)
         return d_y, None, None, d_bias, d_w, None, None
