@@ -380,6 +380,14 @@ int nesie_gemm_nt_3xtf32_pool(long long r, int n, int k, const float *a, long lo
 int nesie_pool_finalize(long long groups, int k, int u, int n, const float *pmax,
                         const unsigned char *amax, const float *bias, float *out, unsigned char *arg,
                         void *stream);
+/* BatchNorm + ReLU + max-pool of an SA level's last layer (point_sa_module.py:136-158,279-288) from the
+ * unit maxima AND minima of nesie_gemm_nt_3xtf32_pool: out[g, c] = relu(scale[c] * (max or min over the
+ * group, by the sign of scale) + shift[c]), stats = mean | invstd | scale | shift (4 x n) as
+ * nesie_bn_rows_forward_fused leaves them; arg = first row of the group attaining it, 255 when the pooled
+ * value is not positive (what nesie_bn_relu_rows_backward expects). */
+int nesie_bn_pool_finalize(long long groups, int k, int u, int n, const float *pmax,
+                           const unsigned char *amax, const float *pmin, const unsigned char *amin,
+                           const float *stats, float *out, unsigned char *arg, void *stream);
 /* Weight gradient of a max-pooled convolution out[g, c] = max_j (a[g k + j, :] . w[c, :]):
  * d_w[c, :] = sum_g d_out[g, c] * a[g k + arg[g, c], :] with a = relu(y_prev * scale + shift) (or y_prev
  * itself when scale / shift are NULL), y_prev (groups * k, k_in) row-major, k_in % 4 == 0, k_in <= 256.

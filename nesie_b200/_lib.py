@@ -57,6 +57,7 @@ SIGNATURES = {
     "nesie_gather_linear_forward": [_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _i, _f, _p, _p, _p],
     "nesie_gather_linear_backward": [_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _f, _p, _p, _p],
     "nesie_pool_finalize": [_ll, _i, _i, _i, _p, _p, _p, _p, _p, _p],
+    "nesie_bn_pool_finalize": [_ll, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p],
     "nesie_pool_wgrad_parts": [_ll],
     "nesie_pool_wgrad": [_ll, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p],
     "nesie_pool_dgrad": [_ll, _i, _i, _i, _p, _p, _p, _p, _p],

@@ -295,15 +295,15 @@ gemm_nt_tma_kernel(const __grid_constant__ CUtensorMap tmA, GemmTmaParams p) {
       for (int blk = 0; blk < 4; ++blk) {
         const int c0 = half * 32 + blk * 32 * (T_EPIW / 4);
         if (c0 >= p.npad) break;
-        unsigned v[32];
-        g_tmem_ld32(tmem + (unsigned)(acc * 256 + c0) + ((unsigned)(q * 32) << 16), v);
         // rows >= R exist only in the last tile; with an operand prologue they are not zero
         const long long row0 = (long long)tile * G_TILE + q * 32;
         const long long left = (long long)p.R - row0;
         const int nvalid = left >= 32 ? 32 : (left > 0 ? (int)left : 0);
-        // group constants (grp_shift >= 4: rows 0-15 and 16-31 of the block lie in one group each),
-        // requested while the accumulator load is in flight: e0 / e1 for this lane's column in the
-        // statistics loop, el / eh for its 16-byte chunk in the store loop
+        // group constants (grp_shift >= 4: rows 0-15 and 16-31 of the block lie in one group each): e0 / e1
+        // for this lane's column in the statistics loop, el / eh for its 16-byte chunk in the store loop.
+        // Requested BEFORE the accumulator load is issued: nothing may sit between tcgen05.ld and its
+        // wait -- the compiler is free to move the asm statement's destination registers, which are not
+        // valid until the wait (an earlier version did, and a few outputs per thousand runs were stale).
         float e0 = 0.f, e1 = 0.f;
         float4 el = make_float4(0.f, 0.f, 0.f, 0.f), eh = el;
         if (p.grp_bias) {
@@ -318,6 +318,8 @@ gemm_nt_tma_kernel(const __grid_constant__ CUtensorMap tmA, GemmTmaParams p) {
             if (nvalid > 16) eh = __ldg(reinterpret_cast<const float4 *>(g1 + c0 + qc * 4));
           }
         }
+        unsigned v[32];
+        g_tmem_ld32(tmem + (unsigned)(acc * 256 + c0) + ((unsigned)(q * 32) << 16), v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (vec) {
 #pragma unroll

@@ -51,6 +51,46 @@ __global__ void __launch_bounds__(PR_THREADS) pool_finalize_kernel(
   }
 }
 
+// BatchNorm + ReLU + max-pool of an SA level's last layer from the unit extrema of the GEMM epilogue:
+// relu(y * scale + shift) is monotone in y, increasing for scale >= 0 and decreasing otherwise, so the
+// pooled value is relu(scale * (max or min over the group) + shift) and the pre-activation is not read
+// again.  arg = first row of the group that attains it (255 when the maximum is not positive: the ReLU
+// passes no gradient), as bn_relu_pool_kernel reports it.
+__global__ void __launch_bounds__(PR_THREADS) bn_pool_finalize_kernel(
+    long long groups, int m, int u, int n, const float *__restrict__ pmax,
+    const unsigned char *__restrict__ amax, const float *__restrict__ pmin,
+    const unsigned char *__restrict__ amin, const float *__restrict__ stats, float *__restrict__ out,
+    unsigned char *__restrict__ arg) {
+  const float *scale = stats + 2 * n, *shift = stats + 3 * n;
+  const long long total = groups * n;
+  for (long long i = (long long)blockIdx.x * PR_THREADS + threadIdx.x; i < total;
+       i += (long long)gridDim.x * PR_THREADS) {
+    const long long g = i / n;
+    const int c = (int)(i - g * n);
+    const float sc = scale[c], sh = shift[c];
+    const long long base = (g * m) * n + c;
+    float best;
+    int bi;
+    if (sc >= 0.f) {
+      best = pmax[base]; bi = amax[base];
+      for (int j = 1; j < m; ++j) {
+        const float v = pmax[base + (long long)j * n];
+        if (v > best) { best = v; bi = j * u + amax[base + (long long)j * n]; }
+      }
+      if (sc == 0.f) bi = 0;            // every row ties
+    } else {
+      best = pmin[base]; bi = amin[base];
+      for (int j = 1; j < m; ++j) {
+        const float v = pmin[base + (long long)j * n];
+        if (v < best) { best = v; bi = j * u + amin[base + (long long)j * n]; }
+      }
+    }
+    const float z = fmaf(best, sc, sh);
+    out[i] = fmaxf(z, 0.f);
+    arg[i] = z > 0.f ? (unsigned char)bi : (unsigned char)255;
+  }
+}
+
 // One CTA = all n output channels x a slice of 64 input columns (blockIdx.y); thread t owns the 32
 // channels of block t >> 4 and the four columns (t & 15) * 4 of the slice, 32 x 4 sums in registers.  It
 // walks groups blockIdx.x, blockIdx.x + gridDim.x, ... and leaves ONE partial block per blockIdx.x.
@@ -383,6 +423,18 @@ extern "C" int nesie_pool_finalize(long long groups, int k, int u, int n, const 
   pool_finalize_kernel<<<pr_grid(groups * (n >> 2)), PR_THREADS, 0, (cudaStream_t)stream>>>(
       groups, k / u, u, n, pmax, amax, bias, out, arg);
   return check_launch("nesie_pool_finalize");
+}
+
+extern "C" int nesie_bn_pool_finalize(long long groups, int k, int u, int n, const float *pmax,
+                                      const unsigned char *amax, const float *pmin,
+                                      const unsigned char *amin, const float *stats, float *out,
+                                      unsigned char *arg, void *stream) {
+  NESIE_REQUIRE(groups >= 0 && u >= 1 && k >= u && k % u == 0 && k <= 254 && n >= 1, "need u | k, k <= 254, n >= 1");
+  if (groups == 0) return NESIE_OK;
+  NESIE_REQUIRE(pmax && amax && pmin && amin && stats && out && arg, "null pointer");
+  bn_pool_finalize_kernel<<<pr_grid(groups * n), PR_THREADS, 0, (cudaStream_t)stream>>>(
+      groups, k / u, u, n, pmax, amax, pmin, amin, stats, out, arg);
+  return check_launch("nesie_bn_pool_finalize");
 }
 
 extern "C" int nesie_pool_wgrad_parts(long long groups) { return groups <= 0 ? 0 : pw_grid_x(groups); }

@@ -214,6 +214,80 @@ class _BNReLULinear(Function):
         return d_y, None, d_gamma, d_beta, None, None, None, None, gw
 
 
+def _pool_unit(k):
+    """Rows per unit of the GEMM epilogue's pooling for groups of k rows (0: not available)."""
+    if k == 16:
+        return 16
+    return 32 if (k % 32 == 0 and 32 <= k <= 224) else 0
+
+
+def pooled_epilogue_enabled():
+    return os.environ.get("NESIE_POOL_FUSE", "1") != "0"
+
+
+class _BNReLULinearPooled(Function):
+    """Last layer of a pooled shared MLP: y = relu(bn_prev(y_prev)) @ w.T, then relu(bn(y)) max-pooled over
+    every k rows -- with the unit maxima / minima of y taken in the GEMM epilogue, so that y is written
+    (the backward needs it) but not read again in the forward (nesie_bn_pool_finalize).
+    Same gradients as _BNReLULinear followed by bn_rows._BNReLURows(k)."""
+
+    @staticmethod
+    def forward(ctx, y_prev, parts_prev, g0, b0, rm0, rv0, eps0, mom0, w, g1, b1, rm1, rv1, eps1, mom1, k):
+        stats0 = _bn_stats(y_prev, parts_prev, g0, b0, rm0, rv0, eps0, mom0)
+        R, K = y_prev.shape
+        N = w.shape[0]
+        dev = y_prev.device
+        u = _pool_unit(k)
+        y = torch.empty((R, N), dtype=torch.float32, device=dev)
+        parts = torch.empty((_lib.lib().nesie_gemm_stats_parts(R), 2, N), dtype=torch.float32, device=dev)
+        pmax = torch.empty((R // u, N), dtype=torch.float32, device=dev)
+        pmin = torch.empty((R // u, N), dtype=torch.float32, device=dev)
+        amax = torch.empty((R // u, N), dtype=torch.uint8, device=dev)
+        amin = torch.empty((R // u, N), dtype=torch.uint8, device=dev)
+        out = torch.empty((R // k, N), dtype=torch.float32, device=dev)
+        arg = torch.empty((R // k, N), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            img = _pack(w, N, K, K, 1)
+            _lib.call("nesie_gemm_nt_3xtf32_pool", R, N, K, _lib.ptr(y_prev), K, _lib.ptr(img), _lib.ptr(y), N,
+                      _lib.ptr(stats0[2]), _lib.ptr(stats0[3]), _lib.ptr(parts), u, _lib.ptr(pmax),
+                      _lib.ptr(amax), _lib.ptr(pmin), _lib.ptr(amin), None, 0, _lib.stream())
+        stats1 = _bn_stats(y, parts, g1, b1, rm1, rv1, eps1, mom1)
+        with torch.cuda.device(dev):
+            _lib.call("nesie_bn_pool_finalize", R // k, k, u, N, _lib.ptr(pmax), _lib.ptr(amax), _lib.ptr(pmin),
+                      _lib.ptr(amin), _lib.ptr(stats1), _lib.ptr(out), _lib.ptr(arg), _lib.stream())
+        ctx.save_for_backward(y_prev, stats0, w, y, stats1, arg)
+        ctx.k = k
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        y_prev, stats0, w, y, stats1, arg = ctx.saved_tensors
+        R, N = y.shape
+        C = y_prev.shape[1]
+        dev = y.device
+        d_out = d_out.contiguous()
+        # BatchNorm + ReLU + max-pool backward of this layer (bn_rows._BNReLURows.backward)
+        gy = torch.empty_like(y)
+        d_g1 = torch.empty((N,), dtype=torch.float32, device=dev)
+        d_b1 = torch.empty((N,), dtype=torch.float32, device=dev)
+        ws = torch.empty((_lib.lib().nesie_bn_rows_workspace_bytes(max(N, C)),), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.call("nesie_bn_relu_rows_backward", R, N, ctx.k, _lib.ptr(y), _lib.ptr(d_out), _lib.ptr(arg),
+                      _lib.ptr(stats1), _lib.ptr(gy), _lib.ptr(d_g1), _lib.ptr(d_b1), _lib.ptr(ws), _lib.stream())
+            _lib.LAUNCHES += 2
+        # ... and of the GEMM with the previous layer's BatchNorm + ReLU in its prologue (_BNReLULinear.backward)
+        gw = _wgrad_fused(gy, y_prev, stats0[2], stats0[3]) if ctx.needs_input_grad[8] else None
+        g_act = gemm_nt(gy, w, transpose_w=True)
+        d_y = torch.empty_like(y_prev)
+        d_g0 = torch.empty((C,), dtype=torch.float32, device=dev)
+        d_b0 = torch.empty((C,), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.call("nesie_bn_relu_rows_backward", R, C, 0, _lib.ptr(y_prev), _lib.ptr(g_act), None,
+                      _lib.ptr(stats0), _lib.ptr(d_y), _lib.ptr(d_g0), _lib.ptr(d_b0), _lib.ptr(ws), _lib.stream())
+            _lib.LAUNCHES += 2
+        return (d_y, None, d_g0, d_b0, None, None, None, None, gw, d_g1, d_b1, None, None, None, None, None)
+
+
 def _bn_buffers(bn):
     if bn.track_running_stats:
         bn_rows.count_batch(bn)
@@ -249,7 +323,17 @@ def supported_tail(layers):
 
 def mlp_rows_tail(y, parts, layers, pool_k=0):
     """mlp_rows from the first layer's pre-activation y = x @ W1^T and its column-sum partials on."""
-    for li in range(1, len(layers)):
+    nl = len(layers)
+    fuse_pool = (nl >= 2 and pool_k > 0 and pooled_epilogue_enabled() and _pool_unit(pool_k) > 0 and
+                 y.shape[0] % pool_k == 0 and pool_k <= 254)
+    for li in range(1, nl):
+        if fuse_pool and li == nl - 1:
+            bn0, bn1 = layers[li - 1][1], layers[li][1]
+            rm0, rv0 = _bn_buffers(bn0)
+            rm1, rv1 = _bn_buffers(bn1)
+            return _BNReLULinearPooled.apply(y, parts, bn0.weight, bn0.bias, rm0, rv0, bn0.eps, bn0.momentum,
+                                             layers[li][0], bn1.weight, bn1.bias, rm1, rv1, bn1.eps,
+                                             bn1.momentum, pool_k)
         bn = layers[li - 1][1]
         rm, rv = _bn_buffers(bn)
         y, parts = _BNReLULinear.apply(y, parts, bn.weight, bn.bias, rm, rv, bn.eps, bn.momentum,

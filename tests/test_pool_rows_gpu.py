@@ -275,3 +275,33 @@ def test_sa_module_commuted_first_layer_equals_grouped_rows(monkeypatch):
     for (name, _), a, b in zip(sa.named_parameters(), p1, p0):
         err = float((a - b).norm())
         assert err < 5e-3 * float(b.norm()) or err < 1e-5 * top, (name, err, float(b.norm()))
+
+
+@pytest.mark.parametrize("k,neg", [(16, False), (32, True), (64, False)])
+def test_sa_pooled_last_layer_from_gemm_epilogue(k, neg, monkeypatch):
+    """BatchNorm + ReLU + max-pool of an SA level from the GEMM epilogue's unit maxima / minima
+    (negative BatchNorm weights exercise the minimum) against the kernel that re-reads the pre-activation."""
+    from nesie_b200.pointnet_modules import PointSAModule
+    torch.manual_seed(k)
+    sa = PointSAModule(num_point=48, radius=0.5, num_sample=k, mlp_channels=[32, 64, 64, 128],
+                       use_xyz=True, normalize_xyz=True).cuda()
+    if neg:
+        with torch.no_grad():
+            for m in sa.modules():
+                if isinstance(m, torch.nn.BatchNorm2d):
+                    m.weight.copy_(torch.randn_like(m.weight))
+    xyz = torch.rand(2, 600, 3, device="cuda")
+    feats = torch.randn(2, 32, 600, device="cuda", requires_grad=True)
+    res = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("NESIE_POOL_FUSE", flag)
+        sa.zero_grad()
+        feats.grad = None
+        _, out, _ = sa(xyz, feats)
+        (out * out).sum().backward()
+        res.append((out.detach().clone(), feats.grad.clone(), [p.grad.clone() for p in sa.parameters()]))
+    (o1, f1, p1), (o0, f0, p0) = res
+    assert torch.equal(o1, o0)                      # same GEMM, same statistics, max of a monotone map
+    assert (f1 - f0).norm() < 1e-4 * f0.norm()
+    for a, b in zip(p1, p0):
+        assert (a - b).norm() <= 1e-4 * b.norm() + 1e-7
