@@ -56,9 +56,10 @@ WORKLOADS = {
                    name="saqe_stress_fwd_bwd_adamw_b16_per_gpu_100kpts_4096seeds"),
 }
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of gemm_nt_tma_kernel at its largest
-# HBM-bound shape (SA1 layer 3, 1048576 x 64 -> 128, 805.3 MB algorithmic), ncu --set full capture
-# summarised in profiles/r01_ncu_notes.md; the tensor-bound SidePooling shape is in r02_ncu_notes.md
-GEMM_DRAM_TRAFFIC = 749.8e6
+# HBM-bound shape (SA1 layer 3, 1048576 x 64 -> 128, 805.3 MB algorithmic + 8.4 MB of pooled extrema):
+# 268.6 MB read + 521.2 MB written in the end-of-round ncu --set full capture (profiles/r02_ncu_notes.md;
+# 749.8 MB in round 1's): no re-reads, the tail of the output is still in L2 when the kernel ends
+GEMM_DRAM_TRAFFIC = 789.7e6
 
 
 def peaks():
