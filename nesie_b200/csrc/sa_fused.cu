@@ -165,17 +165,23 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 __device__ __forceinline__ void mbar_arrive(unsigned mbar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
 }
+// The wait is part of the same asm statement as the load: the destination registers are only valid
+// after it, and the compiler may move or spill the outputs of an asm statement as soon as it ends (seen
+// in gemm_tma.cuh once other code sat between a load and its wait: stale accumulator values).  The
+// price is that the two loads of a 64-column epilogue no longer overlap.
 __device__ __forceinline__ void tmem_ld32_issue(unsigned taddr, unsigned (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
         "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
         "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
         "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
         "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
+      : "r"(taddr)
+      : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -186,7 +192,7 @@ constexpr int NGATHER = 128;   // warps 8-11: build the next tile's A operand
 
 // Layer-1/2 epilogue: `ncols` (32 or 64) accumulator columns starting at col0 of this thread's row
 // -> + bias (shared memory, broadcast) -> ReLU -> bf16 -> the next layer's A operand in shared
-// memory (BN scale is folded into W).  Both x32 TMEM loads are in flight before the single wait.
+// memory (BN scale is folded into W).
 __device__ __forceinline__ void epilogue_to_operand(unsigned d_tmem, int q, int col0, int ncols,
                                                     const float *s_bias, unsigned char *dst,
                                                     int row) {
