@@ -47,13 +47,6 @@ def pool_unit(k):
     return 32 if (k % 32 == 0 and 32 <= k <= 224) else 0
 
 
-def supported(x, w_a, bn, w_b, k):
-    """rows x -> conv_a -> bn -> relu -> conv_b (-> max over k rows) on the pooled GEMM path."""
-    return (enabled() and pool_unit(k) > 0 and x.shape[0] % k == 0 and (k & (k - 1)) == 0 and
-            mlp_rows.supported(x, [(w_a, bn)]) and w_b.shape[0] % 4 == 0 and 4 <= w_b.shape[0] <= 256 and
-            w_b.shape[1] % 4 == 0 and w_b.shape[1] <= 256)
-
-
 def _gemm_pool(x, img, N, scale, shift, want_stats, store, pool_k, grp_bias=None, grp_k=0):
     """x (R, K) [relu(x * scale + shift)] @ W^T with W's packed image `img` -> (y | None, column-sum
     partials | None, unit maxima | None, their rows | None)."""
